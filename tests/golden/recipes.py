@@ -1,0 +1,78 @@
+"""Seeded input recipes shared by the golden generator and the tests.
+
+Everything is produced by CPU ``torch.Generator`` streams, which are
+bit-identical on every machine with the same torch build, so only the
+*outputs* of the reference need to be committed as fixtures.
+"""
+import torch
+
+
+def model_input(seed, b, h, w):
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(b, 3, h, w, generator=g)
+
+
+def targets(seed, b, nt):
+    """SURVEY 8(d) recipe: [img, cls, x, y, w, h] normalised."""
+    g = torch.Generator().manual_seed(seed)
+    if nt == 0:
+        return torch.zeros(0, 6)
+    return torch.cat([
+        torch.randint(0, b, (nt, 1), generator=g).float(),
+        torch.randint(0, 80, (nt, 1), generator=g).float(),
+        torch.rand(nt, 2, generator=g),
+        torch.rand(nt, 2, generator=g) * 0.5 + 0.005,
+    ], 1)
+
+
+def edge_targets(b=2):
+    """G4: boxes on cell boundaries, within one cell of the border, and with
+    w/h ratios exactly at the anchor_t=4 threshold (anchor (1.25,1.625) at P3/80)."""
+    rows = [
+        [0, 1, 0.5, 0.5, 0.1, 0.1],            # x*W integral at every level
+        [0, 2, 1.0 / 80, 1.0 / 80, 0.05, 0.05],  # gxy == 1 at P3 (not > 1)
+        [1, 3, 0.999, 0.999, 0.2, 0.3],        # last cell
+        [1, 4, 0.0, 0.0, 0.3, 0.2],            # first cell, offsets would go negative
+        [0, 5, 0.25, 0.75, 4 * 1.25 / 80, 4 * 1.625 / 80],   # ratio == 4 exactly (fails <)
+        [1, 6, 0.25, 0.75, 1.25 / 80 / 4, 1.625 / 80 / 4],   # ratio == 1/4 exactly
+        [0, 7, 0.50625, 0.49375, 0.15, 0.15],  # frac 0.5 boundary at P3: 40.5 / 39.5
+        [1, 79, 0.3, 0.6, 0.9, 0.9],           # huge box, matches only P5 anchors
+        [0, 0, 0.3, 0.6, 0.001, 0.001],        # tiny box, matches nothing
+        [0, 9, 0.3, 0.6, 0.1, 0.1],
+        [0, 10, 0.3, 0.6, 0.1, 0.1],           # duplicate cell (last write wins in tobj)
+    ]
+    t = torch.tensor(rows, dtype=torch.float32)
+    t[:, 0] = t[:, 0].clamp(max=b - 1)
+    return t
+
+
+def head_outputs(seed, b, h, w, nc=80, scale=1.0):
+    """Random stand-ins for the three head tensors (B,3,H/s,W/s,5+nc)."""
+    g = torch.Generator().manual_seed(seed)
+    return [torch.randn(b, 3, h // s, w // s, 5 + nc, generator=g) * scale for s in (8, 16, 32)]
+
+
+def nms_boxes(seed, b, n, mode="realistic", size=640.0):
+    """(B,N,6) [cls, score, cx, cy, w, h] decoded boxes (SURVEY 8(d) config 5 recipe).
+    modes: realistic (score = sigmoid(N(-5,2))), allpass (sigma ~ 0.5), ties (quantised
+    scores => many exact ties), clustered (heavy overlap)."""
+    g = torch.Generator().manual_seed(seed)
+    cls = torch.randint(0, 80, (b, n, 1), generator=g).float()
+    if mode == "realistic":
+        score = torch.sigmoid(torch.randn(b, n, 1, generator=g) * 2 - 5)
+    elif mode == "allpass":
+        score = torch.sigmoid(torch.randn(b, n, 1, generator=g) * 0.02)
+    elif mode == "ties":
+        score = torch.round(torch.rand(b, n, 1, generator=g) * 20) / 20
+    elif mode == "clustered":
+        score = torch.rand(b, n, 1, generator=g)
+    else:
+        raise ValueError(mode)
+    if mode == "clustered":
+        cxy = 0.5 * size + torch.randn(b, n, 2, generator=g) * 20
+        wh = 60 + torch.rand(b, n, 2, generator=g) * 20
+        cls = torch.randint(0, 3, (b, n, 1), generator=g).float()
+    else:
+        cxy = torch.rand(b, n, 2, generator=g) * size
+        wh = torch.exp(torch.randn(b, n, 2, generator=g) * 0.8 + 4)
+    return torch.cat([cls, score, cxy, wh], -1)
