@@ -1,0 +1,525 @@
+// Implicit-GEMM convolution on tcgen05 + TMA (sm_100a).  See conv_igemm.cuh.
+//
+// Replaces, for the reference's hot path, every nn.Conv2d fprop/dgrad that cuDNN would run
+// (reference model.py:16 CBL conv, model.py:162 head conv; autograd dgrad of the same).
+//
+// CTA = 256 threads, one CTA per SM, persistent over output tiles:
+//   warp 0      TMA producer   (one elected lane): A = shifted NHWC patch [128 px x KC ch], B = weights [BLOCK_N x KC]
+//   warp 1      MMA issuer     (one elected lane): tcgen05.mma kind::f16, M=128, N=BLOCK_N, K=16, fp32 accum in TMEM
+//   warp 2      TMEM allocator (512 columns = 2 accumulator buffers of <=256 columns)
+//   warps 4..7  epilogue       TMEM -> registers -> (BN batch-stat partials) -> scale/shift/SiLU/residual -> global
+// Pipelines: smem ring full/empty mbarriers (TMA <-> MMA), TMEM full/empty mbarriers (MMA <-> epilogue).
+#include "conv_igemm.cuh"
+
+#include <algorithm>
+#include <cstring>
+
+namespace yb {
+
+static constexpr int kThreads = 256;
+static constexpr int kMaxStages = 12;
+static constexpr int kBarRegion = 1024;
+
+struct TileCoord {
+  int g, nb, hb, wb, nt;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int t) {
+  TileCoord c;
+  c.nt = t % p.tiles_c;
+  int m = t / p.tiles_c;
+  c.wb = m % p.tiles_w;
+  m /= p.tiles_w;
+  c.hb = m % p.tiles_h;
+  m /= p.tiles_h;
+  c.nb = m % p.tiles_n;
+  c.g = m / p.tiles_n;
+  return c;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tfull_bar = empty_bar + kMaxStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint8_t* a_smem = smem + kBarRegion;
+  uint8_t* b_smem = a_smem + (size_t)p.stages * p.a_stage_bytes;
+  float* s_stats = reinterpret_cast<float*>(b_smem + (size_t)p.stages * p.b_stage_bytes);  // [4][2][Cout]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.ngroups * p.tiles_n * p.tiles_h * p.tiles_w * p.tiles_c;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmB);
+    for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.tmA[i]);
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  if (p.stats != nullptr && warp >= 4) {
+    for (int i = threadIdx.x - 128; i < 4 * 2 * p.Cout; i += 128) s_stats[i] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(p, t);
+        const ConvGroup& grp = p.groups[tc.g];
+        const int w0 = tc.wb * p.PW, h0 = tc.hb * p.PH, n0 = tc.nb * p.PN, c0 = tc.nt * p.BLOCK_N;
+        for (int tp = grp.tap_begin; tp < grp.tap_end; ++tp) {
+          const ConvTap tap = p.taps[tp];
+          for (int ch = 0; ch < p.chunks; ++ch) {
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            mbar_expect_tx(&full_bar[s], p.a_tx_bytes + p.b_tx_bytes);
+            tma_load_4d(&p.tmA[tap.map], &full_bar[s], a_smem + (size_t)s * p.a_stage_bytes, ch * p.KC, w0 + tap.dw,
+                        h0 + tap.dh, n0);
+            tma_load_2d(&p.tmB, &full_bar[s], b_smem + (size_t)s * p.b_stage_bytes, tap.kbase + ch * p.KC, c0);
+            if (++s == p.stages) {
+              s = 0;
+              ph ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, p.BLOCK_N, 0, 0);
+      const uint32_t row_bytes = 2u * p.KC;
+      const uint32_t lt = swizzle_layout_type(row_bytes);
+      const uint32_t sbo = 8u * row_bytes;
+      const int kinner = p.KC / 16;
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        const TileCoord tc = decode_tile(p, t);
+        const ConvGroup& grp = p.groups[tc.g];
+        const int nk = (grp.tap_end - grp.tap_begin) * p.chunks;
+        const int ab = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[ab], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + ab * 256;
+        for (int ks = 0; ks < nk; ++ks) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(a_smem + (size_t)s * p.a_stage_bytes);
+          const uint32_t b_addr = smem_u32(b_smem + (size_t)s * p.b_stage_bytes);
+          for (int k = 0; k < kinner; ++k) {
+            const uint64_t da = make_smem_desc(a_addr + k * 32, 16, sbo, lt);
+            const uint64_t db = make_smem_desc(b_addr + k * 32, 16, sbo, lt);
+            umma_bf16(d_tmem, da, db, idesc, (ks | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+          if (++s == p.stages) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[ab]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;
+    const int pn = r / (p.PH * p.PW);
+    const int phh = (r / p.PW) % p.PH;
+    const int pw = r % p.PW;
+    float* my_stats = s_stats + (size_t)q * 2 * p.Cout;
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const TileCoord tc = decode_tile(p, t);
+      const int n = tc.nb * p.PN + pn, h = tc.hb * p.PH + phh, w = tc.wb * p.PW + pw;
+      const bool valid = (r < p.PW * p.PH * p.PN) && n < p.NB && h < p.H && w < p.W;
+      const int64_t opix = p.groups[tc.g].out_off + n * p.os_n + h * p.os_h + w * p.os_w;
+      const int64_t apix = n * p.as_n + h * p.as_h + w * p.as_w;
+      const int ab = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      mbar_wait(&tfull_bar[ab], aph);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 256;
+      const int nchunks = p.BLOCK_N / 16;
+      for (int cc = 0; cc < nchunks; ++cc) {
+        const int col0 = tc.nt * p.BLOCK_N + cc * 16;
+        if (col0 >= p.Cout) break;
+        uint32_t vr[16];
+        tmem_ld16(t_addr + cc * 16, vr);
+        tmem_ld_wait();
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(vr[j]);
+
+        if (p.stats != nullptr) {
+          // per-column sum / sum-of-squares over the 32 rows of this warp: butterfly transpose-reduce
+          float a8[8], b8[8];
+          const bool u16 = lane & 16;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float lo = valid ? v[j] : 0.f, hi = valid ? v[j + 8] : 0.f;
+            const float keep = u16 ? hi : lo, send = u16 ? lo : hi;
+            const float rs = __shfl_xor_sync(0xffffffffu, send, 16);
+            const float rq = __shfl_xor_sync(0xffffffffu, send * send, 16);
+            a8[j] = keep + rs;
+            b8[j] = keep * keep + rq;
+          }
+          float a4[4], b4[4];
+          const bool u8 = lane & 8;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float ka = u8 ? a8[j + 4] : a8[j], sa = u8 ? a8[j] : a8[j + 4];
+            const float kb = u8 ? b8[j + 4] : b8[j], sb = u8 ? b8[j] : b8[j + 4];
+            a4[j] = ka + __shfl_xor_sync(0xffffffffu, sa, 8);
+            b4[j] = kb + __shfl_xor_sync(0xffffffffu, sb, 8);
+          }
+          float a2[2], b2[2];
+          const bool u4 = lane & 4;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const float ka = u4 ? a4[j + 2] : a4[j], sa = u4 ? a4[j] : a4[j + 2];
+            const float kb = u4 ? b4[j + 2] : b4[j], sb = u4 ? b4[j] : b4[j + 2];
+            a2[j] = ka + __shfl_xor_sync(0xffffffffu, sa, 4);
+            b2[j] = kb + __shfl_xor_sync(0xffffffffu, sb, 4);
+          }
+          const bool u2 = lane & 2;
+          float a1 = (u2 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, u2 ? a2[0] : a2[1], 2);
+          float b1 = (u2 ? b2[1] : b2[0]) + __shfl_xor_sync(0xffffffffu, u2 ? b2[0] : b2[1], 2);
+          a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+          b1 += __shfl_xor_sync(0xffffffffu, b1, 1);
+          // lane l now holds column ((l>>4)&1)*8 + ((l>>3)&1)*4 + ((l>>2)&1)*2 + ((l>>1)&1)
+          if ((lane & 1) == 0) {
+            const int cj = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+            const int col = col0 + cj;
+            if (col < p.Cout) {
+              my_stats[col] += a1;
+              my_stats[p.Cout + col] += b1;
+            }
+          }
+        }
+
+        if (valid) {
+          if (p.scale != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (col0 + j < p.Cout) v[j] = fmaf(v[j], __ldg(p.scale + col0 + j), __ldg(p.shift + col0 + j));
+          } else if (p.shift != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (col0 + j < p.Cout) v[j] += __ldg(p.shift + col0 + j);
+          }
+          if (p.act) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = silu_f(v[j]);
+          }
+          if (p.addend != nullptr) {
+            const uint4* ap = reinterpret_cast<const uint4*>(p.addend + apix + col0);
+            uint4 r0 = __ldg(ap), r1 = __ldg(ap + 1);
+            const bf16* e0 = reinterpret_cast<const bf16*>(&r0);
+            const bf16* e1 = reinterpret_cast<const bf16*>(&r1);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              v[j] += __bfloat162float(e0[j]);
+              v[8 + j] += __bfloat162float(e1[j]);
+            }
+          }
+          if (p.out_kind == OUT_BF16) {
+            uint4 o0, o1;
+            __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+            __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              h0[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+              h1[j] = __floats2bfloat162_rn(v[8 + 2 * j], v[8 + 2 * j + 1]);
+            }
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + opix + col0);
+            op[0] = o0;
+            op[1] = o1;
+          } else if (p.out_kind == OUT_F32) {
+            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + opix + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {  // OUT_HEAD_F32
+            float* ob = reinterpret_cast<float*>(p.out);
+            const int64_t hw = (int64_t)p.H * p.W;
+            const int64_t pix = (int64_t)h * p.W + w;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int col = col0 + j;
+              if (col < p.Cout) {
+                const int a = col / p.head_no, o = col - a * p.head_no;
+                ob[(((int64_t)n * p.head_na + a) * hw + pix) * p.head_no + o] = v[j];
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[ab]);
+    }
+    if (p.stats != nullptr) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      float* dst = p.stats + (size_t)blockIdx.x * 2 * p.Cout;
+      for (int i = threadIdx.x - 128; i < 2 * p.Cout; i += 128) {
+        dst[i] = ((s_stats[i] + s_stats[2 * p.Cout + i]) + s_stats[4 * p.Cout + i]) + s_stats[6 * p.Cout + i];
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+static int g_num_sms = 0;
+int conv_max_grid() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_num_sms <= 0)
+      g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+static void choose_patch(int W, int H, int NB, int& PW, int& PH, int& PN) {
+  long best = -1;
+  for (int pw = 1; pw <= std::min(W, 128); ++pw) {
+    for (int ph = 1; ph <= std::min(H, 128 / pw); ++ph) {
+      const int pn = std::max(1, std::min(NB, 128 / (pw * ph)));
+      const long tiles = (long)((W + pw - 1) / pw) * ((H + ph - 1) / ph) * ((NB + pn - 1) / pn);
+      // fewer tiles first; then prefer wide patches (longer contiguous runs per TMA row)
+      const long score = tiles * 1024 - pw;
+      if (best < 0 || score < best) {
+        best = score;
+        PW = pw;
+        PH = ph;
+        PN = pn;
+      }
+    }
+  }
+}
+
+static int pick_kc(int C) { return (C % 64 == 0) ? 64 : (C % 32 == 0 ? 32 : 16); }
+
+static int pick_block_n(int Cout) {
+  const int c16 = (Cout + 15) / 16 * 16;
+  if (c16 <= 256) return c16;
+  const int parts = (c16 + 255) / 256;
+  return ((c16 + parts - 1) / parts + 15) / 16 * 16;
+}
+
+// A tensor map over (a parity sub-grid of) an NHWC view: dims (C, W/sx, H/sy, N).
+static int make_a_map(CUtensorMap* m, const TView& v, int KC, int PW, int PH, int PN, int py, int px, int sy, int sx) {
+  const bf16* base = reinterpret_cast<const bf16*>(v.ptr) + ((long)py * v.W + px) * v.pitch;
+  uint64_t dims[4] = {(uint64_t)v.C, (uint64_t)(v.W / sx), (uint64_t)(v.H / sy), (uint64_t)v.N};
+  uint64_t strides[3] = {(uint64_t)v.pitch * sx * 2, (uint64_t)v.pitch * v.W * sy * 2,
+                         (uint64_t)v.pitch * v.W * v.H * 2};
+  uint32_t box[4] = {(uint32_t)KC, (uint32_t)PW, (uint32_t)PH, (uint32_t)PN};
+  return encode_tmap(m, base, 4, dims, strides, box, 2 * KC, 2);
+}
+
+static int finish_plan(ConvPlan& pl, const bf16* wmat, int wrows, long wcols, const TView& out,
+                       const ConvEpilogue& ep) {
+  ConvKParams& kp = pl.kp;
+  kp.Cout = wrows;
+  kp.BLOCK_N = pick_block_n(wrows);
+  kp.tiles_c = (wrows + kp.BLOCK_N - 1) / kp.BLOCK_N;
+  {
+    uint64_t dims[2] = {(uint64_t)wcols, (uint64_t)wrows};
+    uint64_t strides[1] = {(uint64_t)wcols * 2};
+    uint32_t box[2] = {(uint32_t)kp.KC, (uint32_t)kp.BLOCK_N};
+    if (encode_tmap(&kp.tmB, wmat, 2, dims, strides, box, 2 * kp.KC, 2)) return -1;
+  }
+  kp.tiles_w = (kp.W + kp.PW - 1) / kp.PW;
+  kp.tiles_h = (kp.H + kp.PH - 1) / kp.PH;
+  kp.tiles_n = (kp.NB + kp.PN - 1) / kp.PN;
+  kp.a_stage_bytes = 128u * 2u * kp.KC;
+  kp.b_stage_bytes = ((uint32_t)kp.BLOCK_N * 2u * kp.KC + 1023u) & ~1023u;
+  kp.a_tx_bytes = (uint32_t)(kp.PW * kp.PH * kp.PN) * 2u * kp.KC;
+  kp.b_tx_bytes = (uint32_t)kp.BLOCK_N * 2u * kp.KC;
+  kp.out_kind = ep.out_kind;
+  kp.out = out.ptr;
+  kp.scale = ep.scale;
+  kp.shift = ep.shift;
+  kp.act = ep.act;
+  kp.addend = ep.addend;
+  kp.stats = ep.stats;
+  kp.head_na = ep.head_na;
+  kp.head_no = ep.head_no;
+  YB_REQUIRE(ep.out_kind == OUT_HEAD_F32 || wrows % 16 == 0, "conv: Cout=%d must be a multiple of 16", wrows);
+  YB_REQUIRE(ep.scale == nullptr || ep.shift != nullptr, "conv: scale without shift");
+  const size_t stats_bytes = ep.stats ? (size_t)4 * 2 * wrows * sizeof(float) : 0;
+  const size_t budget = 227 * 1024 - 1024 /*align slack*/ - kBarRegion - stats_bytes;
+  int stages = (int)(budget / (kp.a_stage_bytes + kp.b_stage_bytes));
+  stages = std::min(stages, kMaxStages);
+  YB_REQUIRE(stages >= 2, "conv: tile does not fit in shared memory");
+  kp.stages = stages;
+  pl.smem = (int)(1024 + kBarRegion + (size_t)stages * (kp.a_stage_bytes + kp.b_stage_bytes) + stats_bytes);
+  pl.smem = std::max(pl.smem, 120 * 1024);  // one CTA per SM: each CTA allocates all 512 TMEM columns
+  for (int g = 0; g < kp.ngroups; ++g)
+    YB_REQUIRE(kp.groups[g].tap_end > kp.groups[g].tap_begin, "conv: output group %d has no taps", g);
+  const long total = (long)kp.ngroups * kp.tiles_n * kp.tiles_h * kp.tiles_w * kp.tiles_c;
+  pl.grid = (int)std::min<long>(total, conv_max_grid());
+  return 0;
+}
+
+int conv_plan_fwd(ConvPlan& pl, const TView& in, const bf16* wp, int ks, int stride, const TView& out,
+                  const ConvEpilogue& ep) {
+  memset(&pl, 0, sizeof(pl));
+  ConvKParams& kp = pl.kp;
+  YB_REQUIRE((ks == 1 || ks == 3) && (stride == 1 || stride == 2), "conv fwd: ks=%d stride=%d unsupported", ks, stride);
+  YB_REQUIRE(in.C % 16 == 0 && in.pitch % 8 == 0 && (ep.out_kind != OUT_BF16 || out.pitch % 8 == 0),
+             "conv fwd: channel alignment");
+  YB_REQUIRE(in.H % stride == 0 && in.W % stride == 0, "conv fwd: odd input for stride 2");
+  YB_REQUIRE(out.H == in.H / stride && out.W == in.W / stride && out.N == in.N, "conv fwd: geometry");
+  kp.KC = pick_kc(in.C);
+  kp.chunks = in.C / kp.KC;
+  kp.W = out.W;
+  kp.H = out.H;
+  kp.NB = out.N;
+  choose_patch(kp.W, kp.H, kp.NB, kp.PW, kp.PH, kp.PN);
+  const int pad = ks / 2;
+  int nt = 0;
+  if (stride == 1) {
+    if (make_a_map(&kp.tmA[0], in, kp.KC, kp.PW, kp.PH, kp.PN, 0, 0, 1, 1)) return -1;
+    for (int i = 1; i < 4; ++i) kp.tmA[i] = kp.tmA[0];
+    for (int kh = 0; kh < ks; ++kh)
+      for (int kw = 0; kw < ks; ++kw) {
+        kp.taps[nt] = ConvTap{0, (int8_t)(kw - pad), (int8_t)(kh - pad), 0, (int32_t)((kh * ks + kw) * in.C)};
+        ++nt;
+      }
+  } else {
+    // input row 2*ho + kh - 1 :  kh=0 -> parity 1, block ho-1 ; kh=1 -> parity 0, block ho ; kh=2 -> parity 1, block ho
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px)
+        if (make_a_map(&kp.tmA[py * 2 + px], in, kp.KC, kp.PW, kp.PH, kp.PN, py, px, 2, 2)) return -1;
+    for (int kh = 0; kh < ks; ++kh)
+      for (int kw = 0; kw < ks; ++kw) {
+        const int oy = kh - pad, ox = kw - pad;  // input offset relative to 2*ho
+        const int py = oy & 1, px = ox & 1;
+        const int dh = (oy - py) / 2, dw = (ox - px) / 2;
+        kp.taps[nt] = ConvTap{(int8_t)(py * 2 + px), (int8_t)dw, (int8_t)dh, 0, (int32_t)((kh * ks + kw) * in.C)};
+        ++nt;
+      }
+  }
+  kp.ngroups = 1;
+  kp.groups[0] = ConvGroup{0, nt, 0};
+  kp.os_n = (int64_t)out.pitch * out.W * out.H;
+  kp.os_h = (int64_t)out.pitch * out.W;
+  kp.os_w = out.pitch;
+  if (ep.addend) {
+    kp.as_n = (int64_t)ep.addend_pitch * out.W * out.H;
+    kp.as_h = (int64_t)ep.addend_pitch * out.W;
+    kp.as_w = ep.addend_pitch;
+  }
+  return finish_plan(pl, wp, out.C, (long)ks * ks * in.C, out, ep);
+}
+
+int conv_plan_dgrad(ConvPlan& pl, const TView& dy, const bf16* wt, int ks, int stride, const TView& dx,
+                    const ConvEpilogue& ep) {
+  memset(&pl, 0, sizeof(pl));
+  ConvKParams& kp = pl.kp;
+  YB_REQUIRE((ks == 1 || ks == 3) && (stride == 1 || stride == 2), "conv dgrad: ks=%d stride=%d unsupported", ks,
+             stride);
+  YB_REQUIRE(dy.C % 16 == 0 && dy.pitch % 8 == 0 && dx.pitch % 8 == 0, "conv dgrad: channel alignment");
+  YB_REQUIRE(dy.H == dx.H / stride && dy.W == dx.W / stride && dy.N == dx.N, "conv dgrad: geometry");
+  kp.KC = pick_kc(dy.C);
+  kp.chunks = dy.C / kp.KC;
+  kp.NB = dx.N;
+  const int pad = ks / 2;
+  int nt = 0;
+  if (stride == 1) {
+    kp.W = dx.W;
+    kp.H = dx.H;
+    choose_patch(kp.W, kp.H, kp.NB, kp.PW, kp.PH, kp.PN);
+    if (make_a_map(&kp.tmA[0], dy, kp.KC, kp.PW, kp.PH, kp.PN, 0, 0, 1, 1)) return -1;
+    for (int i = 1; i < 4; ++i) kp.tmA[i] = kp.tmA[0];
+    // dx[h,w] = sum_{kh,kw} dy[h + pad - kh, w + pad - kw] * W[:, :, kh, kw]
+    for (int kh = 0; kh < ks; ++kh)
+      for (int kw = 0; kw < ks; ++kw) {
+        kp.taps[nt] = ConvTap{0, (int8_t)(pad - kw), (int8_t)(pad - kh), 0, (int32_t)((kh * ks + kw) * dy.C)};
+        ++nt;
+      }
+    kp.ngroups = 1;
+    kp.groups[0] = ConvGroup{0, nt, 0};
+    kp.os_n = (int64_t)dx.pitch * dx.W * dx.H;
+    kp.os_h = (int64_t)dx.pitch * dx.W;
+    kp.os_w = dx.pitch;
+  } else {
+    // output parity classes: dx[2*hb+py, 2*wb+px]; contributing kh satisfy (2*hb+py+pad-kh) even, ho = that / 2.
+    kp.W = dx.W / 2;
+    kp.H = dx.H / 2;
+    choose_patch(kp.W, kp.H, kp.NB, kp.PW, kp.PH, kp.PN);
+    if (make_a_map(&kp.tmA[0], dy, kp.KC, kp.PW, kp.PH, kp.PN, 0, 0, 1, 1)) return -1;
+    for (int i = 1; i < 4; ++i) kp.tmA[i] = kp.tmA[0];
+    kp.ngroups = 4;
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        const int g = py * 2 + px;
+        kp.groups[g].tap_begin = nt;
+        for (int kh = 0; kh < ks; ++kh) {
+          if (((py + pad - kh) & 1) != 0) continue;
+          for (int kw = 0; kw < ks; ++kw) {
+            if (((px + pad - kw) & 1) != 0) continue;
+            const int dh = (py + pad - kh) / 2, dw = (px + pad - kw) / 2;  // exact: numerators are even
+            kp.taps[nt] = ConvTap{0, (int8_t)dw, (int8_t)dh, 0, (int32_t)((kh * ks + kw) * dy.C)};
+            ++nt;
+          }
+        }
+        kp.groups[g].tap_end = nt;
+        kp.groups[g].out_off = ((int64_t)py * dx.W + px) * dx.pitch;
+      }
+    kp.os_n = (int64_t)dx.pitch * dx.W * dx.H;
+    kp.os_h = (int64_t)dx.pitch * dx.W * 2;
+    kp.os_w = dx.pitch * 2;
+  }
+  if (ep.addend) {
+    YB_REQUIRE(stride == 1, "conv dgrad: addend only for stride 1");
+    kp.as_n = (int64_t)ep.addend_pitch * dx.W * dx.H;
+    kp.as_h = (int64_t)ep.addend_pitch * dx.W;
+    kp.as_w = ep.addend_pitch;
+  }
+  return finish_plan(pl, wt, dx.C, (long)ks * ks * dy.C, dx, ep);
+}
+
+int conv_stats_rows(const ConvPlan& pl) { return pl.grid; }
+
+int conv_run(const ConvPlan& pl, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  conv_igemm_kernel<<<pl.grid, kThreads, pl.smem, st>>>(pl.kp);
+  YB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace yb

@@ -1,0 +1,87 @@
+// Implicit-GEMM convolution on tcgen05 (sm_100a): shared declarations.
+//
+// One persistent, warp-specialised kernel covers
+//   * forward conv 1x1 / 3x3, stride 1 or 2 (stride 2 through four input-parity tensor maps),
+//   * the 6x6/s2 stem as a 3x3/s1 conv over the space-to-depth input,
+//   * data-gradient (dgrad) of all of the above (stride-2 dgrad = four output-parity groups),
+// as "sum over taps of shifted NHWC tiles x K-major weight slices".
+#pragma once
+#include "common.cuh"
+
+namespace yb {
+
+// NHWC bf16 view of (a channel slice of) a tensor.  pitch = elements between consecutive pixels.
+struct TView {
+  void* ptr;   // points at channel 0 of the slice of pixel (0,0,0)
+  int N, H, W, C;
+  long pitch;  // elements per pixel of the underlying buffer (>= C)
+};
+
+struct ConvTap {
+  int8_t map;  // which A tensor map (input parity for stride 2)
+  int8_t dw, dh;
+  int8_t pad;
+  int32_t kbase;  // first column of this tap inside the B (weight) matrix
+};
+
+struct ConvGroup {
+  int32_t tap_begin, tap_end;
+  int64_t out_off;  // element offset of this group's (0,0,0) output pixel
+};
+
+enum { OUT_BF16 = 0, OUT_HEAD_F32 = 1, OUT_F32 = 2 };
+
+struct ConvKParams {
+  CUtensorMap tmA[4];
+  CUtensorMap tmB;
+  ConvTap taps[16];
+  ConvGroup groups[4];
+  int32_t ngroups;
+  int32_t chunks, KC;        // channel chunks per tap, channels per chunk (16/32/64)
+  int32_t PW, PH, PN;        // output-pixel patch of one 128-row tile
+  int32_t tiles_w, tiles_h, tiles_n, tiles_c;
+  int32_t W, H, NB;          // output pixel grid (per group)
+  int32_t Cout, BLOCK_N;
+  int32_t stages;
+  uint32_t a_stage_bytes, b_stage_bytes, a_tx_bytes, b_tx_bytes;
+  // epilogue
+  int32_t out_kind;
+  void* out;
+  int64_t os_n, os_h, os_w;  // output pixel strides in elements
+  const float* scale;        // per out channel or null
+  const float* shift;        // per out channel or null (bias when scale == null)
+  int32_t act;               // 1 = SiLU
+  const bf16* addend;        // optional tensor added after the activation (residual / grad accumulation)
+  int64_t as_n, as_h, as_w;
+  float* stats;              // [gridDim.x][2][Cout] per-CTA partial sum / sum of squares of the RAW accumulator
+  int32_t head_na, head_no;  // OUT_HEAD_F32: out[((n*na+a)*H*W + h*W + w)*no + o], column = a*no+o
+};
+
+struct ConvPlan {
+  ConvKParams kp;
+  int grid;
+  int smem;
+};
+
+struct ConvEpilogue {
+  int out_kind = OUT_BF16;
+  const float* scale = nullptr;
+  const float* shift = nullptr;
+  int act = 0;
+  const bf16* addend = nullptr;  // same geometry as the output view
+  long addend_pitch = 0;
+  float* stats = nullptr;
+  int head_na = 3, head_no = 85;
+};
+
+// forward: in (N,Hin,Win,Cin) -> out (N,Hout,Wout,Cout); wp = [Cout][ks*ks][Cin] bf16.
+int conv_plan_fwd(ConvPlan& pl, const TView& in, const bf16* wp, int ks, int stride, const TView& out,
+                  const ConvEpilogue& ep);
+// dgrad: dy (N,Hout,Wout,Cout) -> dx (N,Hin,Win,Cin); wt = [Cin][ks*ks][Cout] bf16 (tap = kh*ks+kw).
+int conv_plan_dgrad(ConvPlan& pl, const TView& dy, const bf16* wt, int ks, int stride, const TView& dx,
+                    const ConvEpilogue& ep);
+int conv_run(const ConvPlan& pl, cudaStream_t st);
+int conv_stats_rows(const ConvPlan& pl);  // number of per-CTA partial rows written to ep.stats (= grid)
+int conv_max_grid();
+
+}  // namespace yb
