@@ -48,6 +48,79 @@ int yb_conv2d_dgrad(const void* dy, int N, int H, int W, int Cout, int64_t dy_pi
                     int ks, int stride, void* dx, int64_t dx_pitch, const void* addend, int64_t addend_pitch,
                     void* stream);
 
+
+/* ---- cached launch plans (TMA descriptors are encoded once per tensor geometry) ------------------------------
+ * yb_conv_fwd_plan / yb_conv_dgrad_plan take the arguments of yb_conv2d_fwd / yb_conv2d_dgrad (minus the stream),
+ * return an opaque handle (NULL on error -> yb_last_error()).  yb_plan_run launches it.  The pointers baked into a
+ * plan must stay valid for its lifetime. */
+void* yb_conv_fwd_plan(const void* x, int N, int H, int W, int Cin, int64_t x_pitch, const void* w_packed, int Cout,
+                       int ks, int stride, void* y, int64_t y_pitch, int out_kind, const float* scale,
+                       const float* shift, int act, const void* addend, int64_t addend_pitch, float* stats,
+                       int* stats_rows, int head_na, int head_no);
+void* yb_conv_dgrad_plan(const void* dy, int N, int H, int W, int Cout, int64_t dy_pitch, const void* wt_packed, int Cin,
+                         int ks, int stride, void* dx, int64_t dx_pitch, const void* addend, int64_t addend_pitch);
+int yb_plan_run(void* plan, void* stream);
+void yb_plan_destroy(void* plan);
+
+/* ---- Conv2d weight gradient (autograd of model.py:16 / :162) ---------------------------------------------------
+ * dw[co][(kh*ks+kw)*Cin+ci] (+)= sum_{n,ho,wo} dy[n,ho,wo,co] * x[n, ho*s+kh-p, wo*s+kw-p, ci]      (fp32 output)
+ * x: conv input (N,H,W,Cin) bf16 NHWC; dy: (N,H/s,W/s,Cout) bf16 NHWC (Cout a multiple of 16; the head pads 255->256
+ * and passes out_rows = 255).  workspace: fp32 scratch for the split-K partial tiles (>= Cout*ks*ks*Cin floats; more
+ * lets the planner split the pixel reduction over more CTAs).  index_map (optional, int32 [Cout*ks*ks*Cin]): element
+ * i of the packed gradient is written to dw[index_map[i]] (skipped when negative) -- used to fold the space-to-depth
+ * stem back to its 6x6 layout.  Deterministic: partials are reduced in a fixed order. */
+void* yb_conv_wgrad_plan(const void* x, int N, int H, int W, int Cin, int64_t x_pitch, const void* dy, int Cout,
+                         int64_t dy_pitch, int ks, int stride, float* workspace, int64_t workspace_floats,
+                         int max_splits);
+int yb_wgrad_plan_run(void* plan, float* dw, int out_rows, const int* index_map, int accumulate, void* stream);
+int yb_conv2d_wgrad(const void* x, int N, int H, int W, int Cin, int64_t x_pitch, const void* dy, int Cout,
+                    int64_t dy_pitch, int ks, int stride, float* workspace, int64_t workspace_floats, int max_splits,
+                    float* dw, int out_rows, const int* index_map, int accumulate, void* stream);
+
+/* ---- BatchNorm2d(eps, momentum) + SiLU around the convs (model.py:17,23; residual add model.py:50;
+ *      nearest 2x upsample model.py:225 fused as a second store) -----------------------------------------------
+ * yb_bn_finalize: training=1: batch mean / biased variance from the conv's stats partials ([rows][2][C]), updates
+ *   running_mean/var (unbiased variance, momentum) and num_batches_tracked when given; training=0: uses the running
+ *   statistics.  Writes scale = gamma*invstd, shift = beta - mean*scale (and mean, invstd when non-NULL).
+ * yb_bn_act_fwd:   out = SiLU(y*scale+shift) (+ res);  out_up (optional) receives the 2x nearest-upsampled copy.
+ * backward (two passes): reduce -> per-channel sums of dz = da*SiLU'(z) and dz*xhat as [rows][2][C] partials;
+ *   finalize -> dgamma, dbeta (fp32, optional accumulate) and coef[2][C] = sums/count; apply -> dy (bf16). */
+int yb_bn_finalize(const float* stats, int rows, int C, double count, const float* gamma, const float* beta, float eps,
+                   float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked, float* scale,
+                   float* shift, float* mean, float* invstd, int training, void* stream);
+int yb_bn_act_fwd(const void* y, int64_t y_pitch, int N, int H, int W, int C, const float* scale, const float* shift,
+                  const void* res, int64_t res_pitch, void* out, int64_t out_pitch, void* out_up, int64_t up_pitch,
+                  void* stream);
+int yb_bwd_reduce_max_rows(void);
+int yb_bn_act_bwd_reduce(const void* da, int64_t da_pitch, const void* y, int64_t y_pitch, int64_t npix, int C,
+                         const float* scale, const float* shift, const float* mean, const float* invstd, float* partial,
+                         int* rows, void* stream);
+int yb_bn_bwd_finalize(const float* partial, int rows, int C, double count, float* dgamma, float* dbeta, float* coef,
+                       int accumulate, void* stream);
+int yb_bn_act_bwd_apply(const void* da, int64_t da_pitch, const void* y, int64_t y_pitch, int64_t npix, int C,
+                        const float* scale, const float* shift, const float* mean, const float* invstd,
+                        const float* coef, void* dy, int64_t dy_pitch, void* stream);
+/* per-channel column sums of a bf16 NHWC tensor as [rows][2][C] partials (row 0 of each pair); head bias gradient */
+int yb_colsum(const void* x, int64_t x_pitch, int64_t npix, int C, float* partial, int* rows, void* stream);
+int yb_reduce_rows(const float* partial, int rows, int64_t stride, int n, float* out, int accumulate, void* stream);
+
+/* ---- glue ops of YOLOV5m.forward (model.py:210-239) and their backward ----------------------------------------- */
+int yb_upsample2x_fwd(const void* src, int64_t src_pitch, int N, int H, int W, int C, void* dst, int64_t dst_pitch,
+                      void* stream);                                   /* Resize(NEAREST), model.py:225 */
+int yb_upsample2x_bwd(const void* dup, int64_t dup_pitch, int N, int H, int W, int C, void* dsrc, int64_t dsrc_pitch,
+                      int accumulate, void* stream);
+int yb_add_into(const void* src, int64_t src_pitch, void* dst, int64_t dst_pitch, int64_t npix, int C, int accumulate,
+                void* stream);                                         /* gradient fan-in (residual, model.py:50) */
+int yb_maxpool5_fwd(const void* x, int64_t x_pitch, int N, int H, int W, int C, void* y, int64_t y_pitch,
+                    uint8_t* argmax, void* stream);                    /* nn.MaxPool2d(5,1,2), model.py:103 */
+int yb_maxpool5_bwd(const void* dy, int64_t dy_pitch, const uint8_t* argmax, int N, int H, int W, int C, void* dx,
+                    int64_t dx_pitch, int accumulate, void* stream);
+/* x (N,3,H,W) NCHW, dtype 0 = float32 in [0,1], 1 = uint8 (divided by 255, training_utils.py:98)
+ * -> out (N,H/2,W/2,16) bf16: space-to-depth so that the 6x6/s2 stem (model.py:184) becomes a 3x3/s1 conv */
+int yb_prep_input(const void* x, int dtype, int N, int H, int W, void* out, void* stream);
+/* dense gradient of a head output (B,na,H,W,no) fp32 -> bf16 NHWC (B,H,W,Cpad), channel a*no+o (model.py:173 backward) */
+int yb_head_grad_pack(const float* g, int B, int na, int H, int W, int no, void* dy, int Cpad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

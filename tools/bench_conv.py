@@ -1,0 +1,95 @@
+"""Per-layer timing of the tcgen05 conv kernels (fwd with BN-stat partials, dgrad, wgrad) on the distinct
+conv shapes of YOLOV5m at 640x640.  CUDA events, inputs larger than L2 at bs=64.
+
+    python tools/bench_conv.py [--bs 64] [--iters 10] [--only fwd,dgrad,wgrad]
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from yolov5m_b200 import _lib  # noqa: E402
+
+SHAPES = [  # Cin, Cout, k, stride, Hout, count
+    (16, 48, 3, 1, 320, 1), (48, 96, 3, 2, 160, 1), (96, 48, 1, 1, 160, 2), (48, 48, 1, 1, 160, 2),
+    (48, 48, 3, 1, 160, 2), (96, 96, 1, 1, 160, 1), (96, 192, 3, 2, 80, 1), (192, 96, 1, 1, 80, 2),
+    (96, 96, 1, 1, 80, 6), (96, 96, 3, 1, 80, 6), (192, 192, 1, 1, 80, 2), (384, 96, 1, 1, 80, 2),
+    (192, 384, 3, 2, 40, 1), (384, 192, 1, 1, 40, 5), (192, 192, 1, 1, 40, 10), (192, 192, 3, 1, 40, 10),
+    (384, 384, 1, 1, 40, 3), (768, 192, 1, 1, 40, 2), (192, 192, 3, 2, 40, 1), (384, 768, 3, 2, 20, 1),
+    (768, 384, 1, 1, 20, 6), (384, 384, 1, 1, 20, 4), (384, 384, 3, 1, 20, 4), (768, 768, 1, 1, 20, 2),
+    (1536, 768, 1, 1, 20, 1), (384, 384, 3, 2, 20, 1), (192, 256, 1, 1, 80, 1), (384, 256, 1, 1, 40, 1),
+    (768, 256, 1, 1, 20, 1),
+]
+
+
+def time_it(fn, iters):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e-3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--bs", type=int, default=64)
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--only", default="fwd,dgrad,wgrad")
+    ap.add_argument("--out", default=None)
+    a = ap.parse_args()
+    L = _lib.lib()
+    st = _lib.stream()
+    ws = torch.empty(64 << 20, device="cuda", dtype=torch.float32)
+    rows = []
+    tot = {"fwd": 0.0, "dgrad": 0.0, "wgrad": 0.0}
+    totf = 0.0
+    for (cin, cout, k, s, ho, cnt) in SHAPES:
+        B, hin = a.bs, ho * s
+        x = torch.randn(B, hin, hin, cin, device="cuda").to(torch.bfloat16)
+        y = torch.empty(B, ho, ho, cout, device="cuda", dtype=torch.bfloat16)
+        w = (torch.randn(cout, k * k, cin, device="cuda") * 0.05).to(torch.bfloat16)
+        wt = (torch.randn(cin, k * k, cout, device="cuda") * 0.05).to(torch.bfloat16)
+        dw = torch.zeros(cout, k * k, cin, device="cuda")
+        stats = torch.zeros(L.yb_conv_max_partials(), 2, cout, device="cuda")
+        flops = 2.0 * B * ho * ho * cout * cin * k * k
+        r = dict(shape=f"{cin}->{cout} k{k} s{s} @{ho}", count=cnt, gflop=flops / 1e9)
+        nrows = ctypes.c_int(0)
+        if "fwd" in a.only:
+            p = _lib.checkp(L.yb_conv_fwd_plan(x.data_ptr(), B, hin, hin, cin, cin, w.data_ptr(), cout, k, s, y.data_ptr(),
+                                               cout, 0, None, None, 0, None, 0, stats.data_ptr(), ctypes.byref(nrows), 3, 85))
+            t = time_it(lambda: L.yb_plan_run(p, st), a.iters)
+            r["fwd_us"] = t * 1e6; r["fwd_tf"] = flops / t / 1e12; tot["fwd"] += t * cnt
+            L.yb_plan_destroy(p)
+        if "dgrad" in a.only and cin != 16:
+            p = _lib.checkp(L.yb_conv_dgrad_plan(y.data_ptr(), B, hin, hin, cout, cout, wt.data_ptr(), cin, k, s,
+                                                 x.data_ptr(), cin, None, 0))
+            t = time_it(lambda: L.yb_plan_run(p, st), a.iters)
+            r["dgrad_us"] = t * 1e6; r["dgrad_tf"] = flops / t / 1e12; tot["dgrad"] += t * cnt
+            L.yb_plan_destroy(p)
+        if "wgrad" in a.only:
+            p = _lib.checkp(L.yb_conv_wgrad_plan(x.data_ptr(), B, hin, hin, cin, cin, y.data_ptr(), cout, cout, k, s,
+                                                 ws.data_ptr(), ws.numel(), 0))
+            t = time_it(lambda: L.yb_wgrad_plan_run(p, dw.data_ptr(), cout, None, 0, st), a.iters)
+            r["wgrad_us"] = t * 1e6; r["wgrad_tf"] = flops / t / 1e12; tot["wgrad"] += t * cnt
+            L.yb_plan_destroy(p)
+        totf += flops * cnt
+        rows.append(r)
+        print(json.dumps({k_: (round(v, 1) if isinstance(v, float) else v) for k_, v in r.items()}), flush=True)
+        del x, y, w, wt, dw
+    summ = {k_: dict(ms=v * 1e3, tflops=totf / v / 1e12 if v else None) for k_, v in tot.items()}
+    print(json.dumps(dict(bs=a.bs, total_gflop_per_pass=totf / 1e9, summary=summ)))
+    if a.out:
+        json.dump(dict(rows=rows, summary=summ, bs=a.bs), open(a.out, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

@@ -3,6 +3,7 @@
 
 #include "common.cuh"
 #include "conv_igemm.cuh"
+#include "conv_wgrad.cuh"
 
 namespace yb {
 const char* last_error();
@@ -50,6 +51,94 @@ int yb_conv2d_dgrad(const void* dy, int N, int H, int W, int Cout, int64_t dy_pi
   int rc = conv_plan_dgrad(pl, g, reinterpret_cast<const bf16*>(wt_packed), ks, stride, o, ep);
   if (rc) return rc;
   return conv_run(pl, reinterpret_cast<cudaStream_t>(stream));
+}
+
+
+struct YbPlan {
+  int kind;  // 0 conv (fwd/dgrad), 1 wgrad
+  ConvPlan conv;
+  WgradPlan wgrad;
+};
+
+void* yb_conv_fwd_plan(const void* x, int N, int H, int W, int Cin, int64_t x_pitch, const void* w_packed, int Cout,
+                       int ks, int stride, void* y, int64_t y_pitch, int out_kind, const float* scale,
+                       const float* shift, int act, const void* addend, int64_t addend_pitch, float* stats,
+                       int* stats_rows, int head_na, int head_no) {
+  TView in{const_cast<void*>(x), N, H, W, Cin, (long)x_pitch};
+  TView out{y, N, H / stride, W / stride, Cout, (long)y_pitch};
+  ConvEpilogue ep;
+  ep.out_kind = out_kind;
+  ep.scale = scale;
+  ep.shift = shift;
+  ep.act = act;
+  ep.addend = reinterpret_cast<const bf16*>(addend);
+  ep.addend_pitch = (long)addend_pitch;
+  ep.stats = stats;
+  ep.head_na = head_na;
+  ep.head_no = head_no;
+  YbPlan* pl = new YbPlan();
+  pl->kind = 0;
+  if (conv_plan_fwd(pl->conv, in, reinterpret_cast<const bf16*>(w_packed), ks, stride, out, ep)) {
+    delete pl;
+    return nullptr;
+  }
+  if (stats_rows) *stats_rows = conv_stats_rows(pl->conv);
+  return pl;
+}
+
+void* yb_conv_dgrad_plan(const void* dy, int N, int H, int W, int Cout, int64_t dy_pitch, const void* wt_packed, int Cin,
+                         int ks, int stride, void* dx, int64_t dx_pitch, const void* addend, int64_t addend_pitch) {
+  TView g{const_cast<void*>(dy), N, H / stride, W / stride, Cout, (long)dy_pitch};
+  TView o{dx, N, H, W, Cin, (long)dx_pitch};
+  ConvEpilogue ep;
+  ep.addend = reinterpret_cast<const bf16*>(addend);
+  ep.addend_pitch = (long)addend_pitch;
+  YbPlan* pl = new YbPlan();
+  pl->kind = 0;
+  if (conv_plan_dgrad(pl->conv, g, reinterpret_cast<const bf16*>(wt_packed), ks, stride, o, ep)) {
+    delete pl;
+    return nullptr;
+  }
+  return pl;
+}
+
+int yb_plan_run(void* plan, void* stream) {
+  YbPlan* pl = reinterpret_cast<YbPlan*>(plan);
+  YB_REQUIRE(pl != nullptr && pl->kind == 0, "yb_plan_run: not a conv plan");
+  return conv_run(pl->conv, reinterpret_cast<cudaStream_t>(stream));
+}
+
+void yb_plan_destroy(void* plan) { delete reinterpret_cast<YbPlan*>(plan); }
+
+void* yb_conv_wgrad_plan(const void* x, int N, int H, int W, int Cin, int64_t x_pitch, const void* dy, int Cout,
+                         int64_t dy_pitch, int ks, int stride, float* workspace, int64_t workspace_floats,
+                         int max_splits) {
+  TView xv{const_cast<void*>(x), N, H, W, Cin, (long)x_pitch};
+  TView gv{const_cast<void*>(dy), N, H / stride, W / stride, Cout, (long)dy_pitch};
+  YbPlan* pl = new YbPlan();
+  pl->kind = 1;
+  if (wgrad_plan(pl->wgrad, xv, gv, ks, stride, workspace, (size_t)workspace_floats, max_splits)) {
+    delete pl;
+    return nullptr;
+  }
+  return pl;
+}
+
+int yb_wgrad_plan_run(void* plan, float* dw, int out_rows, const int* index_map, int accumulate, void* stream) {
+  YbPlan* pl = reinterpret_cast<YbPlan*>(plan);
+  YB_REQUIRE(pl != nullptr && pl->kind == 1, "yb_wgrad_plan_run: not a wgrad plan");
+  return wgrad_run(pl->wgrad, dw, out_rows, index_map, accumulate, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int yb_conv2d_wgrad(const void* x, int N, int H, int W, int Cin, int64_t x_pitch, const void* dy, int Cout,
+                    int64_t dy_pitch, int ks, int stride, float* workspace, int64_t workspace_floats, int max_splits,
+                    float* dw, int out_rows, const int* index_map, int accumulate, void* stream) {
+  TView xv{const_cast<void*>(x), N, H, W, Cin, (long)x_pitch};
+  TView gv{const_cast<void*>(dy), N, H / stride, W / stride, Cout, (long)dy_pitch};
+  WgradPlan pl;
+  int rc = wgrad_plan(pl, xv, gv, ks, stride, workspace, (size_t)workspace_floats, max_splits);
+  if (rc) return rc;
+  return wgrad_run(pl, dw, out_rows, index_map, accumulate, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

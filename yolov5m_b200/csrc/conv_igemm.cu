@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       const int n = tc.nb * p.PN + pn, h = tc.hb * p.PH + phh, w = tc.wb * p.PW + pw;
       const bool valid = (r < p.PW * p.PH * p.PN) && n < p.NB && h < p.H && w < p.W;
       const int64_t opix = p.groups[tc.g].out_off + n * p.os_n + h * p.os_h + w * p.os_w;
-      const int64_t apix = n * p.as_n + h * p.as_h + w * p.as_w;
+      const int64_t apix = p.groups[tc.g].add_off + n * p.as_n + h * p.as_h + w * p.as_w;
       const int ab = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       mbar_wait(&tfull_bar[ab], aph);
@@ -430,7 +430,7 @@ int conv_plan_fwd(ConvPlan& pl, const TView& in, const bf16* wp, int ks, int str
       }
   }
   kp.ngroups = 1;
-  kp.groups[0] = ConvGroup{0, nt, 0};
+  kp.groups[0] = ConvGroup{0, nt, 0, 0};
   kp.os_n = (int64_t)out.pitch * out.W * out.H;
   kp.os_h = (int64_t)out.pitch * out.W;
   kp.os_w = out.pitch;
@@ -468,7 +468,7 @@ int conv_plan_dgrad(ConvPlan& pl, const TView& dy, const bf16* wt, int ks, int s
         ++nt;
       }
     kp.ngroups = 1;
-    kp.groups[0] = ConvGroup{0, nt, 0};
+    kp.groups[0] = ConvGroup{0, nt, 0, 0};
     kp.os_n = (int64_t)dx.pitch * dx.W * dx.H;
     kp.os_h = (int64_t)dx.pitch * dx.W;
     kp.os_w = dx.pitch;
@@ -495,16 +495,16 @@ int conv_plan_dgrad(ConvPlan& pl, const TView& dy, const bf16* wt, int ks, int s
         }
         kp.groups[g].tap_end = nt;
         kp.groups[g].out_off = ((int64_t)py * dx.W + px) * dx.pitch;
+        kp.groups[g].add_off = ((int64_t)py * dx.W + px) * ep.addend_pitch;
       }
     kp.os_n = (int64_t)dx.pitch * dx.W * dx.H;
     kp.os_h = (int64_t)dx.pitch * dx.W * 2;
     kp.os_w = dx.pitch * 2;
   }
   if (ep.addend) {
-    YB_REQUIRE(stride == 1, "conv dgrad: addend only for stride 1");
     kp.as_n = (int64_t)ep.addend_pitch * dx.W * dx.H;
-    kp.as_h = (int64_t)ep.addend_pitch * dx.W;
-    kp.as_w = ep.addend_pitch;
+    kp.as_h = (int64_t)ep.addend_pitch * dx.W * stride;
+    kp.as_w = ep.addend_pitch * stride;
   }
   return finish_plan(pl, wt, dx.C, (long)ks * ks * dy.C, dx, ep);
 }

@@ -27,6 +27,7 @@ struct ConvTap {
 struct ConvGroup {
   int32_t tap_begin, tap_end;
   int64_t out_off;  // element offset of this group's (0,0,0) output pixel
+  int64_t add_off;  // same for the addend tensor
 };
 
 enum { OUT_BF16 = 0, OUT_HEAD_F32 = 1, OUT_F32 = 2 };

@@ -1,0 +1,640 @@
+// HBM-bound NHWC bf16 passes around the tcgen05 convolutions (sm_100a):
+//   BatchNorm2d batch-stat finalize / apply + SiLU (+ residual, + fused nearest 2x upsample)   model.py:17,23,50,225
+//   their backward (two-pass BN backward with the SiLU derivative folded in)                     autograd of the above
+//   SPPF 5x5/1/2 max pooling fwd/bwd (argmax kept as a 1-byte window offset)                     model.py:103,108-110
+//   input staging (NCHW float/uint8 -> space-to-depth NHWC bf16 for the 6x6/s2 stem)             model.py:184, training_utils.py:98
+//   dense head-gradient repack                                                                   model.py:173 (permute backward)
+// Every thread moves 16-byte vectors (8 bf16 channels); channel counts are multiples of 8 by construction.
+#include "../../include/yolov5m_b200.h"
+#include "common.cuh"
+
+#include <algorithm>
+
+namespace yb {
+
+static inline int ew_blocks(long n, int threads = 256, int per_sm = 8) {
+  int sms = 148;
+  static int cached = 0;
+  if (!cached) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
+        sms > 0)
+      cached = sms;
+    else
+      cached = 148;
+  }
+  sms = cached;
+  long b = (n + threads - 1) / threads;
+  return (int)std::max<long>(1, std::min<long>(b, (long)sms * per_sm));
+}
+
+struct V8 {
+  float v[8];
+};
+__device__ __forceinline__ V8 ld8(const bf16* p) {
+  const uint4 r = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+  V8 o;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __bfloat1622float2(h[j]);
+    o.v[2 * j] = f.x;
+    o.v[2 * j + 1] = f.y;
+  }
+  return o;
+}
+__device__ __forceinline__ void st8(bf16* p, const V8& a) {
+  uint4 r;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(a.v[2 * j], a.v[2 * j + 1]);
+  *reinterpret_cast<uint4*>(p) = r;
+}
+__device__ __forceinline__ V8 ldf8(const float* p) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  V8 o;
+  o.v[0] = a.x; o.v[1] = a.y; o.v[2] = a.z; o.v[3] = a.w;
+  o.v[4] = b.x; o.v[5] = b.y; o.v[6] = b.z; o.v[7] = b.w;
+  return o;
+}
+
+// ------------------------------------------------------------------------------------------------ BN finalize
+// one thread per channel.  training: mean/var from the per-CTA partial sums written by the conv epilogue.
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, int rows, int C, double count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float momentum, float* running_mean, float* running_var, long long* nbt,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                                   float* __restrict__ invstd_out, int training) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && training && nbt != nullptr) *nbt += 1;
+  if (c >= C) return;
+  float mean, var;
+  if (training) {
+    double s = 0.0, q = 0.0;
+    for (int r = 0; r < rows; ++r) {
+      s += (double)stats[(size_t)r * 2 * C + c];
+      q += (double)stats[(size_t)r * 2 * C + C + c];
+    }
+    const double m = s / count;
+    double v = q / count - m * m;
+    if (v < 0.0) v = 0.0;
+    mean = (float)m;
+    var = (float)v;
+    if (running_mean != nullptr) {
+      const double unb = count > 1.0 ? v * count / (count - 1.0) : v;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+    }
+  } else {
+    mean = running_mean[c];
+    var = running_var[c];
+  }
+  const float inv = rsqrtf(var + eps);
+  const float sc = gamma[c] * inv;
+  scale[c] = sc;
+  shift[c] = beta[c] - mean * sc;
+  if (mean_out) mean_out[c] = mean;
+  if (invstd_out) invstd_out[c] = inv;
+}
+
+// ------------------------------------------------------------------------------------------------ BN apply + SiLU
+__global__ void bn_act_fwd_kernel(const bf16* __restrict__ y, long y_pitch, int H, int W, int C, long npix,
+                                  const float* __restrict__ scale, const float* __restrict__ shift,
+                                  const bf16* __restrict__ res, long res_pitch, bf16* __restrict__ out, long out_pitch,
+                                  bf16* __restrict__ out_up, long up_pitch) {
+  const int cv = C >> 3;
+  const long total = npix * cv;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long pix = i / cv;
+    const int c = (int)(i - pix * cv) << 3;
+    V8 v = ld8(y + pix * y_pitch + c);
+    const V8 sc = ldf8(scale + c), sh = ldf8(shift + c);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v.v[j] = silu_f(fmaf(v.v[j], sc.v[j], sh.v[j]));
+    if (res != nullptr) {
+      const V8 r = ld8(res + pix * res_pitch + c);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v.v[j] += r.v[j];
+    }
+    st8(out + pix * out_pitch + c, v);
+    if (out_up != nullptr) {
+      const long w = pix % W, t = pix / W;
+      const long h = t % H, n = t / H;
+      bf16* u = out_up + (((n * 2 * H + 2 * h) * 2 * W) + 2 * w) * up_pitch + c;
+      st8(u, v);
+      st8(u + up_pitch, v);
+      st8(u + 2 * W * up_pitch, v);
+      st8(u + (2 * W + 1) * up_pitch, v);
+    }
+  }
+}
+
+// plain nearest 2x upsample (eval path: the producer conv already applied BN+SiLU in its epilogue)
+__global__ void upsample2x_fwd_kernel(const bf16* __restrict__ src, long src_pitch, int H, int W, int C, long npix,
+                                      bf16* __restrict__ dst, long dst_pitch) {
+  const int cv = C >> 3;
+  const long total = npix * cv;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long pix = i / cv;
+    const int c = (int)(i - pix * cv) << 3;
+    const uint4 v = *reinterpret_cast<const uint4*>(src + pix * src_pitch + c);
+    const long w = pix % W, t = pix / W;
+    const long h = t % H, n = t / H;
+    bf16* u = dst + (((n * 2 * H + 2 * h) * 2 * W) + 2 * w) * dst_pitch + c;
+    *reinterpret_cast<uint4*>(u) = v;
+    *reinterpret_cast<uint4*>(u + dst_pitch) = v;
+    *reinterpret_cast<uint4*>(u + 2 * W * dst_pitch) = v;
+    *reinterpret_cast<uint4*>(u + (2 * W + 1) * dst_pitch) = v;
+  }
+}
+
+// d(src)[n,h,w] (+)= sum of the 2x2 block of d(up)
+__global__ void upsample2x_bwd_kernel(const bf16* __restrict__ dup, long dup_pitch, int H, int W, int C, long npix,
+                                      bf16* __restrict__ dsrc, long dsrc_pitch, int accumulate) {
+  const int cv = C >> 3;
+  const long total = npix * cv;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long pix = i / cv;
+    const int c = (int)(i - pix * cv) << 3;
+    const long w = pix % W, t = pix / W;
+    const long h = t % H, n = t / H;
+    const bf16* u = dup + (((n * 2 * H + 2 * h) * 2 * W) + 2 * w) * dup_pitch + c;
+    const V8 a = ld8(u), b = ld8(u + dup_pitch), d = ld8(u + 2 * W * dup_pitch), e = ld8(u + (2 * W + 1) * dup_pitch);
+    V8 o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o.v[j] = (a.v[j] + b.v[j]) + (d.v[j] + e.v[j]);
+    bf16* dp = dsrc + pix * dsrc_pitch + c;
+    if (accumulate) {
+      const V8 p = ld8(dp);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o.v[j] += p.v[j];
+    }
+    st8(dp, o);
+  }
+}
+
+__global__ void add_into_kernel(const bf16* __restrict__ src, long src_pitch, bf16* __restrict__ dst, long dst_pitch,
+                                long npix, int C, int accumulate) {
+  const int cv = C >> 3;
+  const long total = npix * cv;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long pix = i / cv;
+    const int c = (int)(i - pix * cv) << 3;
+    V8 v = ld8(src + pix * src_pitch + c);
+    bf16* dp = dst + pix * dst_pitch + c;
+    if (accumulate) {
+      const V8 p = ld8(dp);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v.v[j] += p.v[j];
+    }
+    st8(dp, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ BN + SiLU backward
+__device__ __forceinline__ float dsilu_f(float z) {
+  const float s = 1.f / (1.f + __expf(-z));
+  return s * (1.f + z * (1.f - s));
+}
+
+// pass 1: per-channel sums of dz and dz*xhat, dz = da * silu'(y*scale+shift), xhat = (y-mean)*invstd.
+// block = (rows x cv) threads; every block owns a contiguous pixel range; partial[block][2][C].
+// mode 1: plain column sums of `da` (head bias gradient): partial[block][0][C] only.
+__global__ void bn_act_bwd_reduce_kernel(const bf16* __restrict__ da, long da_pitch, const bf16* __restrict__ y,
+                                         long y_pitch, long npix, int C, const float* __restrict__ scale,
+                                         const float* __restrict__ shift, const float* __restrict__ mean,
+                                         const float* __restrict__ invstd, float* __restrict__ partial, int rows_pb,
+                                         int mode) {
+  extern __shared__ float sred[];  // [rows_pb][2][C]
+  const int cv = C >> 3;
+  const int tid = threadIdx.x;
+  const int row = tid / cv, c = (tid - row * cv) << 3;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  if (row < rows_pb) {
+    const long per = (npix + gridDim.x - 1) / gridDim.x;
+    const long p0 = (long)blockIdx.x * per, p1 = min(npix, p0 + per);
+    V8 sc, sh, mu, is;
+    if (mode == 0) {
+      sc = ldf8(scale + c); sh = ldf8(shift + c); mu = ldf8(mean + c); is = ldf8(invstd + c);
+    }
+    for (long p = p0 + row; p < p1; p += rows_pb) {
+      const V8 g = ld8(da + p * da_pitch + c);
+      if (mode == 0) {
+        const V8 yv = ld8(y + p * y_pitch + c);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float dz = g.v[j] * dsilu_f(fmaf(yv.v[j], sc.v[j], sh.v[j]));
+          s1[j] += dz;
+          s2[j] += dz * ((yv.v[j] - mu.v[j]) * is.v[j]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s1[j] += g.v[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sred[(size_t)row * 2 * C + c + j] = s1[j];
+      sred[(size_t)row * 2 * C + C + c + j] = s2[j];
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < 2 * C; i += blockDim.x) {
+    float a = 0.f;
+    for (int r = 0; r < rows_pb; ++r) a += sred[(size_t)r * 2 * C + i];
+    partial[(size_t)blockIdx.x * 2 * C + i] = a;
+  }
+}
+
+// dgamma = sum dz*xhat, dbeta = sum dz; coef[0][c] = dbeta/m, coef[1][c] = dgamma/m
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int rows, int C, double count,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef,
+                                       int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int r = 0; r < rows; ++r) {
+    s += (double)partial[(size_t)r * 2 * C + c];
+    q += (double)partial[(size_t)r * 2 * C + C + c];
+  }
+  if (dbeta) dbeta[c] = accumulate ? dbeta[c] + (float)s : (float)s;
+  if (dgamma) dgamma[c] = accumulate ? dgamma[c] + (float)q : (float)q;
+  if (coef) {
+    coef[c] = (float)(s / count);
+    coef[C + c] = (float)(q / count);
+  }
+}
+
+// pass 2: dy = scale * (dz - coef0 - xhat*coef1)
+__global__ void bn_act_bwd_apply_kernel(const bf16* __restrict__ da, long da_pitch, const bf16* __restrict__ y,
+                                        long y_pitch, long npix, int C, const float* __restrict__ scale,
+                                        const float* __restrict__ shift, const float* __restrict__ mean,
+                                        const float* __restrict__ invstd, const float* __restrict__ coef,
+                                        bf16* __restrict__ dy, long dy_pitch) {
+  const int cv = C >> 3;
+  const long total = npix * cv;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long pix = i / cv;
+    const int c = (int)(i - pix * cv) << 3;
+    const V8 g = ld8(da + pix * da_pitch + c);
+    const V8 yv = ld8(y + pix * y_pitch + c);
+    const V8 sc = ldf8(scale + c), sh = ldf8(shift + c), mu = ldf8(mean + c), is = ldf8(invstd + c);
+    const V8 c0 = ldf8(coef + c), c1 = ldf8(coef + C + c);
+    V8 o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float dz = g.v[j] * dsilu_f(fmaf(yv.v[j], sc.v[j], sh.v[j]));
+      const float xh = (yv.v[j] - mu.v[j]) * is.v[j];
+      o.v[j] = sc.v[j] * (dz - c0.v[j] - xh * c1.v[j]);
+    }
+    st8(dy + pix * dy_pitch + c, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ SPPF max pool 5/1/2
+__global__ void maxpool5_fwd_kernel(const bf16* __restrict__ x, long x_pitch, int H, int W, int C, long npix,
+                                    bf16* __restrict__ out, long out_pitch, uint8_t* __restrict__ argmax) {
+  const int cv = C >> 3;
+  const long total = npix * cv;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long pix = i / cv;
+    const int c = (int)(i - pix * cv) << 3;
+    const int w = (int)(pix % W);
+    const long t = pix / W;
+    const int h = (int)(t % H);
+    const long n = t / H;
+    float best[8];
+    int arg[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      best[j] = -INFINITY;
+      arg[j] = 0;
+    }
+    bool first = true;
+    for (int kh = 0; kh < 5; ++kh) {
+      const int ih = h + kh - 2;
+      if (ih < 0 || ih >= H) continue;
+      for (int kw = 0; kw < 5; ++kw) {
+        const int iw = w + kw - 2;
+        if (iw < 0 || iw >= W) continue;
+        const V8 v = ld8(x + ((n * H + ih) * W + iw) * x_pitch + c);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (first || v.v[j] > best[j] || v.v[j] != v.v[j]) {  // first max wins; NaN propagates (ATen max_pool2d)
+            best[j] = v.v[j];
+            arg[j] = kh * 5 + kw;
+          }
+        first = false;
+      }
+    }
+    V8 o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o.v[j] = best[j];
+    st8(out + pix * out_pitch + c, o);
+    if (argmax != nullptr) {
+      uint2 pk;
+      pk.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+      pk.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
+      *reinterpret_cast<uint2*>(argmax + pix * C + c) = pk;
+    }
+  }
+}
+
+// gather form (deterministic): dx[i] (+)= sum over the <=25 outputs whose recorded argmax is i
+__global__ void maxpool5_bwd_kernel(const bf16* __restrict__ dy, long dy_pitch, const uint8_t* __restrict__ argmax, int H,
+                                    int W, int C, long npix, bf16* __restrict__ dx, long dx_pitch, int accumulate) {
+  const int cv = C >> 3;
+  const long total = npix * cv;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long pix = i / cv;
+    const int c = (int)(i - pix * cv) << 3;
+    const int w = (int)(pix % W);
+    const long t = pix / W;
+    const int h = (int)(t % H);
+    const long n = t / H;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int kh = 0; kh < 5; ++kh) {
+      const int oh = h - kh + 2;
+      if (oh < 0 || oh >= H) continue;
+      for (int kw = 0; kw < 5; ++kw) {
+        const int ow = w - kw + 2;
+        if (ow < 0 || ow >= W) continue;
+        const long op = (n * H + oh) * W + ow;
+        const uint2 pk = *reinterpret_cast<const uint2*>(argmax + op * C + c);
+        const V8 g = ld8(dy + op * dy_pitch + c);
+        const unsigned k = kh * 5 + kw;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const unsigned a = ((j < 4 ? pk.x : pk.y) >> (8 * (j & 3))) & 0xffu;
+          if (a == k) acc[j] += g.v[j];
+        }
+      }
+    }
+    bf16* dp = dx + pix * dx_pitch + c;
+    V8 o;
+    if (accumulate) {
+      o = ld8(dp);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o.v[j] += acc[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o.v[j] = acc[j];
+    }
+    st8(dp, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ input staging
+// x (N,3,H,W) float in [0,1] (or uint8, divided by 255) -> out (N,H/2,W/2,16) bf16 with channel (r*2+s)*3+c = x[c][2h+r][2w+s]
+template <typename T>
+__global__ void prep_input_kernel(const T* __restrict__ x, int N, int H, int W, bf16* __restrict__ out) {
+  const int Ho = H >> 1, Wo = W >> 1;
+  const long total = (long)N * Ho * Wo;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int wo = (int)(i % Wo);
+    const long t = i / Wo;
+    const int ho = (int)(t % Ho);
+    const long n = t / Ho;
+    float v[16];
+#pragma unroll
+    for (int j = 12; j < 16; ++j) v[j] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const T* p = x + ((n * 3 + c) * H + 2 * ho + r) * (long)W + 2 * wo;
+        float a, b;
+        if constexpr (sizeof(T) == 1) {
+          a = (float)p[0] / 255.f;
+          b = (float)p[1] / 255.f;
+        } else {
+          const float2 f = *reinterpret_cast<const float2*>(p);
+          a = f.x;
+          b = f.y;
+        }
+        v[(r * 2 + 0) * 3 + c] = a;
+        v[(r * 2 + 1) * 3 + c] = b;
+      }
+    V8 lo, hi;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      lo.v[j] = v[j];
+      hi.v[j] = v[8 + j];
+    }
+    st8(out + i * 16, lo);
+    st8(out + i * 16 + 8, hi);
+  }
+}
+
+// g (B,na,H,W,no) fp32 -> dy (B,H,W,Cpad) bf16, channel a*no+o; channels >= na*no are zero
+__global__ void head_grad_pack_kernel(const float* __restrict__ g, int na, long hw, int no, bf16* __restrict__ dy, int Cpad,
+                                      long total) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cpad);
+    const long t = i / Cpad;
+    const long pix = t % hw, b = t / hw;
+    float v = 0.f;
+    if (c < na * no) {
+      const int a = c / no, o = c - a * no;
+      v = g[((b * na + a) * hw + pix) * no + o];
+    }
+    dy[i] = __float2bfloat16(v);
+  }
+}
+
+// out[i] (+)= sum_r partial[r*stride + i]
+__global__ void reduce_rows_kernel(const float* __restrict__ partial, int rows, long stride, int n, float* __restrict__ out,
+                                   int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int r = 0; r < rows; ++r) s += (double)partial[(size_t)r * stride + i];
+  out[i] = accumulate ? out[i] + (float)s : (float)s;
+}
+
+}  // namespace yb
+
+using namespace yb;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+#define B16(p) reinterpret_cast<bf16*>(p)
+#define CB16(p) reinterpret_cast<const bf16*>(p)
+#define LAUNCH_OK() YB_CHECK_CUDA(cudaGetLastError())
+
+extern "C" {
+
+int yb_bn_finalize(const float* stats, int rows, int C, double count, const float* gamma, const float* beta, float eps,
+                   float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked, float* scale,
+                   float* shift, float* mean, float* invstd, int training, void* stream) {
+  YB_REQUIRE(training ? (stats != nullptr && rows > 0) : (running_mean && running_var), "bn_finalize: missing inputs");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(stats, rows, C, count, gamma, beta, eps, momentum,
+                                                               running_mean, running_var,
+                                                               reinterpret_cast<long long*>(num_batches_tracked), scale,
+                                                               shift, mean, invstd, training);
+  LAUNCH_OK();
+  return 0;
+}
+
+int yb_bn_act_fwd(const void* y, int64_t y_pitch, int N, int H, int W, int C, const float* scale, const float* shift,
+                  const void* res, int64_t res_pitch, void* out, int64_t out_pitch, void* out_up, int64_t up_pitch,
+                  void* stream) {
+  YB_REQUIRE(C % 8 == 0 && y_pitch % 8 == 0 && out_pitch % 8 == 0 && res_pitch % 8 == 0 && up_pitch % 8 == 0,
+             "bn_act_fwd: C and pitches must be multiples of 8");
+  const long npix = (long)N * H * W;
+  bn_act_fwd_kernel<<<ew_blocks(npix * (C / 8)), 256, 0, ST(stream)>>>(CB16(y), y_pitch, H, W, C, npix, scale, shift,
+                                                                        CB16(res), res_pitch, B16(out), out_pitch,
+                                                                        B16(out_up), up_pitch);
+  LAUNCH_OK();
+  return 0;
+}
+
+int yb_upsample2x_fwd(const void* src, int64_t src_pitch, int N, int H, int W, int C, void* dst, int64_t dst_pitch,
+                      void* stream) {
+  YB_REQUIRE(C % 8 == 0 && src_pitch % 8 == 0 && dst_pitch % 8 == 0, "upsample2x_fwd: alignment");
+  const long npix = (long)N * H * W;
+  upsample2x_fwd_kernel<<<ew_blocks(npix * (C / 8)), 256, 0, ST(stream)>>>(CB16(src), src_pitch, H, W, C, npix, B16(dst),
+                                                                            dst_pitch);
+  LAUNCH_OK();
+  return 0;
+}
+
+int yb_upsample2x_bwd(const void* dup, int64_t dup_pitch, int N, int H, int W, int C, void* dsrc, int64_t dsrc_pitch,
+                      int accumulate, void* stream) {
+  YB_REQUIRE(C % 8 == 0 && dup_pitch % 8 == 0 && dsrc_pitch % 8 == 0, "upsample2x_bwd: alignment");
+  const long npix = (long)N * H * W;
+  upsample2x_bwd_kernel<<<ew_blocks(npix * (C / 8)), 256, 0, ST(stream)>>>(CB16(dup), dup_pitch, H, W, C, npix, B16(dsrc),
+                                                                            dsrc_pitch, accumulate);
+  LAUNCH_OK();
+  return 0;
+}
+
+int yb_add_into(const void* src, int64_t src_pitch, void* dst, int64_t dst_pitch, int64_t npix, int C, int accumulate,
+                void* stream) {
+  YB_REQUIRE(C % 8 == 0 && src_pitch % 8 == 0 && dst_pitch % 8 == 0, "add_into: alignment");
+  add_into_kernel<<<ew_blocks(npix * (C / 8)), 256, 0, ST(stream)>>>(CB16(src), src_pitch, B16(dst), dst_pitch, npix, C,
+                                                                      accumulate);
+  LAUNCH_OK();
+  return 0;
+}
+
+static int reduce_geometry(int C, long npix, int& threads, int& rows_pb, int& grid, size_t& smem) {
+  const int cv = C / 8;
+  YB_REQUIRE(C % 8 == 0 && cv <= 256, "bwd_reduce: C=%d unsupported", C);
+  rows_pb = std::max(1, 256 / cv);
+  while (rows_pb > 1 && (size_t)rows_pb * 2 * C * sizeof(float) > 96 * 1024) --rows_pb;
+  threads = ((rows_pb * cv + 31) / 32) * 32;
+  smem = (size_t)rows_pb * 2 * C * sizeof(float);
+  const long want = (npix + (long)rows_pb * 16 - 1) / ((long)rows_pb * 16);  // >= 16 pixels per thread row
+  grid = (int)std::max<long>(1, std::min<long>(want, 592));
+  return 0;
+}
+
+int yb_bwd_reduce_max_rows(void) { return 592; }
+
+int yb_bn_act_bwd_reduce(const void* da, int64_t da_pitch, const void* y, int64_t y_pitch, int64_t npix, int C,
+                         const float* scale, const float* shift, const float* mean, const float* invstd, float* partial,
+                         int* rows, void* stream) {
+  int threads, rows_pb, grid;
+  size_t smem;
+  if (reduce_geometry(C, npix, threads, rows_pb, grid, smem)) return -1;
+  YB_REQUIRE(da_pitch % 8 == 0 && y_pitch % 8 == 0, "bn_act_bwd_reduce: alignment");
+  static bool attr = false;
+  if (!attr) {
+    YB_CHECK_CUDA(cudaFuncSetAttribute(bn_act_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr = true;
+  }
+  bn_act_bwd_reduce_kernel<<<grid, threads, smem, ST(stream)>>>(CB16(da), da_pitch, CB16(y), y_pitch, npix, C, scale,
+                                                                shift, mean, invstd, partial, rows_pb, 0);
+  LAUNCH_OK();
+  if (rows) *rows = grid;
+  return 0;
+}
+
+int yb_colsum(const void* x, int64_t x_pitch, int64_t npix, int C, float* partial, int* rows, void* stream) {
+  int threads, rows_pb, grid;
+  size_t smem;
+  if (reduce_geometry(C, npix, threads, rows_pb, grid, smem)) return -1;
+  static bool attr = false;
+  if (!attr) {
+    YB_CHECK_CUDA(cudaFuncSetAttribute(bn_act_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr = true;
+  }
+  bn_act_bwd_reduce_kernel<<<grid, threads, smem, ST(stream)>>>(CB16(x), x_pitch, nullptr, 0, npix, C, nullptr, nullptr,
+                                                                nullptr, nullptr, partial, rows_pb, 1);
+  LAUNCH_OK();
+  if (rows) *rows = grid;
+  return 0;
+}
+
+int yb_bn_bwd_finalize(const float* partial, int rows, int C, double count, float* dgamma, float* dbeta, float* coef,
+                       int accumulate, void* stream) {
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(partial, rows, C, count, dgamma, dbeta, coef,
+                                                                   accumulate);
+  LAUNCH_OK();
+  return 0;
+}
+
+int yb_bn_act_bwd_apply(const void* da, int64_t da_pitch, const void* y, int64_t y_pitch, int64_t npix, int C,
+                        const float* scale, const float* shift, const float* mean, const float* invstd,
+                        const float* coef, void* dy, int64_t dy_pitch, void* stream) {
+  YB_REQUIRE(C % 8 == 0 && da_pitch % 8 == 0 && y_pitch % 8 == 0 && dy_pitch % 8 == 0, "bn_act_bwd_apply: alignment");
+  bn_act_bwd_apply_kernel<<<ew_blocks(npix * (C / 8)), 256, 0, ST(stream)>>>(CB16(da), da_pitch, CB16(y), y_pitch, npix, C,
+                                                                              scale, shift, mean, invstd, coef, B16(dy),
+                                                                              dy_pitch);
+  LAUNCH_OK();
+  return 0;
+}
+
+int yb_maxpool5_fwd(const void* x, int64_t x_pitch, int N, int H, int W, int C, void* y, int64_t y_pitch,
+                    uint8_t* argmax, void* stream) {
+  YB_REQUIRE(C % 8 == 0 && x_pitch % 8 == 0 && y_pitch % 8 == 0, "maxpool5_fwd: alignment");
+  const long npix = (long)N * H * W;
+  maxpool5_fwd_kernel<<<ew_blocks(npix * (C / 8)), 256, 0, ST(stream)>>>(CB16(x), x_pitch, H, W, C, npix, B16(y), y_pitch,
+                                                                          argmax);
+  LAUNCH_OK();
+  return 0;
+}
+
+int yb_maxpool5_bwd(const void* dy, int64_t dy_pitch, const uint8_t* argmax, int N, int H, int W, int C, void* dx,
+                    int64_t dx_pitch, int accumulate, void* stream) {
+  YB_REQUIRE(C % 8 == 0 && dy_pitch % 8 == 0 && dx_pitch % 8 == 0, "maxpool5_bwd: alignment");
+  const long npix = (long)N * H * W;
+  maxpool5_bwd_kernel<<<ew_blocks(npix * (C / 8)), 256, 0, ST(stream)>>>(CB16(dy), dy_pitch, argmax, H, W, C, npix,
+                                                                          B16(dx), dx_pitch, accumulate);
+  LAUNCH_OK();
+  return 0;
+}
+
+int yb_prep_input(const void* x, int dtype, int N, int H, int W, void* out, void* stream) {
+  YB_REQUIRE(H % 2 == 0 && W % 2 == 0, "prep_input: odd image size");
+  const long total = (long)N * (H / 2) * (W / 2);
+  if (dtype == 0)
+    prep_input_kernel<float><<<ew_blocks(total), 256, 0, ST(stream)>>>(reinterpret_cast<const float*>(x), N, H, W,
+                                                                        B16(out));
+  else if (dtype == 1)
+    prep_input_kernel<uint8_t><<<ew_blocks(total), 256, 0, ST(stream)>>>(reinterpret_cast<const uint8_t*>(x), N, H, W,
+                                                                          B16(out));
+  else
+    YB_REQUIRE(false, "prep_input: dtype %d (0 = float32, 1 = uint8)", dtype);
+  LAUNCH_OK();
+  return 0;
+}
+
+int yb_head_grad_pack(const float* g, int B, int na, int H, int W, int no, void* dy, int Cpad, void* stream) {
+  YB_REQUIRE(Cpad >= na * no, "head_grad_pack: Cpad");
+  const long total = (long)B * H * W * Cpad;
+  head_grad_pack_kernel<<<ew_blocks(total), 256, 0, ST(stream)>>>(g, na, (long)H * W, no, B16(dy), Cpad, total);
+  LAUNCH_OK();
+  return 0;
+}
+
+int yb_reduce_rows(const float* partial, int rows, int64_t stride, int n, float* out, int accumulate, void* stream) {
+  reduce_rows_kernel<<<(n + 127) / 128, 128, 0, ST(stream)>>>(partial, rows, stride, n, out, accumulate);
+  LAUNCH_OK();
+  return 0;
+}
+
+}  // extern "C"
