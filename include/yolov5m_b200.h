@@ -121,6 +121,27 @@ int yb_prep_input(const void* x, int dtype, int N, int H, int W, void* out, void
 /* dense gradient of a head output (B,na,H,W,no) fp32 -> bf16 NHWC (B,H,W,Cpad), channel a*no+o (model.py:173 backward) */
 int yb_head_grad_pack(const float* g, int B, int na, int H, int W, int no, void* dy, int Cpad, void* stream);
 
+/* ---- parameter packing + optimiser tail on the flat fp32 master / gradient buffers ------------------------------
+ * The master weights stay in the reference's state_dict tensors (fp32, conv weights channels-last = [Cout][kh*kw][Cin]),
+ * laid out back to back in one flat buffer; the tcgen05 operands are bf16 copies:
+ *   yb_cast_bf16     forward operands: element-wise cast of the whole flat buffer (same offsets)
+ *   yb_repack_dgrad  dgrad operands [Cin][tap][Cout_pad]; table = int64 [nlayers][8]
+ *                    {src_off, dst_off, Cout, taps, Cin, Cout_pad, cum_begin, cum_end} (offsets in elements)
+ *   yb_repack_stem   6x6/s2 stem [Cout][6][6][3] -> space-to-depth 3x3 [Cout][9][16]
+ * yb_grad_norm / yb_adam_step replace scaler.unscale_ + clip_grad_norm_(max_norm) + Adam.step of
+ * utils/training_utils.py:114-122 (train.py:61: Adam(lr, weight_decay) = L2 added to the gradient, all parameters):
+ *   norm_out[0] = grad_scale * ||g||_2 ;  clip = min(1, max_norm/(norm+1e-6)) (max_norm <= 0: no clipping)
+ *   step counts from 1 (host value), or is read from step_dev when non-NULL (CUDA-graph replay; yb_counter_inc). */
+int yb_cast_bf16(const float* src, void* dst, int64_t n, void* stream);
+int yb_repack_dgrad(const float* src, void* dst, const int64_t* table, int nlayers, int64_t total, void* stream);
+int yb_repack_stem(const float* w6, void* w3, int Cout, void* stream);
+int yb_grad_norm(const float* g, int64_t n, float grad_scale, float* partial, int partial_len, float* norm_out,
+                 void* stream);
+int yb_counter_inc(int64_t* counter, void* stream);
+int yb_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                 float weight_decay, int64_t step, const int64_t* step_dev, float grad_scale, float max_norm,
+                 const float* norm, void* w_bf16, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -105,8 +105,9 @@ def test_bn_eval_finalize():
     gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
     rm, rv = torch.randn(C, generator=g), torch.rand(C, generator=g) + 0.1
     scale = torch.empty(C, device="cuda"); shift = torch.empty(C, device="cuda")
-    _lib.check(L.yb_bn_finalize(None, 0, C, ctypes.c_double(1), _lib.ptr(gamma.cuda()), _lib.ptr(beta.cuda()),
-                                _lib.c_f(1e-3), _lib.c_f(0.03), _lib.ptr(rm.cuda()), _lib.ptr(rv.cuda()), None,
+    gd, bd, rmd, rvd = gamma.cuda(), beta.cuda(), rm.cuda(), rv.cuda()  # keep the device copies alive across the launch
+    _lib.check(L.yb_bn_finalize(None, 0, C, ctypes.c_double(1), _lib.ptr(gd), _lib.ptr(bd),
+                                _lib.c_f(1e-3), _lib.c_f(0.03), _lib.ptr(rmd), _lib.ptr(rvd), None,
                                 _lib.ptr(scale), _lib.ptr(shift), None, None, 0, _lib.stream()))
     sc = gamma / (rv + 1e-3).sqrt()
     assert torch.allclose(scale.cpu(), sc, rtol=1e-5) and torch.allclose(shift.cpu(), beta - rm * sc, atol=1e-5)

@@ -1,0 +1,712 @@
+"""YOLOV5m: drop-in for the reference network (reference model.py:178-239) running on hand-written sm_100a kernels.
+
+Same constructor, module tree / state_dict keys (481 entries for first_out=48, nc=80), ``forward()`` contract
+(list of three ``(B, 3, H/s, W/s, 5+nc)`` raw-logit tensors, autograd-connected in train mode) and head attributes
+(``model.head.nc/nl/naxs/anchors/stride``) as the reference, so it drops in under train.py / detect.py.
+
+What is different underneath (B200-first, not a translation):
+  * activations are NHWC bf16; every ``torch.cat`` of the reference (model.py:91,112,226,230) is a channel slice of a
+    shared buffer that the producing kernels write directly (zero-copy concat);
+  * Conv2d fprop / dgrad / wgrad are tcgen05 implicit GEMMs (csrc/conv_igemm.cu, csrc/conv_wgrad.cu); the conv epilogue
+    emits the BatchNorm batch-statistic partials, BN-apply + SiLU (+ residual, + nearest-2x upsample) is one pass;
+  * eval mode folds BN into the conv epilogue (scale/shift + SiLU in registers, model.py:17-23);
+  * the 6x6/s2 stem runs as a 3x3/s1 conv over a space-to-depth staging of the image;
+  * parameters live in ONE flat fp32 buffer (the tensors in ``state_dict()`` are views of it, conv weights in
+    channels-last memory order = the kernels' [Cout][tap][Cin] packing); gradients land in one flat fp32 buffer that is
+    also the NCCL all-reduce bucket and the input of the fused clip+Adam kernel.
+There is no CPU / PyTorch fallback: calling forward without the CUDA library or on CPU tensors raises.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+BN_EPS = 1e-3      # reference model.py:17
+BN_MOMENTUM = 0.03
+HEAD_PAD = 256     # head conv Cout = 3*(5+nc) padded to a multiple of 16 for the bf16 gradient tensor
+
+
+# ------------------------------------------------------------------------------------------------ module tree
+class _Conv(nn.Module):
+    """Parameter holder for an nn.Conv2d (reference model.py:16,162).  The arithmetic runs in the engine."""
+
+    def __init__(self, cin, cout, k, stride, bias=False):
+        super().__init__()
+        self.in_channels, self.out_channels, self.kernel_size, self.stride = cin, cout, k, stride
+        ref = nn.Conv2d(cin, cout, k, stride, k // 2 if k != 6 else 2, bias=bias)  # same init / RNG draws as the reference
+        self.weight = nn.Parameter(ref.weight.data)
+        self.bias = nn.Parameter(ref.bias.data) if bias else None
+
+    def extra_repr(self):
+        return f"{self.in_channels}, {self.out_channels}, k={self.kernel_size}, s={self.stride}, bias={self.bias is not None}"
+
+    def forward(self, x):
+        raise _lib.YBError("sub-modules hold parameters only; call YOLOV5m.forward (fused sm_100a engine)")
+
+
+class _BN(nn.Module):
+    """Parameter / buffer holder for nn.BatchNorm2d(eps=1e-3, momentum=0.03) (reference model.py:17)."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.num_features, self.eps, self.momentum = c, BN_EPS, BN_MOMENTUM
+        self.weight = nn.Parameter(torch.ones(c))
+        self.bias = nn.Parameter(torch.zeros(c))
+        self.register_buffer("running_mean", torch.zeros(c))
+        self.register_buffer("running_var", torch.ones(c))
+        self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
+
+    forward = _Conv.forward
+
+
+class CBL(nn.Module):  # reference model.py:12-28
+    def __init__(self, cin, cout, k, stride, padding=None):
+        super().__init__()
+        self.cbl = nn.Sequential(_Conv(cin, cout, k, stride), _BN(cout), nn.SiLU(inplace=True))
+
+    forward = _Conv.forward
+
+
+class Bottleneck(nn.Module):  # reference model.py:32-50
+    def __init__(self, cin, cout, width_multiple=1):
+        super().__init__()
+        c_ = int(width_multiple * cin)
+        self.c1 = CBL(cin, c_, 1, 1)
+        self.c2 = CBL(c_, cout, 3, 1)
+
+    forward = _Conv.forward
+
+
+class C3(nn.Module):  # reference model.py:54-92
+    def __init__(self, cin, cout, width_multiple=1, depth=1, backbone=True):
+        super().__init__()
+        c_ = int(width_multiple * cin)
+        self.is_backbone, self.depth, self.hidden = backbone, depth, c_
+        self.c1 = CBL(cin, c_, 1, 1)
+        self.c_skipped = CBL(cin, c_, 1, 1)
+        if backbone:
+            self.seq = nn.Sequential(*[Bottleneck(c_, c_, 1) for _ in range(depth)])
+        else:
+            self.seq = nn.Sequential(*[nn.Sequential(CBL(c_, c_, 1, 1), CBL(c_, c_, 3, 1)) for _ in range(depth)])
+        self.c_out = CBL(c_ * 2, cout, 1, 1)
+
+    forward = _Conv.forward
+
+
+class SPPF(nn.Module):  # reference model.py:96-112
+    def __init__(self, cin, cout):
+        super().__init__()
+        c_ = cin // 2
+        self.c1 = CBL(cin, c_, 1, 1)
+        self.pool = nn.MaxPool2d(kernel_size=5, stride=1, padding=2)
+        self.c_out = CBL(c_ * 4, cout, 1, 1)
+
+    forward = _Conv.forward
+
+
+class HEADS(nn.Module):  # reference model.py:143-175
+    def __init__(self, nc=80, anchors=(), ch=()):
+        super().__init__()
+        self.nc = nc
+        self.nl = len(anchors)
+        self.naxs = len(anchors[0])
+        self.stride = [8, 16, 32]
+        anchors_ = torch.tensor(anchors).float().view(self.nl, -1, 2) / torch.tensor(self.stride).repeat(6, 1).T.reshape(3, 3, 2)
+        self.register_buffer("anchors", anchors_)
+        self.out_convs = nn.ModuleList([_Conv(c, (5 + nc) * self.naxs, 1, 1, bias=True) for c in ch])
+
+    forward = _Conv.forward
+
+
+# ------------------------------------------------------------------------------------------------ engine pieces
+class _Buf:
+    """NHWC bf16 allocation (+ same-shaped gradient when training)."""
+
+    def __init__(self, N, H, W, C, grad, dev):
+        self.N, self.H, self.W, self.C = N, H, W, C
+        self.t = torch.empty(N, H, W, C, device=dev, dtype=torch.bfloat16)
+        self.g = torch.empty(N, H, W, C, device=dev, dtype=torch.bfloat16) if grad else None
+        self.gw = np.zeros(C, bool)  # (backward-list construction) which gradient channels already hold a value
+        self.pending = []            # identity gradient contributions (c0, C, src_view) not yet materialised
+
+    def v(self, c0=0, C=None):
+        return _View(self, c0, self.C - c0 if C is None else C)
+
+
+class _View:
+    def __init__(self, buf, c0, C):
+        self.buf, self.c0, self.C = buf, c0, C
+        self.N, self.H, self.W, self.pitch = buf.N, buf.H, buf.W, buf.C
+        self.npix = buf.N * buf.H * buf.W
+
+    @property
+    def ptr(self):
+        return self.buf.t.data_ptr() + 2 * self.c0
+
+    @property
+    def gptr(self):
+        return self.buf.g.data_ptr() + 2 * self.c0
+
+    def tensor(self):
+        return self.buf.t[..., self.c0:self.c0 + self.C]
+
+    def gtensor(self):
+        return self.buf.g[..., self.c0:self.c0 + self.C]
+
+
+class _LayerRec:
+    """Flat-buffer bookkeeping of one conv (+BN)."""
+    __slots__ = ("name", "conv", "bn", "cin", "cout", "k", "stride", "w_off", "g_off", "b_off", "wt_off", "bias_off",
+                 "rm", "rv", "nbt", "is_stem", "is_head", "kin", "kk", "cout_pad")
+
+
+class _Engine:
+    """Static launch plan for one (batch, height, width, mode): buffers, TMA plans, forward / backward op lists."""
+
+    def __init__(self, net, B, H, W, train):
+        self.net, self.B, self.H, self.W, self.train = net, B, H, W, train
+        self.dev = net._pflat.device
+        self.L = _lib.lib()
+        self.fwd_ops, self.bwd_ops, self.tape = [], [], []
+        self.plans = []
+        self.bufs = []
+        self.nbytes = 0
+        L = self.L
+        self.max_rows = L.yb_conv_max_partials()
+        self.red_rows = L.yb_bwd_reduce_max_rows()
+        # per-layer fp32 scratch: stats partials + scale/shift/mean/invstd
+        tot_c = sum(r.cout for r in net._recs if not r.is_head)
+        self.stat_pool = torch.zeros(tot_c * (2 * self.max_rows + 4), device=self.dev, dtype=torch.float32)
+        self._stat_off = 0
+        if train:
+            cmax = max(HEAD_PAD, max(r.cout for r in net._recs))
+            self.red_partial = torch.zeros(self.red_rows * 2 * cmax, device=self.dev, dtype=torch.float32)
+            self.coef = torch.zeros(2 * cmax, device=self.dev, dtype=torch.float32)
+            self.wg_ws = torch.empty(32 << 20, device=self.dev, dtype=torch.float32)
+            self.dy = None  # allocated after the forward build (max conv output size)
+            self._dy_elems = 0
+        self._build()
+
+    # -- allocation helpers
+    def buf(self, N, H, W, C, grad=None):
+        b = _Buf(N, H, W, C, self.train if grad is None else grad, self.dev)
+        self.bufs.append(b)
+        self.nbytes += b.t.numel() * 2 * (2 if b.g is not None else 1)
+        return b
+
+    def _stat(self, n):
+        t = self.stat_pool[self._stat_off:self._stat_off + n]
+        self._stat_off += n
+        return t
+
+    # -- forward construction
+    def cbl(self, mod, xin, out, res=None, up=None):
+        net, L = self.net, self.L
+        r = net._rec_of[mod.cbl[0]]
+        Ho, Wo = xin.H // (1 if r.is_stem else r.stride), xin.W // (1 if r.is_stem else r.stride)
+        assert (out.H, out.W, out.C) == (Ho, Wo, r.cout), (r.name, out.H, out.W, out.C)
+        C = r.cout
+        scale, shift = self._stat(C), self._stat(C)
+        w_ptr = net._wstem.data_ptr() if r.is_stem else net._wfwd.data_ptr() + 2 * r.w_off
+        gam, bet = net._pflat.data_ptr() + 4 * r.g_off, net._pflat.data_ptr() + 4 * r.b_off
+        rm, rv, nbt = r.rm.data_ptr(), r.rv.data_ptr(), r.nbt.data_ptr()
+        k, s = (3, 1) if r.is_stem else (r.k, r.stride)
+        if not self.train:
+            # eval: BN folded into the conv epilogue (running statistics), SiLU + residual in registers
+            plan = _lib.checkp(L.yb_conv_fwd_plan(xin.ptr, xin.N, xin.H, xin.W, xin.C, xin.pitch, w_ptr, C, k, s, out.ptr,
+                                                  out.pitch, 0, scale.data_ptr(), shift.data_ptr(), 1,
+                                                  res.ptr if res is not None else None, res.pitch if res is not None else 0,
+                                                  None, None, 3, 85))
+            self.plans.append(plan)
+            sp, hp = scale.data_ptr(), shift.data_ptr()
+
+            def op(st, plan=plan):
+                _lib.check(L.yb_bn_finalize(None, 0, C, 1.0, gam, bet, BN_EPS, BN_MOMENTUM, rm, rv, None, sp, hp, None, None, 0, st))
+                _lib.check(L.yb_plan_run(plan, st))
+            self.fwd_ops.append(op)
+            if up is not None:
+                self.fwd_ops.append(lambda st: _lib.check(L.yb_upsample2x_fwd(out.ptr, out.pitch, out.N, out.H, out.W, C,
+                                                                               up.ptr, up.pitch, st)))
+            return
+        mean, invstd = self._stat(C), self._stat(C)
+        stats = self._stat(2 * self.max_rows * C)
+        y = self.buf(xin.N, Ho, Wo, C, grad=False).v()
+        rows = ctypes.c_int(0)
+        plan = _lib.checkp(L.yb_conv_fwd_plan(xin.ptr, xin.N, xin.H, xin.W, xin.C, xin.pitch, w_ptr, C, k, s, y.ptr, C, 0,
+                                              None, None, 0, None, 0, stats.data_ptr(), ctypes.byref(rows), 3, 85))
+        self.plans.append(plan)
+        nrows, count = rows.value, float(y.npix)
+        ptrs = (stats.data_ptr(), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), invstd.data_ptr())
+        resp, resl = (res.ptr, res.pitch) if res is not None else (None, 0)
+        upp, upl = (up.ptr, up.pitch) if up is not None else (None, 0)
+
+        def op(st):
+            _lib.check(L.yb_plan_run(plan, st))
+            _lib.check(L.yb_bn_finalize(ptrs[0], nrows, C, count, gam, bet, BN_EPS, BN_MOMENTUM, rm, rv, nbt, ptrs[1], ptrs[2],
+                                        ptrs[3], ptrs[4], 1, st))
+            _lib.check(L.yb_bn_act_fwd(y.ptr, C, y.N, y.H, y.W, C, ptrs[1], ptrs[2], resp, resl, out.ptr, out.pitch, upp,
+                                       upl, st))
+        self.fwd_ops.append(op)
+        self._dy_elems = max(self._dy_elems, y.npix * C)
+        self.tape.append(("cbl", r, xin, out, y, res, up, ptrs))
+
+    def c3(self, mod, xin, out):
+        c_ = mod.hidden
+        N, H, W = xin.N, xin.H, xin.W
+        cat = self.buf(N, H, W, 2 * c_)
+        a = self.buf(N, H, W, c_).v()
+        self.cbl(mod.c1, xin, a)
+        for j in range(mod.depth):
+            blk = mod.seq[j]
+            first, second = (blk.c1, blk.c2) if mod.is_backbone else (blk[0], blk[1])
+            h = self.buf(N, H, W, c_).v()
+            self.cbl(first, a, h)
+            dst = cat.v(0, c_) if j == mod.depth - 1 else self.buf(N, H, W, c_).v()
+            self.cbl(second, h, dst, res=a if mod.is_backbone else None)
+            a = dst
+        self.cbl(mod.c_skipped, xin, cat.v(c_, c_))
+        self.cbl(mod.c_out, cat.v(), out)
+
+    def sppf(self, mod, xin, out):
+        L = self.L
+        c_ = xin.C // 2
+        N, H, W = xin.N, xin.H, xin.W
+        cat = self.buf(N, H, W, 4 * c_)
+        self.cbl(mod.c1, xin, cat.v(0, c_))
+        for i in range(3):
+            src, dst = cat.v(i * c_, c_), cat.v((i + 1) * c_, c_)
+            am = torch.empty(N, H, W, c_, device=self.dev, dtype=torch.uint8) if self.train else None
+            amp = am.data_ptr() if am is not None else None
+            self.fwd_ops.append(lambda st, src=src, dst=dst, amp=amp: _lib.check(
+                L.yb_maxpool5_fwd(src.ptr, src.pitch, N, H, W, c_, dst.ptr, dst.pitch, amp, st)))
+            if self.train:
+                self.tape.append(("pool", src, dst, am))
+        self.cbl(mod.c_out, cat.v(), out)
+
+    def head(self, i, xin):
+        net, L = self.net, self.L
+        r = net._rec_of[net.head.out_convs[i]]
+        na, no = net.head.naxs, 5 + net.head.nc
+        out = torch.empty(xin.N, na, xin.H, xin.W, no, device=self.dev, dtype=torch.float32)
+        plan = _lib.checkp(L.yb_conv_fwd_plan(xin.ptr, xin.N, xin.H, xin.W, xin.C, xin.pitch,
+                                              net._wfwd.data_ptr() + 2 * r.w_off, r.cout, 1, 1, out.data_ptr(), r.cout, 1,
+                                              None, net._pflat.data_ptr() + 4 * r.bias_off, 0, None, 0, None, None, na, no))
+        self.plans.append(plan)
+        self.fwd_ops.append(lambda st: _lib.check(L.yb_plan_run(plan, st)))
+        self.outs.append(out)
+        if self.train:
+            dyh = torch.zeros(xin.N, xin.H, xin.W, HEAD_PAD, device=self.dev, dtype=torch.bfloat16)
+            self.head_dy.append(dyh)
+            self.tape.append(("head", r, xin, dyh))
+
+    def _build(self):
+        net, B, H, W = self.net, self.B, self.H, self.W
+        bb, nk = net.backbone, net.neck
+        c = net._first_out
+        self.outs, self.head_dy = [], []
+        self.x16 = self.buf(B, H // 2, W // 2, 16, grad=False)
+        b0 = self.buf(B, H // 2, W // 2, c); self.cbl(bb[0], self.x16.v(), b0.v())
+        b1 = self.buf(B, H // 4, W // 4, 2 * c); self.cbl(bb[1], b0.v(), b1.v())
+        b2 = self.buf(B, H // 4, W // 4, 2 * c); self.c3(bb[2], b1.v(), b2.v())
+        b3 = self.buf(B, H // 8, W // 8, 4 * c); self.cbl(bb[3], b2.v(), b3.v())
+        cat3 = self.buf(B, H // 8, W // 8, 8 * c)      # [up(N2) | tapA]   (model.py:226, second pass)
+        tapA = cat3.v(4 * c, 4 * c); self.c3(bb[4], b3.v(), tapA)
+        b5 = self.buf(B, H // 16, W // 16, 8 * c); self.cbl(bb[5], tapA, b5.v())
+        cat1 = self.buf(B, H // 16, W // 16, 16 * c)   # [up(N0) | tapB]   (model.py:226, first pass)
+        tapB = cat1.v(8 * c, 8 * c); self.c3(bb[6], b5.v(), tapB)
+        b7 = self.buf(B, H // 32, W // 32, 16 * c); self.cbl(bb[7], tapB, b7.v())
+        b8 = self.buf(B, H // 32, W // 32, 16 * c); self.c3(bb[8], b7.v(), b8.v())
+        b9 = self.buf(B, H // 32, W // 32, 16 * c); self.sppf(bb[9], b8.v(), b9.v())
+        cat7 = self.buf(B, H // 32, W // 32, 16 * c)   # [neck.6 | N0]     (model.py:230)
+        N0 = cat7.v(8 * c, 8 * c); self.cbl(nk[0], b9.v(), N0, up=cat1.v(0, 8 * c))
+        n1 = self.buf(B, H // 16, W // 16, 8 * c); self.c3(nk[1], cat1.v(), n1.v())
+        cat5 = self.buf(B, H // 16, W // 16, 8 * c)    # [neck.4 | N2]
+        N2 = cat5.v(4 * c, 4 * c); self.cbl(nk[2], n1.v(), N2, up=cat3.v(0, 4 * c))
+        P3 = self.buf(B, H // 8, W // 8, 4 * c); self.c3(nk[3], cat3.v(), P3.v())
+        self.cbl(nk[4], P3.v(), cat5.v(0, 4 * c))
+        P4 = self.buf(B, H // 16, W // 16, 8 * c); self.c3(nk[5], cat5.v(), P4.v())
+        self.cbl(nk[6], P4.v(), cat7.v(0, 8 * c))
+        P5 = self.buf(B, H // 32, W // 32, 16 * c); self.c3(nk[7], cat7.v(), P5.v())
+        for i, p in enumerate((P3, P4, P5)):
+            self.head(i, p.v())
+        if self.train:
+            self.dy = torch.empty(self._dy_elems, device=self.dev, dtype=torch.bfloat16)
+            self.nbytes += self._dy_elems * 2
+            self._build_backward()
+
+    # -- backward construction (reverse tape); gradient fan-in is resolved statically
+    def _contrib_state(self, view):
+        w = view.buf.gw[view.c0:view.c0 + view.C]
+        if w.all():
+            return True
+        assert not w.any(), "partially written gradient slice"
+        return False
+
+    def _flush_pending(self, view):
+        """materialise identity contributions that target `view` (called before its gradient is consumed)."""
+        L = self.L
+        keep = []
+        for (c0, C, src) in view.buf.pending:
+            if c0 >= view.c0 and c0 + C <= view.c0 + view.C:
+                tgt = view.buf.v(c0, C)
+                acc = 1 if self._contrib_state(tgt) else 0
+                self.bwd_ops.append(lambda st, g, src=src, tgt=tgt, acc=acc: _lib.check(
+                    L.yb_add_into(src.gptr, src.pitch, tgt.gptr, tgt.pitch, tgt.npix, tgt.C, acc, st)))
+                view.buf.gw[c0:c0 + C] = True
+            else:
+                keep.append((c0, C, src))
+        view.buf.pending = keep
+
+    def _take_pending_exact(self, view):
+        for i, (c0, C, src) in enumerate(view.buf.pending):
+            if c0 == view.c0 and C == view.C:
+                del view.buf.pending[i]
+                return src
+        return None
+
+    def _build_backward(self):
+        net, L = self.net, self.L
+        dy_ptr = self.dy.data_ptr()
+        redp, coefp = self.red_partial.data_ptr(), self.coef.data_ptr()
+        ws, wsn = self.wg_ws.data_ptr(), self.wg_ws.numel()
+        for rec in reversed(self.tape):
+            kind = rec[0]
+            if kind == "head":
+                _, r, xin, dyh = rec
+                dyp = dyh.data_ptr()
+                npix = xin.npix
+                wplan = _lib.checkp(L.yb_conv_wgrad_plan(xin.ptr, xin.N, xin.H, xin.W, xin.C, xin.pitch, dyp, HEAD_PAD,
+                                                         HEAD_PAD, 1, 1, ws, wsn, 0))
+                acc = 1 if self._contrib_state(xin) else 0
+                dplan = _lib.checkp(L.yb_conv_dgrad_plan(dyp, xin.N, xin.H, xin.W, HEAD_PAD, HEAD_PAD,
+                                                         net._wdg.data_ptr() + 2 * r.wt_off, xin.C, 1, 1, xin.gptr,
+                                                         xin.pitch, xin.gptr if acc else None, xin.pitch if acc else 0))
+                self.plans += [wplan, dplan]
+                xin.buf.gw[xin.c0:xin.c0 + xin.C] = True
+                rows = ctypes.c_int(0)
+
+                def op(st, g, r=r, dyp=dyp, npix=npix, wplan=wplan, dplan=dplan, rows=rows):
+                    _lib.check(L.yb_colsum(dyp, HEAD_PAD, npix, HEAD_PAD, redp, ctypes.byref(rows), st))
+                    _lib.check(L.yb_reduce_rows(redp, rows.value, 2 * HEAD_PAD, r.cout, g + 4 * r.bias_off, 0, st))
+                    _lib.check(L.yb_wgrad_plan_run(wplan, g + 4 * r.w_off, r.cout, None, 0, st))
+                    _lib.check(L.yb_plan_run(dplan, st))
+                self.bwd_ops.append(op)
+            elif kind == "pool":
+                _, src, dst, am = rec
+                self._flush_pending(dst)
+                acc = 1 if self._contrib_state(src) else 0
+                src.buf.gw[src.c0:src.c0 + src.C] = True
+                self.bwd_ops.append(lambda st, g, src=src, dst=dst, am=am, acc=acc: _lib.check(
+                    L.yb_maxpool5_bwd(dst.gptr, dst.pitch, am.data_ptr(), src.N, src.H, src.W, src.C, src.gptr, src.pitch,
+                                      acc, st)))
+            else:
+                _, r, xin, out, y, res, up, ptrs = rec
+                C, npix = r.cout, y.npix
+                k, s = (3, 1) if r.is_stem else (r.k, r.stride)
+                self._flush_pending(out)
+                assert self._contrib_state(out), f"{r.name}: output gradient never produced"
+                if up is not None:
+                    assert self._contrib_state(up), f"{r.name}: upsampled gradient never produced"
+                    self.bwd_ops.append(lambda st, g, up=up, out=out: _lib.check(
+                        L.yb_upsample2x_bwd(up.gptr, up.pitch, out.N, out.H, out.W, out.C, out.gptr, out.pitch, 1, st)))
+                if res is not None:
+                    res.buf.pending.append((res.c0, res.C, out))
+                wplan = _lib.checkp(L.yb_conv_wgrad_plan(xin.ptr, xin.N, xin.H, xin.W, xin.C, xin.pitch, dy_ptr, C, C, k, s,
+                                                         ws, wsn, 0))
+                self.plans.append(wplan)
+                dplan = None
+                if not r.is_stem:
+                    src = self._take_pending_exact(xin)
+                    written = self._contrib_state(xin)
+                    if src is not None and written:  # both an identity source and an earlier value: fold the identity first
+                        self.bwd_ops.append(lambda st, g, src=src, xin=xin: _lib.check(
+                            L.yb_add_into(src.gptr, src.pitch, xin.gptr, xin.pitch, xin.npix, xin.C, 1, st)))
+                        src = None
+                    if src is not None:
+                        addp, addl = src.gptr, src.pitch
+                    elif written:
+                        addp, addl = xin.gptr, xin.pitch
+                    else:
+                        addp, addl = None, 0
+                    dplan = _lib.checkp(L.yb_conv_dgrad_plan(dy_ptr, xin.N, xin.H, xin.W, C, C,
+                                                             net._wdg.data_ptr() + 2 * r.wt_off, xin.C, k, s, xin.gptr,
+                                                             xin.pitch, addp, addl))
+                    self.plans.append(dplan)
+                    xin.buf.gw[xin.c0:xin.c0 + xin.C] = True
+                mapp = net._stem_map.data_ptr() if r.is_stem else None
+                rows = ctypes.c_int(0)
+                count = float(npix)
+
+                def op(st, g, r=r, out=out, y=y, ptrs=ptrs, C=C, npix=npix, wplan=wplan, dplan=dplan, mapp=mapp, rows=rows,
+                       count=count):
+                    _lib.check(L.yb_bn_act_bwd_reduce(out.gptr, out.pitch, y.ptr, C, npix, C, ptrs[1], ptrs[2], ptrs[3],
+                                                      ptrs[4], redp, ctypes.byref(rows), st))
+                    _lib.check(L.yb_bn_bwd_finalize(redp, rows.value, C, count, g + 4 * r.g_off, g + 4 * r.b_off, coefp, 0, st))
+                    _lib.check(L.yb_bn_act_bwd_apply(out.gptr, out.pitch, y.ptr, C, npix, C, ptrs[1], ptrs[2], ptrs[3],
+                                                     ptrs[4], coefp, dy_ptr, C, st))
+                    _lib.check(L.yb_wgrad_plan_run(wplan, g + 4 * r.w_off, C, mapp, 0, st))
+                    if dplan is not None:
+                        _lib.check(L.yb_plan_run(dplan, st))
+                self.bwd_ops.append(op)
+
+    # -- execution
+    def run_forward(self, x):
+        L = self.L
+        st = _lib.stream()
+        dt = 0 if x.dtype == torch.float32 else 1
+        _lib.check(L.yb_prep_input(x.data_ptr(), dt, self.B, self.H, self.W, self.x16.t.data_ptr(), st))
+        for op in self.fwd_ops:
+            op(st)
+        return self.outs
+
+    def run_backward(self, gflat):
+        st = _lib.stream()
+        g = gflat.data_ptr()
+        for op in self.bwd_ops:
+            op(st, g)
+
+    def __del__(self):
+        try:
+            for p in self.plans:
+                self.L.yb_plan_destroy(p)
+        except Exception:
+            pass
+
+
+class _NetFn(torch.autograd.Function):
+    """Autograd boundary: forward / backward of the whole network are the engine's launch lists."""
+
+    @staticmethod
+    def forward(ctx, net, eng, x, *params):
+        outs = eng.run_forward(x)
+        ctx.net, ctx.eng = net, eng
+        eng.head_ready = False
+        res = tuple(o.view_as(o) for o in outs)  # fresh autograd outputs over the engine's head tensors
+        return res
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        net, eng = ctx.net, ctx.eng
+        L = _lib.lib()
+        st = _lib.stream()
+        if not eng.head_ready:  # generic path: dense fp32 gradients from an arbitrary loss
+            for i, go in enumerate(gouts):
+                dyh = eng.head_dy[i]
+                if go is None:
+                    dyh.zero_()
+                    continue
+                go = go.contiguous().float()
+                B, na, H, W, no = go.shape
+                _lib.check(L.yb_head_grad_pack(go.data_ptr(), B, na, H, W, no, dyh.data_ptr(), HEAD_PAD, st))
+        eng.head_ready = False
+        gflat = net._grad_target()
+        eng.run_backward(gflat)
+        grads = tuple(net._grad_views(gflat))
+        return (None, None, None) + grads
+
+
+# ------------------------------------------------------------------------------------------------ the network
+class YOLOV5m(nn.Module):
+    """Same signature as the reference: YOLOV5m(first_out, nc=80, anchors=(), ch=(), inference=False)  (model.py:178-180)."""
+
+    def __init__(self, first_out, nc=80, anchors=(), ch=(), inference=False):
+        super().__init__()
+        c = first_out
+        self.inference = inference
+        self._first_out = c
+        self.backbone = nn.ModuleList([
+            CBL(3, c, 6, 2), CBL(c, c * 2, 3, 2), C3(c * 2, c * 2, 0.5, 2), CBL(c * 2, c * 4, 3, 2),
+            C3(c * 4, c * 4, 0.5, 4), CBL(c * 4, c * 8, 3, 2), C3(c * 8, c * 8, 0.5, 6), CBL(c * 8, c * 16, 3, 2),
+            C3(c * 16, c * 16, 0.5, 2), SPPF(c * 16, c * 16)])
+        self.neck = nn.ModuleList([
+            CBL(c * 16, c * 8, 1, 1), C3(c * 16, c * 8, 0.25, 2, backbone=False), CBL(c * 8, c * 4, 1, 1),
+            C3(c * 8, c * 4, 0.25, 2, backbone=False), CBL(c * 4, c * 4, 3, 2), C3(c * 8, c * 8, 0.5, 2, backbone=False),
+            CBL(c * 8, c * 8, 3, 2), C3(c * 16, c * 16, 0.5, 2, backbone=False)])
+        self.head = HEADS(nc=nc, anchors=anchors, ch=ch)
+        assert tuple(ch) == (c * 4, c * 8, c * 16), "ch must be (4, 8, 16) x first_out (reference call sites)"
+        assert (5 + nc) * self.head.naxs <= HEAD_PAD, "head width exceeds the padded gradient width"
+        assert c % 16 == 0, "first_out must be a multiple of 16 (bf16 NHWC channel alignment)"
+        self._engines = {}
+        self._packed_sig = None
+        self._gflat = [None, None]
+        self._flatten()
+
+    # -- flat parameter storage -----------------------------------------------------------------
+    def _flatten(self):
+        """(re)build the flat fp32 master buffer and point every Parameter at its slice."""
+        params = list(self.parameters())
+        dev = params[0].device
+        recs, rec_of = [], {}
+        off = 0
+        offs = {}
+        for p in params:
+            offs[id(p)] = off
+            off += (p.numel() + 3) // 4 * 4  # 16-byte aligned slices
+        flat = torch.zeros(off, device=dev, dtype=torch.float32)
+        for p in params:
+            o, n = offs[id(p)], p.numel()
+            if p.dim() == 4:
+                co, ci, kh, kw = p.shape
+                view = flat[o:o + n].view(co, kh, kw, ci).permute(0, 3, 1, 2)  # channels-last: memory = [Cout][tap][Cin]
+            else:
+                view = flat[o:o + n].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+        self._pflat = flat
+        self._poffs = [(offs[id(p)], p.numel()) for p in params]
+        wt_off = 0
+        for name, m in self.named_modules():
+            if isinstance(m, CBL):
+                conv, bn = m.cbl[0], m.cbl[1]
+                r = _LayerRec()
+                r.name, r.conv, r.bn = name, conv, bn
+                r.cin, r.cout, r.k, r.stride = conv.in_channels, conv.out_channels, conv.kernel_size, conv.stride
+                r.is_stem, r.is_head = conv.kernel_size == 6, False
+                r.w_off, r.g_off, r.b_off = offs[id(conv.weight)], offs[id(bn.weight)], offs[id(bn.bias)]
+                r.bias_off = -1
+                r.rm, r.rv, r.nbt = bn.running_mean, bn.running_var, bn.num_batches_tracked
+                r.cout_pad = r.cout
+            elif isinstance(m, _Conv) and m.bias is not None:
+                r = _LayerRec()
+                r.name, r.conv, r.bn = name, m, None
+                r.cin, r.cout, r.k, r.stride = m.in_channels, m.out_channels, 1, 1
+                r.is_stem, r.is_head = False, True
+                r.w_off, r.bias_off, r.g_off, r.b_off = offs[id(m.weight)], offs[id(m.bias)], -1, -1
+                r.rm = r.rv = r.nbt = None
+                r.cout_pad = HEAD_PAD
+            else:
+                continue
+            if r.is_stem:
+                r.wt_off = -1
+            else:
+                r.wt_off = wt_off
+                wt_off += r.cin * r.k * r.k * r.cout_pad
+            recs.append(r)
+            rec_of[r.conv] = r
+        self._recs, self._rec_of, self._wdg_elems = recs, rec_of, wt_off
+        self._engines = {}
+        self._packed_sig = None
+        self._gflat = [None, None]
+        if dev.type == "cuda":
+            self._alloc_device_side()
+
+    def _alloc_device_side(self):
+        dev = self._pflat.device
+        self._wfwd = torch.zeros(self._pflat.numel(), device=dev, dtype=torch.bfloat16)
+        self._wdg = torch.zeros(self._wdg_elems, device=dev, dtype=torch.bfloat16)
+        stem = next(r for r in self._recs if r.is_stem)
+        self._wstem = torch.zeros(stem.cout * 9 * 16, device=dev, dtype=torch.bfloat16)
+        rows, cum = [], 0
+        for r in self._recs:
+            if r.is_stem:
+                continue
+            n = r.cin * r.k * r.k * r.cout_pad
+            rows.append([r.w_off, r.wt_off, r.cout, r.k * r.k, r.cin, r.cout_pad, cum, cum + n])
+            cum += n
+        self._dg_table = torch.tensor(rows, dtype=torch.int64, device=dev)
+        # stem wgrad: packed 3x3/16ch gradient index -> offset inside the [Cout][6][6][3] master slice
+        co, tap, ch = np.meshgrid(np.arange(stem.cout), np.arange(9), np.arange(16), indexing="ij")
+        c, rs = ch % 3, ch // 3
+        rr, ss, a, b = rs >> 1, rs & 1, tap // 3, tap % 3
+        m = ((co * 6 + 2 * a + rr) * 6 + 2 * b + ss) * 3 + c
+        m[ch >= 12] = -1
+        self._stem_map = torch.from_numpy(m.reshape(-1).astype(np.int32)).to(dev)
+        self._stem_rec = stem
+
+    def _apply(self, fn, recurse=True):
+        super()._apply(fn)
+        p0 = next(self.parameters())
+        if p0.dtype != torch.float32:
+            raise TypeError("YOLOV5m (B200): master weights are fp32 and compute is bf16; dtype casts of the module are not supported")
+        self._flatten()
+        return self
+
+    def _param_signature(self):
+        return sum(p._version for p in self.parameters())
+
+    def refresh_packed(self, force=False):
+        """bf16 tensor-core operands derived from the fp32 master weights (re-run after any parameter update)."""
+        sig = self._param_signature()
+        if not force and sig == self._packed_sig:
+            return
+        L, st = _lib.lib(), _lib.stream()
+        _lib.check(L.yb_cast_bf16(self._pflat.data_ptr(), self._wfwd.data_ptr(), self._pflat.numel(), st))
+        self._repack_derived(st)
+        self._packed_sig = sig
+
+    def _repack_derived(self, st):
+        L = _lib.lib()
+        _lib.check(L.yb_repack_dgrad(self._pflat.data_ptr(), self._wdg.data_ptr(), self._dg_table.data_ptr(),
+                                     self._dg_table.shape[0], self._wdg_elems, st))
+        s = self._stem_rec
+        _lib.check(L.yb_repack_stem(self._pflat.data_ptr() + 4 * s.w_off, self._wstem.data_ptr(), s.cout, st))
+
+    # -- gradients ---------------------------------------------------------------------------------
+    def _grad_target(self):
+        """flat fp32 gradient buffer the next backward writes: buffer 0 unless live .grad tensors alias it
+        (gradient accumulation across backward calls), then buffer 1."""
+        if self._gflat[0] is None:
+            self._gflat[0] = torch.zeros_like(self._pflat)
+        base = self._gflat[0].untyped_storage().data_ptr()
+        for p in self.parameters():
+            if p.grad is not None and p.grad.untyped_storage().data_ptr() == base:
+                if self._gflat[1] is None:
+                    self._gflat[1] = torch.zeros_like(self._pflat)
+                return self._gflat[1]
+        return self._gflat[0]
+
+    def _grad_views(self, gflat):
+        out = []
+        for p, (o, n) in zip(self.parameters(), self._poffs):
+            if p.dim() == 4:
+                co, ci, kh, kw = p.shape
+                out.append(gflat[o:o + n].view(co, kh, kw, ci).permute(0, 3, 1, 2))
+            else:
+                out.append(gflat[o:o + n].view(p.shape))
+        return out
+
+    @property
+    def flat_params(self):
+        return self._pflat
+
+    @property
+    def flat_grads(self):
+        if self._gflat[0] is None:
+            self._gflat[0] = torch.zeros_like(self._pflat)
+        return self._gflat[0]
+
+    # -- forward -------------------------------------------------------------------------------------
+    def engine(self, B, H, W, train):
+        key = (B, H, W, bool(train))
+        e = self._engines.get(key)
+        if e is None:
+            if len(self._engines) >= 4:  # multi-scale training visits many shapes: keep the cache bounded
+                self._engines.pop(next(iter(self._engines)))
+            e = _Engine(self, B, H, W, train)
+            self._engines[key] = e
+        return e
+
+    def forward(self, x):
+        assert x.shape[2] % 32 == 0 and x.shape[3] % 32 == 0, "Width and Height aren't divisible by 32!"  # model.py:211
+        if not (torch.is_tensor(x) and x.is_cuda and self._pflat.is_cuda):
+            raise _lib.YBError("YOLOV5m (B200): model and input must be on a CUDA device (no CPU fallback)")
+        if x.dtype not in (torch.float32, torch.uint8):
+            x = x.float()
+        x = x.contiguous()
+        B, _, H, W = x.shape
+        self.refresh_packed()
+        train = self.training
+        eng = self.engine(B, H, W, train)
+        if train and torch.is_grad_enabled():
+            outs = _NetFn.apply(self, eng, x, *self.parameters())
+            outs = list(outs)
+            for o in outs:
+                o._yb_engine = eng
+            return outs
+        with torch.no_grad():
+            outs = eng.run_forward(x)
+        return [o.clone() for o in outs] if not train else list(outs)
