@@ -1,0 +1,390 @@
+// Box decode + per-image NMS on the GPU (sm_100a; HBM/latency-bound fp32 + integer work, no tensor cores).
+//
+// Replaces, for the detect / eval path of the reference:
+//   cells_to_bboxes(is_pred=True)   utils/plot_utils.py:10-40   sigmoid, grid/anchor decode, class argmax
+//   non_max_suppression             utils/bboxes_utils.py:175-209  confidence filter, xywh->xyxy, +cls offset,
+//                                   torchvision.ops.nms (stable descending sort + greedy IoU suppression), first max_det rows
+//
+// decode_kernel     one warp per cell: coalesced 85-float row, warp arg-max (first maximum wins, like torch.argmax)
+// nms_image_kernel  ONE CTA PER IMAGE (B = 128 images ~ one per SM), three phases, no host round trip:
+//   1. ordered compaction of the candidates with score > threshold (block prefix sum -> original order preserved)
+//   2. stable LSD radix sort (4 x 8 bit) on the descending-score key; every warp owns a contiguous segment so its
+//      per-digit running offsets live in shared memory and ties keep their original order (= stable sort of
+//      torchvision: ties -> lower index first)
+//   3. greedy suppression in tiles of 512 sorted candidates: test against the kept list (<= max_det boxes in shared
+//      memory), then a 512x512 bit matrix + warp-serial resolve inside the tile; stops at max_det keeps, which
+//      yields exactly the first max_det rows the reference keeps after its full N^2 pass (bboxes_utils.py:202-203).
+// IoU arithmetic uses explicitly rounded fp32 ops (no FMA contraction) in torchvision's operation order so keep
+// sets are bit-exact.
+#include "../../include/yolov5m_b200.h"
+#include "common.cuh"
+
+#include <algorithm>
+
+namespace yb {
+
+__device__ __forceinline__ float sigmoid_t(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// ------------------------------------------------------------------------------------------------ decode
+__global__ void __launch_bounds__(256) decode_kernel(const float* __restrict__ p, long cells, int na, int H, int W, int no,
+                                                     float stride, float aw0, float ah0, float aw1, float ah1, float aw2,
+                                                     float ah2, const float* __restrict__ anchors_px, float* __restrict__ out,
+                                                     long rows_per_image, long level_off) {
+  const int lane = threadIdx.x & 31;
+  const long wglobal = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+  const long per_img = (long)na * H * W;
+  const int nc = no - 5;
+  for (long c = wglobal; c < cells; c += nwarps) {
+    const float* ps = p + c * no;
+    // class arg-max over sigmoid(logit): first maximum wins (torch.argmax), plot_utils.py:27
+    float bv = -1.f;
+    int bi = 0x7fffffff;
+    for (int k = lane; k < nc; k += 32) {
+      const float s = sigmoid_t(ps[5 + k]);
+      if (s > bv) {
+        bv = s;
+        bi = k;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) {
+        bv = ov;
+        bi = oi;
+      }
+    }
+    if (lane < 6) {
+      const long b = c / per_img, rem = c - b * per_img;
+      const int a = (int)(rem / ((long)H * W));
+      const long sp = rem - (long)a * H * W;
+      const int gy = (int)(sp / W), gx = (int)(sp - (long)gy * W);
+      float v;
+      if (lane == 0) {
+        v = (float)bi;
+      } else if (lane == 1) {
+        v = sigmoid_t(ps[4]);  // :24
+      } else if (lane < 4) {
+        const float s = sigmoid_t(ps[lane - 2]);
+        const float g = lane == 2 ? (float)gx : (float)gy;
+        v = __fmul_rn(__fsub_rn(__fadd_rn(__fmul_rn(2.f, s), g), 0.5f), stride);  // (2*s + grid - 0.5) * stride, :25
+      } else {
+        const float s = sigmoid_t(ps[lane - 2]);
+        const float t = __fmul_rn(2.f, s);
+        const float an = anchors_px[a * 2 + (lane - 4)];
+        v = __fmul_rn(__fmul_rn(t, t), an);  // (2*s)**2 * anchor_grid, :26
+      }
+      out[(b * rows_per_image + level_off + rem) * 6 + lane] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ NMS
+struct NmsParams {
+  const float* boxes;  // (B,N,6)
+  long N;
+  float iou_thr, thr;
+  int max_det;
+  uint32_t *keys0, *keys1, *idx0, *idx1;  // [B][N] scratch
+  float* out;                              // [B][max_det][6]
+  int* out_count;                          // [B]
+  int* out_index;                          // [B][max_det] or null
+  int* cand_count;                         // [B] or null
+};
+
+static constexpr int kNmsThreads = 1024;
+static constexpr int kTile = 512;
+static constexpr int kTileWords = kTile / 32;
+
+__device__ __forceinline__ bool iou_gt(float ix1, float iy1, float ix2, float iy2, float iarea, float jx1, float jy1,
+                                       float jx2, float jy2, float jarea, float thr) {
+  const float xx1 = fmaxf(ix1, jx1), yy1 = fmaxf(iy1, jy1), xx2 = fminf(ix2, jx2), yy2 = fminf(iy2, jy2);
+  const float w = fmaxf(0.f, __fsub_rn(xx2, xx1)), h = fmaxf(0.f, __fsub_rn(yy2, yy1));
+  const float inter = __fmul_rn(w, h);
+  const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(iarea, jarea), inter));
+  return ovr > thr;
+}
+
+__global__ void __launch_bounds__(kNmsThreads, 1) nms_image_kernel(const __grid_constant__ NmsParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  // layout: whist[32][256] ints (32 KB, reused as the tile bit matrix), digit_total[256], tile arrays, kept arrays
+  int* whist = reinterpret_cast<int*>(smem_raw);
+  uint32_t* tmask = reinterpret_cast<uint32_t*>(smem_raw);  // [kTile][kTileWords] = 32 KB (phase 3)
+  int* digit_total = whist + 32 * 256;
+  float* tbox = reinterpret_cast<float*>(digit_total + 256);  // [5][kTile]: ox1, oy1, ox2, oy2, area
+  float* trow = tbox + 5 * kTile;                              // [kTile][6]  output rows
+  int* tidx = reinterpret_cast<int*>(trow + 6 * kTile);        // [kTile]
+  uint32_t* talive = reinterpret_cast<uint32_t*>(tidx + kTile);  // [kTileWords]
+  float* kbox = reinterpret_cast<float*>(talive + kTileWords);   // [5][max_det]
+  __shared__ int s_warp_tot[32];
+  __shared__ int s_running;
+  __shared__ int s_skip;
+  __shared__ int s_kept;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long img = blockIdx.x;
+  const float* boxes = P.boxes + img * P.N * 6;
+  uint32_t* kA = P.keys0 + img * P.N;
+  uint32_t* kB = P.keys1 + img * P.N;
+  uint32_t* vA = P.idx0 + img * P.N;
+  uint32_t* vB = P.idx1 + img * P.N;
+
+  // ---------------------------------------------------------------- phase 1: filter (ordered compaction)
+  if (tid == 0) s_running = 0;
+  __syncthreads();
+  for (long base = 0; base < P.N; base += kNmsThreads) {
+    const long i = base + tid;
+    float sc = 0.f;
+    bool take = false;
+    if (i < P.N) {
+      sc = boxes[i * 6 + 1];
+      take = sc > P.thr;  // bboxes_utils.py:186
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, take);
+    if (lane == 0) s_warp_tot[warp] = __popc(bal);
+    __syncthreads();
+    int before = s_running;
+    for (int w2 = 0; w2 < warp; ++w2) before += s_warp_tot[w2];
+    if (take) {
+      const int pos = before + __popc(bal & ((1u << lane) - 1u));
+      uint32_t u = __float_as_uint(sc);
+      u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // ascending-orderable
+      kA[pos] = ~u;                                     // descending score = ascending key
+      vA[pos] = (uint32_t)i;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int s = s_running;
+      for (int w2 = 0; w2 < 32; ++w2) s += s_warp_tot[w2];
+      s_running = s;
+    }
+    __syncthreads();
+  }
+  const int n = s_running;
+  if (tid == 0 && P.cand_count != nullptr) P.cand_count[img] = n;
+
+  // ---------------------------------------------------------------- phase 2: stable LSD radix sort, 4 x 8 bits
+  const int seg = ((((n + 31) / 32) + 31) / 32) * 32;  // per-warp contiguous segment, multiple of 32
+  const int s0 = min(n, warp * seg), s1 = min(n, (warp + 1) * seg);
+  for (int pass = 0; pass < 4 && n > 1; ++pass) {
+    const int shift = pass * 8;
+    for (int i = tid; i < 32 * 256; i += kNmsThreads) whist[i] = 0;
+    __syncthreads();
+    int* myh = whist + warp * 256;
+    for (int base = s0; base < s1; base += 32) {
+      const int i = base + lane;
+      const bool act = i < s1;
+      const uint32_t d = act ? ((kA[i] >> shift) & 255u) : (256u + lane);
+      const unsigned peers = __match_any_sync(0xffffffffu, d);
+      if (act && (peers & ((1u << lane) - 1u)) == 0) myh[d] += __popc(peers);
+      __syncwarp();
+    }
+    __syncthreads();
+    if (tid < 256) {  // column prefix over warps
+      int run = 0;
+      for (int w2 = 0; w2 < 32; ++w2) {
+        const int c = whist[w2 * 256 + tid];
+        whist[w2 * 256 + tid] = run;
+        run += c;
+      }
+      digit_total[tid] = run;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int run = 0, skip = 0;
+      for (int d = 0; d < 256; ++d) {
+        const int c = digit_total[d];
+        if (c == n) skip = 1;  // every key has the same digit: the pass is the identity
+        digit_total[d] = run;
+        run += c;
+      }
+      s_skip = skip;
+    }
+    __syncthreads();
+    if (s_skip) continue;
+    for (int i = tid; i < 32 * 256; i += kNmsThreads) whist[i] += digit_total[i & 255];
+    __syncthreads();
+    for (int base = s0; base < s1; base += 32) {
+      const int i = base + lane;
+      const bool act = i < s1;
+      uint32_t key = 0, val = 0;
+      if (act) {
+        key = kA[i];
+        val = vA[i];
+      }
+      const uint32_t d = act ? ((key >> shift) & 255u) : (256u + lane);
+      const unsigned peers = __match_any_sync(0xffffffffu, d);
+      const int rank = __popc(peers & ((1u << lane) - 1u));
+      int off = 0;
+      if (act) off = myh[d];
+      __syncwarp();
+      if (act) {
+        kB[off + rank] = key;
+        vB[off + rank] = val;
+        if (rank == 0) myh[d] = off + __popc(peers);
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    uint32_t* t = kA; kA = kB; kB = t;
+    t = vA; vA = vB; vB = t;
+  }
+  __syncthreads();
+
+  // ---------------------------------------------------------------- phase 3: greedy suppression, early exit at max_det
+  if (tid == 0) s_kept = 0;
+  __syncthreads();
+  float* out = P.out + img * (long)P.max_det * 6;
+  for (int base = 0; base < n; base += kTile) {
+    const int kept0 = s_kept;
+    if (kept0 >= P.max_det) break;
+    const int tn = min(kTile, n - base);
+    if (tid < kTileWords) talive[tid] = 0;
+    __syncthreads();
+    if (tid < kTile) {
+      bool alive = false;
+      if (tid < tn) {
+        const uint32_t ci = vA[base + tid];
+        const float* r = boxes + (long)ci * 6;
+        const float cls = r[0], sc = r[1], cx = r[2], cy = r[3], w = r[4], h = r[5];
+        const float x1 = __fsub_rn(cx, __fdiv_rn(w, 2.f));  // :190
+        const float y1 = __fsub_rn(cy, __fdiv_rn(h, 2.f));  // :191
+        const float y2 = __fadd_rn(h, y1);                  // :192
+        const float x2 = __fadd_rn(w, x1);                  // :193
+        const float ox1 = __fadd_rn(x1, cls), oy1 = __fadd_rn(y1, cls), ox2 = __fadd_rn(x2, cls), oy2 = __fadd_rn(y2, cls);  // :195
+        const float area = __fmul_rn(__fsub_rn(ox2, ox1), __fsub_rn(oy2, oy1));
+        tbox[0 * kTile + tid] = ox1; tbox[1 * kTile + tid] = oy1; tbox[2 * kTile + tid] = ox2; tbox[3 * kTile + tid] = oy2;
+        tbox[4 * kTile + tid] = area;
+        float* tr = trow + tid * 6;
+        tr[0] = cls; tr[1] = sc; tr[2] = x1; tr[3] = y1; tr[4] = x2; tr[5] = y2;
+        tidx[tid] = (int)ci;
+        alive = true;
+        for (int k = 0; k < kept0; ++k) {
+          if (iou_gt(kbox[k], kbox[P.max_det + k], kbox[2 * P.max_det + k], kbox[3 * P.max_det + k], kbox[4 * P.max_det + k],
+                     ox1, oy1, ox2, oy2, area, P.iou_thr)) {
+            alive = false;
+            break;
+          }
+        }
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, alive);
+      if (lane == 0) talive[tid >> 5] = bal;
+    }
+    __syncthreads();
+    {  // bit matrix among the tile's survivors: two threads per row
+      const int r = tid >> 1, half = tid & 1;
+      const bool ra = r < tn && ((talive[r >> 5] >> (r & 31)) & 1u);
+      const float rx1 = tbox[r], ry1 = tbox[kTile + r], rx2 = tbox[2 * kTile + r], ry2 = tbox[3 * kTile + r], rar = tbox[4 * kTile + r];
+      for (int wd = half * (kTileWords / 2); wd < (half + 1) * (kTileWords / 2); ++wd) {
+        uint32_t bits = 0;
+        if (ra && wd * 32 + 31 > r) {
+          const uint32_t al = talive[wd];
+          for (int bbit = 0; bbit < 32; ++bbit) {
+            const int j = wd * 32 + bbit;
+            if (j > r && ((al >> bbit) & 1u) &&
+                iou_gt(rx1, ry1, rx2, ry2, rar, tbox[j], tbox[kTile + j], tbox[2 * kTile + j], tbox[3 * kTile + j],
+                       tbox[4 * kTile + j], P.iou_thr))
+              bits |= 1u << bbit;
+          }
+        }
+        tmask[r * kTileWords + wd] = bits;
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {  // serial resolve over the survivors (in score order)
+      uint32_t aw = lane < kTileWords ? talive[lane] : 0u;
+      int kept = kept0;
+      while (kept < P.max_det) {
+        int pos = aw ? (lane * 32 + __ffs(aw) - 1) : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) pos = min(pos, __shfl_xor_sync(0xffffffffu, pos, o));
+        if (pos == 0x7fffffff) break;
+        if (lane < kTileWords) {
+          aw &= ~tmask[pos * kTileWords + lane];
+          if ((pos >> 5) == lane) aw &= ~(1u << (pos & 31));
+        }
+        if (lane < 5) kbox[lane * P.max_det + kept] = tbox[lane * kTile + pos];
+        if (lane < 6) out[(long)kept * 6 + lane] = trow[pos * 6 + lane];
+        if (lane == 6 && P.out_index != nullptr) P.out_index[img * P.max_det + kept] = tidx[pos];
+        ++kept;
+      }
+      if (lane == 0) s_kept = kept;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) P.out_count[img] = s_kept;
+}
+
+static int nms_sm_count() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        sms <= 0)
+      sms = 148;
+  }
+  return sms;
+}
+
+}  // namespace yb
+
+using namespace yb;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+int yb_decode_level(const float* p, int B, int na, int H, int W, int no, float stride, const float* anchors_px, float* out,
+                    int64_t rows_per_image, int64_t level_off, void* stream) {
+  YB_REQUIRE(no >= 6 && na >= 1, "decode: no=%d na=%d", no, na);
+  const long cells = (long)B * na * H * W;
+  if (cells == 0) return 0;
+  const int blocks = (int)std::max<long>(1, std::min<long>((cells + 7) / 8, (long)nms_sm_count() * 32));
+  decode_kernel<<<blocks, 256, 0, ST(stream)>>>(p, cells, na, H, W, no, stride, 0, 0, 0, 0, 0, 0, anchors_px, out,
+                                                rows_per_image, level_off);
+  YB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int64_t yb_nms_scratch_bytes(int B, int64_t N) { return (int64_t)4 * sizeof(uint32_t) * B * N; }
+
+int yb_nms_batched(const float* boxes, int B, int64_t N, float iou_threshold, float threshold, int max_det, void* scratch,
+                   float* out, int* out_count, int* out_index, int* cand_count, void* stream) {
+  YB_REQUIRE(max_det >= 1 && max_det <= 4096, "nms: max_det=%d (1..4096)", max_det);
+  YB_REQUIRE(N < (1L << 31), "nms: N too large");
+  if (B == 0) return 0;
+  if (N == 0) {
+    YB_CHECK_CUDA(cudaMemsetAsync(out_count, 0, sizeof(int) * B, ST(stream)));
+    if (cand_count) YB_CHECK_CUDA(cudaMemsetAsync(cand_count, 0, sizeof(int) * B, ST(stream)));
+    return 0;
+  }
+  NmsParams P;
+  P.boxes = boxes;
+  P.N = N;
+  P.iou_thr = iou_threshold;
+  P.thr = threshold;
+  P.max_det = max_det;
+  uint32_t* s = reinterpret_cast<uint32_t*>(scratch);
+  const size_t bn = (size_t)B * N;
+  P.keys0 = s;
+  P.keys1 = s + bn;
+  P.idx0 = s + 2 * bn;
+  P.idx1 = s + 3 * bn;
+  P.out = out;
+  P.out_count = out_count;
+  P.out_index = out_index;
+  P.cand_count = cand_count;
+  const size_t smem = (size_t)(32 * 256 + 256) * 4 + (size_t)(5 * kTile + 6 * kTile + kTile + kTileWords) * 4 +
+                      (size_t)5 * max_det * 4;
+  static size_t attr = 0;
+  if (smem > attr) {
+    YB_CHECK_CUDA(cudaFuncSetAttribute(nms_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  nms_image_kernel<<<B, kNmsThreads, smem, ST(stream)>>>(P);
+  YB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"
