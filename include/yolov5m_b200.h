@@ -142,6 +142,57 @@ int yb_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float 
                  float weight_decay, int64_t step, const int64_t* step_dev, float grad_scale, float max_norm,
                  const float* norm, void* w_bf16, void* stream);
 
+/* ---- ComputeLoss (ultralytics_loss.py:17-311) ---------------------------------------------------------------------
+ * One yb_loss_level per detection level; all pointers are device pointers owned by the caller, `cap` = row capacity of
+ * the per-level arrays (>= 5*na*nt, the exact upper bound of build_targets). */
+typedef struct yb_loss_level {
+  const float* p;       /* (B,na,H,W,no) fp32 raw logits of this level (model.py:173 layout) */
+  int32_t H, W;
+  float balance;        /* ultralytics_loss.py:37 */
+  int32_t pad_;
+  int64_t* idx;         /* [4][cap]: image b, anchor a, grid row gj, grid column gi   (ultralytics_loss.py:285) */
+  float* tbox;          /* [cap][4]: gx-gi, gy-gj, gw, gh in grid units               (:296) */
+  float* anch;          /* [cap][2]: matched anchor                                   (:301) */
+  int64_t* tcls;        /* [cap]:    class index                                      (:306) */
+  float* row_val;       /* [3][cap]: GIoU.clamp(0), 1-GIoU, sum_c BCE(cls)            (scratch) */
+  float* row_grad;      /* [cap][no]: unit-scale d(row loss)/d(logits)                (scratch) */
+  int32_t* row_prev;    /* [cap]: previous row that hit the same cell (1-based, 0 = none) */
+  int32_t* cell_head;   /* [B*na*H*W]: last-linked row of each cell (1-based, 0 = none) */
+  float* obj_partial;   /* [yb_loss_obj_rows()] per-CTA objectness BCE partial sums */
+  float* grad_f32;      /* optional out: dL/dp, (B,na,H,W,no) fp32 */
+  void* grad_bf16;      /* optional out: dL/dp as the head conv's gradient operand, (B,H,W,cpad) bf16, channel a*no+o */
+} yb_loss_level;
+
+int yb_loss_obj_rows(void);
+/* intersection_over_union (utils/bboxes_utils.py:33-87): (n,4) x (n,4) fp32 -> (n,) IoU or GIoU; midpoint = xywh boxes */
+int yb_box_iou(const float* boxes_preds, const float* boxes_labels, int64_t n, int midpoint, int giou, float eps, float* out,
+               void* stream);
+/* build_targets (ultralytics_loss.py:122-311): targets (nt,6) fp32 [img,cls,x,y,w,h] normalised; anchors [nl][na][2]
+ * (stride-divided, model.py:156-157).  Writes idx/tbox/anch/tcls of every level in the reference's row order
+ * (offset-major, then anchor, then target -- the order boolean-mask indexing produces) and counts[nl]. */
+int yb_build_targets(const float* targets, int nt, const float* anchors, const yb_loss_level* levels, int nl, int na,
+                     float anchor_t, int64_t cap, int* counts, void* stream);
+/* ComputeLoss.__call__ (ultralytics_loss.py:60-120): out4 = [(lbox+lobj+lcls)*B, lbox, lobj, lcls] (weighted parts). */
+int yb_loss_fwd(const yb_loss_level* levels, int nl, int B, int na, int no, int64_t cap, const int* counts,
+                float lam_box, float lam_obj, float lam_cls, float* out4, void* stream);
+/* its backward: gout = device scalar dLoss (NULL = 1).  Needs the scratch yb_loss_fwd left in the levels. */
+int yb_loss_bwd(const yb_loss_level* levels, int nl, int B, int na, int no, int64_t cap, const int* counts,
+                float lam_box, float lam_obj, float lam_cls, const float* gout, int cpad, void* stream);
+
+/* ---- cells_to_bboxes(is_pred=True) (utils/plot_utils.py:10-40) and non_max_suppression (utils/bboxes_utils.py:175-209)
+ * yb_decode_level: p (B,na,H,W,no) logits of one level -> rows [cls, sigmoid(obj), cx, cy, w, h] (pixels) written at
+ *   out[(b*rows_per_image + level_off + (a*H+y)*W+x)*6]; anchors_px = anchors[level]*stride, [na][2].  is_pred = 0:
+ *   the target-tensor branch (plot_utils.py:29-34; no = 6, no sigmoid, class id in channel 5).
+ * yb_nms_batched: boxes (B,N,6) rows as above.  Per image: keep score > threshold, xywh->xyxy, +cls offset, stable
+ *   descending sort, greedy suppression (IoU > iou_threshold), first max_det survivors.  out [B][max_det][6] rows
+ *   [cls, score, x1, y1, x2, y2]; out_count [B]; out_index (optional) [B][max_det] = row index into N; cand_count
+ *   (optional) [B] = candidates above threshold.  scratch: yb_nms_scratch_bytes(B,N) bytes. */
+int yb_decode_level(const float* p, int B, int na, int H, int W, int no, float stride, const float* anchors_px, int is_pred,
+                    float* out, int64_t rows_per_image, int64_t level_off, void* stream);
+int64_t yb_nms_scratch_bytes(int B, int64_t N);
+int yb_nms_batched(const float* boxes, int B, int64_t N, float iou_threshold, float threshold, int max_det, void* scratch,
+                   float* out, int* out_count, int* out_index, int* cand_count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,5 +8,16 @@ Drop-in surface (same names / signatures as the reference):
     intersection_over_union(...)                                       utils/bboxes_utils.py:33
 """
 from . import _lib  # noqa: F401
+from .model import YOLOV5m  # noqa: F401
+from .loss import ComputeLoss  # noqa: F401
+from .boxes import cells_to_bboxes, non_max_suppression, intersection_over_union  # noqa: F401
 
-__all__ = ["_lib"]
+ANCHORS = [  # reference config.py:33-37
+    [(10, 13), (16, 30), (33, 23)],
+    [(30, 61), (62, 45), (59, 119)],
+    [(116, 90), (156, 198), (373, 326)],
+]
+FIRST_OUT = 48  # reference config.py:15
+
+__all__ = ["YOLOV5m", "ComputeLoss", "cells_to_bboxes", "non_max_suppression", "intersection_over_union", "ANCHORS",
+           "FIRST_OUT"]

@@ -392,6 +392,36 @@ __global__ void __launch_bounds__(256) loss_bwd_kernel(const __grid_constant__ L
   }
 }
 
+// ------------------------------------------------------------------------------------------------ standalone IoU / GIoU
+// utils/bboxes_utils.py:33-87: (n,4) x (n,4) -> (n,), same operation order as the reference
+__global__ void box_iou_kernel(const float* __restrict__ a, const float* __restrict__ b, long n, int midpoint, int giou,
+                               float eps, float* __restrict__ out) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float4 p = reinterpret_cast<const float4*>(a)[i], t = reinterpret_cast<const float4*>(b)[i];
+    float b1x1, b1y1, b1x2, b1y2, b2x1, b2y1, b2x2, b2y2;
+    if (midpoint) {
+      b1x1 = __fsub_rn(p.x, p.z / 2.f); b1y1 = __fsub_rn(p.y, p.w / 2.f); b1x2 = __fadd_rn(p.x, p.z / 2.f); b1y2 = __fadd_rn(p.y, p.w / 2.f);
+      b2x1 = __fsub_rn(t.x, t.z / 2.f); b2y1 = __fsub_rn(t.y, t.w / 2.f); b2x2 = __fadd_rn(t.x, t.z / 2.f); b2y2 = __fadd_rn(t.y, t.w / 2.f);
+    } else {
+      b1x1 = p.x; b1y1 = p.y; b1x2 = p.z; b1y2 = p.w;
+      b2x1 = t.x; b2y1 = t.y; b2x2 = t.z; b2y2 = t.w;
+    }
+    const float w1 = __fsub_rn(b1x2, b1x1), h1 = __fsub_rn(b1y2, b1y1), w2 = __fsub_rn(b2x2, b2x1), h2 = __fsub_rn(b2y2, b2y1);
+    const float iw = fmaxf(__fsub_rn(fminf(b1x2, b2x2), fmaxf(b1x1, b2x1)), 0.f);
+    const float ih = fmaxf(__fsub_rn(fminf(b1y2, b2y2), fmaxf(b1y1, b2y1)), 0.f);
+    const float inter = __fmul_rn(iw, ih);
+    const float uni = __fadd_rn(__fsub_rn(__fadd_rn(__fmul_rn(w1, h1), __fmul_rn(w2, h2)), inter), eps);
+    const float iou = __fdiv_rn(inter, uni);
+    float r = iou;
+    if (giou) {
+      const float cw = __fsub_rn(fmaxf(b1x2, b2x2), fminf(b1x1, b2x1)), ch = __fsub_rn(fmaxf(b1y2, b2y2), fminf(b1y1, b2y1));
+      const float carea = __fadd_rn(__fmul_rn(cw, ch), eps);
+      r = __fsub_rn(iou, __fdiv_rn(__fsub_rn(carea, uni), carea));
+    }
+    out[i] = r;
+  }
+}
+
 static int fill_params(LossKParams& P, const yb_loss_level* levels, int nl, int B, int na, int no, int64_t cap,
                        const int* counts) {
   YB_REQUIRE(nl >= 1 && nl <= kMaxLevels, "loss: nl=%d (max %d)", nl, kMaxLevels);
@@ -427,6 +457,15 @@ using namespace yb;
 extern "C" {
 
 int yb_loss_obj_rows(void) { return sm_count() * 8; }
+
+int yb_box_iou(const float* boxes_preds, const float* boxes_labels, int64_t n, int midpoint, int giou, float eps, float* out,
+               void* stream) {
+  if (n == 0) return 0;
+  const int blocks = (int)std::max<long>(1, std::min<long>((n + 255) / 256, (long)sm_count() * 8));
+  box_iou_kernel<<<blocks, 256, 0, ST(stream)>>>(boxes_preds, boxes_labels, n, midpoint, giou, eps, out);
+  YB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
 
 int yb_build_targets(const float* targets, int nt, const float* anchors, const yb_loss_level* levels, int nl, int na,
                      float anchor_t, int64_t cap, int* counts, void* stream) {

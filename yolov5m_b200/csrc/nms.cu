@@ -27,9 +27,8 @@ __device__ __forceinline__ float sigmoid_t(float x) { return 1.0f / (1.0f + expf
 
 // ------------------------------------------------------------------------------------------------ decode
 __global__ void __launch_bounds__(256) decode_kernel(const float* __restrict__ p, long cells, int na, int H, int W, int no,
-                                                     float stride, float aw0, float ah0, float aw1, float ah1, float aw2,
-                                                     float ah2, const float* __restrict__ anchors_px, float* __restrict__ out,
-                                                     long rows_per_image, long level_off) {
+                                                     float stride, const float* __restrict__ anchors_px, int is_pred,
+                                                     float* __restrict__ out, long rows_per_image, long level_off) {
   const int lane = threadIdx.x & 31;
   const long wglobal = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
@@ -37,6 +36,20 @@ __global__ void __launch_bounds__(256) decode_kernel(const float* __restrict__ p
   const int nc = no - 5;
   for (long c = wglobal; c < cells; c += nwarps) {
     const float* ps = p + c * no;
+    if (!is_pred) {  // target tensors (plot_utils.py:29-34): no sigmoid, class id stored in channel 5
+      if (lane < 6) {
+        const long b = c / per_img, rem = c - b * per_img;
+        const long sp = rem % ((long)H * W);
+        const int gy = (int)(sp / W), gx = (int)(sp - (long)gy * W);
+        float v;
+        if (lane == 0) v = ps[5];
+        else if (lane == 1) v = ps[4];
+        else if (lane < 4) v = __fmul_rn(__fadd_rn(ps[lane - 2], lane == 2 ? (float)gx : (float)gy), stride);
+        else v = __fmul_rn(ps[lane - 2], stride);
+        out[(b * rows_per_image + level_off + rem) * 6 + lane] = v;
+      }
+      continue;
+    }
     // class arg-max over sigmoid(logit): first maximum wins (torch.argmax), plot_utils.py:27
     float bv = -1.f;
     int bi = 0x7fffffff;
@@ -335,14 +348,14 @@ using namespace yb;
 
 extern "C" {
 
-int yb_decode_level(const float* p, int B, int na, int H, int W, int no, float stride, const float* anchors_px, float* out,
-                    int64_t rows_per_image, int64_t level_off, void* stream) {
+int yb_decode_level(const float* p, int B, int na, int H, int W, int no, float stride, const float* anchors_px, int is_pred,
+                    float* out, int64_t rows_per_image, int64_t level_off, void* stream) {
   YB_REQUIRE(no >= 6 && na >= 1, "decode: no=%d na=%d", no, na);
   const long cells = (long)B * na * H * W;
   if (cells == 0) return 0;
   const int blocks = (int)std::max<long>(1, std::min<long>((cells + 7) / 8, (long)nms_sm_count() * 32));
-  decode_kernel<<<blocks, 256, 0, ST(stream)>>>(p, cells, na, H, W, no, stride, 0, 0, 0, 0, 0, 0, anchors_px, out,
-                                                rows_per_image, level_off);
+  decode_kernel<<<blocks, 256, 0, ST(stream)>>>(p, cells, na, H, W, no, stride, anchors_px, is_pred, out, rows_per_image,
+                                                level_off);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

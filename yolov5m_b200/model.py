@@ -505,6 +505,8 @@ class _NetFn(torch.autograd.Function):
         eng.head_ready = False
         gflat = net._grad_target()
         eng.run_backward(gflat)
+        if not net.expose_param_grads:  # fused optimiser path: the flat bucket is consumed directly (trainer.py)
+            return (None, None, None) + (None,) * len(net._poffs)
         grads = tuple(net._grad_views(gflat))
         return (None, None, None) + grads
 
@@ -533,6 +535,9 @@ class YOLOV5m(nn.Module):
         self._engines = {}
         self._packed_sig = None
         self._gflat = [None, None]
+        # True: backward publishes p.grad views of the flat gradient bucket (stock torch optimisers work);
+        # False: gradients stay only in `flat_grads` (yolov5m_b200.trainer.Adam reads the bucket) -- saves 243 view objects
+        self.expose_param_grads = True
         self._flatten()
 
     # -- flat parameter storage -----------------------------------------------------------------

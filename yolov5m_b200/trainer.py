@@ -1,0 +1,133 @@
+"""Training-step plumbing around the hot path: the fused optimiser tail, the data-parallel gradient exchange and the
+step function that mirrors the body of the reference's ``train_loop`` (reference utils/training_utils.py:97-122).
+
+    reference (per batch)                                   here
+    ---------------------------------------------------     -----------------------------------------------------------
+    images.float()/255 ; .to(DEVICE)        (:98,:102)      uint8 H2D (4x fewer bytes) + /255 fused into the stem staging
+    out = model(images)                     (:107)          YOLOV5m engine (csrc/conv_*.cu, elementwise.cu)
+    loss = loss_fn(out, bboxes, ...)        (:108)          ComputeLoss kernels (csrc/loss.cu)
+    scaler.scale(loss).backward()           (:114)          engine backward; gradients land in ONE flat fp32 bucket
+    --- (no data parallelism in the reference) ---          all-reduce of that bucket over NCCL / NVLink
+    scaler.unscale_ ; clip_grad_norm_(10)   (:117-118)      yb_grad_norm + yb_adam_step: unscale, 1/world, clip and
+    scaler.step(optim) [Adam, L2 wd]        (:119, train.py:61)   Adam in one pass over the bucket, which also writes the
+    optim.zero_grad(set_to_none=True)       (:121)          bf16 tensor-core operands of the next forward
+
+One process per GPU; `torch.distributed` (NCCL) is only plumbing.  BatchNorm statistics stay local to each rank, like
+the reference's plain nn.BatchNorm2d (model.py:17).
+"""
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+class Adam:
+    """torch.optim.Adam(params, lr, betas, eps, weight_decay) semantics (train.py:61: L2 weight decay added to the
+    gradient of EVERY parameter) fused with gradient unscale + global-norm clipping, on the model's flat buffers."""
+
+    def __init__(self, model, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=5e-4):
+        self.model = model
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        flat = model.flat_params
+        if not flat.is_cuda:
+            raise _lib.YBError("yolov5m_b200.Adam: move the model to a CUDA device first (no CPU fallback)")
+        self.m = torch.zeros_like(flat)
+        self.v = torch.zeros_like(flat)
+        self.step_count = 0
+        self._partial = torch.zeros(4096, device=flat.device, dtype=torch.float32)
+        self.grad_norm = torch.zeros(1, device=flat.device, dtype=torch.float32)
+        self._step_dev = torch.zeros(1, device=flat.device, dtype=torch.int64)  # device-side counter (CUDA-graph replay)
+
+    def zero_grad(self, set_to_none=True):
+        if set_to_none:
+            for p in self.model.parameters():
+                p.grad = None
+        else:
+            self.model.flat_grads.zero_()
+
+    def step(self, grad_scale=1.0, max_norm=0.0, grads=None, device_step=False):
+        """grad_scale multiplies the stored gradient (1/loss_scale, 1/world_size); max_norm > 0 clips the global norm of
+        the scaled gradient like torch.nn.utils.clip_grad_norm_ (training_utils.py:118)."""
+        model = self.model
+        L, st = _lib.lib(), _lib.stream()
+        g = model.flat_grads if grads is None else grads
+        p = model.flat_params
+        n = p.numel()
+        if max_norm > 0:
+            _lib.check(L.yb_grad_norm(g.data_ptr(), n, grad_scale, self._partial.data_ptr(), self._partial.numel(),
+                                      self.grad_norm.data_ptr(), st))
+        self.step_count += 1
+        if device_step:
+            _lib.check(L.yb_counter_inc(self._step_dev.data_ptr(), st))
+        _lib.check(L.yb_adam_step(p.data_ptr(), g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), n, self.lr, self.betas[0],
+                                  self.betas[1], self.eps, self.weight_decay, self.step_count,
+                                  self._step_dev.data_ptr() if device_step else None, grad_scale, max_norm,
+                                  self.grad_norm.data_ptr() if max_norm > 0 else None, model._wfwd.data_ptr(), st))
+        model._repack_derived(st)                     # dgrad-layout / stem operands from the updated masters
+        model._packed_sig = model._param_signature()  # the bf16 operands are current
+
+    def state_dict(self):
+        return {"step": self.step_count, "exp_avg": self.m, "exp_avg_sq": self.v, "lr": self.lr, "betas": self.betas,
+                "eps": self.eps, "weight_decay": self.weight_decay}
+
+    def load_state_dict(self, sd):
+        self.step_count = int(sd["step"])
+        self.m.copy_(sd["exp_avg"]); self.v.copy_(sd["exp_avg_sq"])
+        self._step_dev.fill_(self.step_count)
+
+
+class GradSync:
+    """Data-parallel gradient exchange: one all-reduce (sum) of the flat fp32 gradient bucket per step, split into a few
+    large chunks so the collective is not latency-bound.  The 1/world_size average is folded into the
+    optimiser's grad_scale, so the bucket is never rescaled in memory."""
+
+    def __init__(self, model, chunks=4, group=None):
+        self.model, self.group = model, group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.chunks = max(1, chunks)
+
+    def broadcast_parameters(self, src=0):
+        if self.world > 1:
+            dist.broadcast(self.model.flat_params, src, group=self.group)
+            for b in self.model.buffers():
+                dist.broadcast(b, src, group=self.group)
+            self.model.refresh_packed(force=True)
+
+    def all_reduce(self, grads=None):
+        if self.world == 1:
+            return
+        g = self.model.flat_grads if grads is None else grads
+        n = g.numel()
+        per = (n + self.chunks - 1) // self.chunks
+        # gradients are produced head-first (end of the bucket first): reduce from the tail
+        for c in reversed(range(self.chunks)):
+            lo, hi = c * per, min(n, (c + 1) * per)
+            if hi > lo:
+                dist.all_reduce(g[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+
+
+class TrainStep:
+    """One optimisation step = the body of the reference train_loop (training_utils.py:97-122) for one batch."""
+
+    def __init__(self, model, loss_fn, optimizer, max_norm=10.0, sync=None, loss_scale=1.0):
+        self.model, self.loss_fn, self.opt = model, loss_fn, optimizer
+        self.max_norm, self.loss_scale = max_norm, loss_scale
+        self.sync = sync if sync is not None else GradSync(model)
+        model.expose_param_grads = False  # the fused optimiser reads the flat bucket
+
+    def __call__(self, images, targets):
+        """images: (B,3,H,W) uint8 (0..255) or float32 (0..1), host or device; targets (nt,6) [img,cls,x,y,w,h]."""
+        model = self.model
+        dev = model.flat_params.device
+        if not images.is_cuda:
+            images = images.to(dev, non_blocking=True)
+        out = model(images)
+        loss = self.loss_fn(out, targets, pred_size=images.shape[2:4])
+        if self.loss_scale != 1.0:
+            (loss * self.loss_scale).backward()
+        else:
+            loss.backward()
+        self.sync.all_reduce()
+        self.opt.step(grad_scale=1.0 / (self.loss_scale * self.sync.world), max_norm=self.max_norm)
+        self.opt.zero_grad(set_to_none=True)
+        return loss
