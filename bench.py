@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py -- training-step images/sec of the B200-native YOLOV5m hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[2] / [3]): full train step, bf16 tensor-core compute with fp32 master weights, bs=64 per
+GPU, 640x640, synthetic COCO-80-like targets (8 boxes / image), random-init weights: forward + ComputeLoss + backward +
+(NCCL all-reduce of the flat gradient bucket when N > 1) + global-norm clip (10) + Adam(5e-4, wd 5e-4).
+
+One JSON line on rank 0.  `value` = whole-job img/s with the batch resident in HBM; `e2e` = the same step through the
+public API (yolov5m_b200.trainer.TrainStep) with the uint8 batch in pinned host memory copied to the device every step
+and the loss read back every step; `roofline` = tensor-core roofline of the dominant kernel (conv_igemm_kernel: all
+forward + dgrad convolutions) from CUDA events around each of its launches; `cpu_baseline` = the oracle port of the
+reference step on the host cores (bounded sample).  `--impl reference` times that CPU path alone.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "train_step_images_per_sec_640x640_bs64_per_gpu"
+UNIT = "img/s"
+TRAIN_GFLOP_PER_IMG = 146.62  # 3 x 48.872 GFLOP (fwd + dgrad + wgrad of the 82 convs at 640x640)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--bs", type=int, default=64, help="images per GPU (the metric is quoted at 64)")
+    ap.add_argument("--size", type=int, default=640)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["bf16_tflops_sustained"]), float(p["hbm_gbs"]), "measured"
+    except Exception:
+        return 1400.0, 6650.0, "fallback"
+
+
+# ---------------------------------------------------------------------------------------------------- clocks sampler
+class Clocks:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc, self.th = index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.th = threading.Thread(target=self._read, daemon=True)
+        self.th.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+
+    def summary(self, windows):
+        sm, mx, reasons, pw = [], 0.0, set(), 0.0
+        for t, c in self.rows:
+            if not any(a <= t <= b for a, b in windows) or len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx = max(mx, float(c[2])); pw = max(pw, float(c[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "power_w_max": pw or None, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------- reference arm (CPU)
+def cpu_reference(steps, warmup, budget_s, size):
+    """the reference step (oracle port) on the host cores; batch sized so the run fits the time budget."""
+    from oracle.cpu_step import CpuTrainer
+    tr = CpuTrainer()
+    _, t1 = tr.time_steps(1, 1, 1, size=size)                 # probe: seconds per image-step at bs=1
+    bs = 8
+    while bs > 1 and (steps + warmup) * t1 * bs * 0.8 > budget_s:
+        bs //= 2
+    ips, sec = tr.time_steps(bs, steps, warmup, size=size)
+    return ips, sec, bs, tr.threads
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ips, sec, bs, threads = cpu_reference(a.steps, a.warmup, budget_s=150.0, size=a.size)
+    sample = f"{a.steps} timed + {a.warmup} warm-up full train steps at bs={bs}, {a.size}x{a.size}, fp32, oracle port of the reference step"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": "full train step (fwd+ComputeLoss+bwd+clip+Adam), CPU host cores", "batch_per_step": bs,
+                   "image": a.size},
+        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ---------------------------------------------------------------------------------------------------- our arm (GPU)
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from yolov5m_b200.build import build
+    build()
+    import yolov5m_b200 as yb
+    from yolov5m_b200 import _lib
+    from yolov5m_b200.trainer import Adam, GradSync, TrainStep
+    L = _lib.lib()
+
+    torch.manual_seed(0)
+    model = yb.YOLOV5m(first_out=yb.FIRST_OUT, nc=80, anchors=yb.ANCHORS, ch=(192, 384, 768)).to(dev).train()
+    loss_fn = yb.ComputeLoss(model)
+    opt = Adam(model, lr=5e-4, weight_decay=5e-4)
+    sync = GradSync(model)
+    sync.broadcast_parameters(0)
+    step = TrainStep(model, loss_fn, opt, max_norm=10.0, sync=sync)
+
+    B, S = a.bs, a.size
+    g = torch.Generator().manual_seed(1 + rank)
+    nt = 8 * B
+    nbuf = 2
+    host_imgs = [torch.randint(0, 256, (B, 3, S, S), dtype=torch.uint8, generator=g).pin_memory() for _ in range(nbuf)]
+    host_tgts = [torch.cat([torch.randint(0, B, (nt, 1), generator=g).float(), torch.randint(0, 80, (nt, 1), generator=g).float(),
+                            torch.rand(nt, 2, generator=g), torch.rand(nt, 2, generator=g) * 0.5 + 0.005], 1).pin_memory()
+                 for _ in range(nbuf)]
+    dev_imgs = [h.to(dev) for h in host_imgs]
+    dev_tgts = [h.to(dev) for h in host_tgts]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
+    windows = []
+
+    # ---- (1) device-resident: inputs already in HBM
+    for i in range(a.warmup):
+        step(dev_imgs[i % nbuf], dev_tgts[i % nbuf])
+    barrier()
+    l0 = L.yb_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
+    e0.record()
+    for i in range(a.steps):
+        loss = step(dev_imgs[i % nbuf], dev_tgts[i % nbuf])
+    e1.record()
+    barrier()
+    windows.append((w0, time.perf_counter()))
+    launches = L.yb_launch_count() - l0
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    value = world * B * a.steps / (ms * 1e-3)
+    last_loss = float(loss.item())
+
+    # ---- (2) end to end through the public API: pinned host batch -> H2D -> step -> loss D2H, every step;
+    #      the copy of batch i+1 overlaps the compute of batch i on a second stream (double buffering)
+    e2e = None
+    if not a.no_e2e:
+        copy_stream = torch.cuda.Stream()
+        stage_i = [torch.empty_like(d) for d in dev_imgs]
+        stage_t = [torch.empty_like(d) for d in dev_tgts]
+        ready = [torch.cuda.Event() for _ in range(nbuf)]
+        consumed = [torch.cuda.Event() for _ in range(nbuf)]
+
+        def prefetch(i):
+            k = i % nbuf
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[k])
+                stage_i[k].copy_(host_imgs[k], non_blocking=True)
+                stage_t[k].copy_(host_tgts[k], non_blocking=True)
+                ready[k].record(copy_stream)
+
+        def e2e_loop(n):
+            for k in range(nbuf):
+                consumed[k].record()
+            prefetch(0)
+            tot = 0.0
+            for i in range(n):
+                k = i % nbuf
+                if i + 1 < n:
+                    prefetch(i + 1)
+                torch.cuda.current_stream().wait_event(ready[k])
+                ls = step(stage_i[k], stage_t[k])
+                consumed[k].record()
+                tot += float(ls.item())  # device -> host read of the step's result, every step
+            return tot
+
+        e2e_loop(max(2, a.warmup // 2))
+        barrier()
+        w0 = time.perf_counter()
+        e0.record()
+        e2e_loop(a.steps)
+        e1.record()
+        barrier()
+        windows.append((w0, time.perf_counter()))
+        ms_e = max_over_ranks(e0.elapsed_time(e1))
+        e2e = {"value": world * B * a.steps / (ms_e * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(host_imgs[0].numel() + host_tgts[0].numel() * 4) * world,
+               "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e / a.steps}
+
+    # ---- (3) roofline of the dominant kernel: CUDA events around every conv launch (separate instrumented steps)
+    roof, kern = None, None
+    if rank == 0:
+        eng = model.engine(B, S, S, True)
+        eng.prof = []
+        nprof = min(3, a.steps)
+        for i in range(nprof):
+            step(dev_imgs[i % nbuf], dev_tgts[i % nbuf])
+        torch.cuda.synchronize()
+        acc = {}
+        for kind, flops, s0, s1 in eng.prof:
+            d = acc.setdefault(kind, [0.0, 0.0, 0])
+            d[0] += flops; d[1] += s0.elapsed_time(s1) * 1e-3; d[2] += 1
+        eng.prof = None
+        peak_tf, peak_hbm, peak_src = peaks()
+        igemm_f = acc["fwd"][0] + acc["dgrad"][0]
+        igemm_t = acc["fwd"][1] + acc["dgrad"][1]
+        igemm_n = acc["fwd"][2] + acc["dgrad"][2]
+        ach = igemm_f / igemm_t / 1e12
+        roof = {"bound": "tensor", "kernel": "conv_igemm_kernel (fwd + dgrad convolutions)", "achieved": ach,
+                "peak": peak_tf, "peak_source": peak_src + " bf16_tflops_sustained", "unit": "TFLOP/s", "frac": ach / peak_tf,
+                "traffic": None, "launches_per_step": igemm_n // nprof, "avg_launch_us": igemm_t / igemm_n * 1e6,
+                "ms_per_step": igemm_t / nprof * 1e3}
+        kern = {k: {"tflops": v[0] / v[1] / 1e12, "ms_per_step": v[1] / nprof * 1e3, "launches_per_step": v[2] // nprof}
+                for k, v in acc.items()}
+        kern["whole_step_conv_tflops"] = value / world * TRAIN_GFLOP_PER_IMG * 1e9 / 1e12
+    if world > 1:
+        dist.barrier()
+
+    cpu = None
+    if rank == 0:
+        clocks.stop()
+        if world == 1 and not a.no_cpu_baseline:
+            ips, sec, bs, threads = cpu_reference(2, 1, budget_s=25.0, size=S)
+            cpu = {"value": ips, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"2 timed + 1 warm-up full train steps at bs={bs}, {S}x{S}, fp32 (oracle port of the reference step)"}
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": "configs[2]: full train step bf16 bs=64/GPU 640x640 synthetic COCO-80 "
+                                   "(fwd + ComputeLoss + bwd + grad all-reduce + clip(10) + Adam)",
+                       "batch_per_gpu": B, "global_batch": B * world, "image": S, "targets_per_image": 8,
+                       "parallelism": f"dp{world}", "l2_policy": "inputs larger than L2 (activations of one step >> 126 MB)"},
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks.summary(windows), "kernels": kern, "loss": last_loss,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

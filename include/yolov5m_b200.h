@@ -22,6 +22,8 @@ extern "C" {
 
 const char* yb_last_error(void);
 int yb_version(void);
+/* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t yb_launch_count(void);
 /* number of per-CTA partial rows a conv launch may write to `stats` (= max grid = #SMs) */
 int yb_conv_max_partials(void);
 

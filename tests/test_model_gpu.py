@@ -102,7 +102,7 @@ class _Mirror(model_ref.Net):
         for rec in eng.tape:
             if rec[0] != "cbl":
                 continue
-            _, r, xin, out, y, res, up, ptrs = rec
+            _, r, xin, out, y, res, up, ptrs = rec[:8]
             o = out.tensor().float().cpu().permute(0, 3, 1, 2)
             if res is not None:
                 o = o - res.tensor().float().cpu().permute(0, 3, 1, 2)  # engine stores silu(bn(y)) + residual

@@ -7,6 +7,7 @@
 
 namespace yb {
 const char* last_error();
+long long launch_count();
 }
 using namespace yb;
 
@@ -14,6 +15,7 @@ extern "C" {
 
 const char* yb_last_error(void) { return yb::last_error(); }
 int yb_version(void) { return 1; }
+int64_t yb_launch_count(void) { return (int64_t)yb::launch_count(); }
 int yb_conv_max_partials(void) { return conv_max_grid(); }
 
 int yb_conv2d_fwd(const void* x, int N, int H, int W, int Cin, int64_t x_pitch, const void* w_packed, int Cout,

@@ -21,6 +21,13 @@ void set_error(const char* fmt, ...);
       return -2;                                                                     \
     }                                                                                \
   } while (0)
+// after every kernel launch: count it (yb_launch_count) and surface launch errors
+void note_launch();
+#define YB_LAUNCHED()          \
+  do {                         \
+    yb::note_launch();         \
+    YB_CHECK_CUDA(cudaGetLastError()); \
+  } while (0)
 #define YB_REQUIRE(cond, ...)                 \
   do {                                        \
     if (!(cond)) {                            \

@@ -518,7 +518,7 @@ int conv_run(const ConvPlan& pl, cudaStream_t st) {
     attr_set = true;
   }
   conv_igemm_kernel<<<pl.grid, kThreads, pl.smem, st>>>(pl.kp);
-  YB_CHECK_CUDA(cudaGetLastError());
+  YB_LAUNCHED();
   return 0;
 }
 

@@ -374,13 +374,13 @@ int wgrad_run(const WgradPlan& pl, float* out, int out_rows, const int* map, int
     attr_set = true;
   }
   conv_wgrad_kernel<<<pl.grid, kThreads, pl.smem, st>>>(pl.kp);
-  YB_CHECK_CUDA(cudaGetLastError());
+  YB_LAUNCHED();
   YB_REQUIRE(out_rows > 0 && out_rows <= pl.kp.Cout, "wgrad: out_rows=%d", out_rows);
   const long n = (long)out_rows * pl.kp.ldo;
   const long nfull = (long)pl.kp.Cout * pl.kp.ldo;
   const int blocks = (int)std::min<long>((n / 4 + 255) / 256 + 1, 4L * wgrad_max_grid());
   wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(pl.kp.partial, pl.kp.splits, n, nfull, out, map, accumulate);
-  YB_CHECK_CUDA(cudaGetLastError());
+  YB_LAUNCHED();
   return 0;
 }
 

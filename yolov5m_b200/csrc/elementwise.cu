@@ -462,7 +462,7 @@ using namespace yb;
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 #define B16(p) reinterpret_cast<bf16*>(p)
 #define CB16(p) reinterpret_cast<const bf16*>(p)
-#define LAUNCH_OK() YB_CHECK_CUDA(cudaGetLastError())
+#define LAUNCH_OK() YB_LAUNCHED()
 
 extern "C" {
 

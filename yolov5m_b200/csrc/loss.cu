@@ -463,7 +463,7 @@ int yb_box_iou(const float* boxes_preds, const float* boxes_labels, int64_t n, i
   if (n == 0) return 0;
   const int blocks = (int)std::max<long>(1, std::min<long>((n + 255) / 256, (long)sm_count() * 8));
   box_iou_kernel<<<blocks, 256, 0, ST(stream)>>>(boxes_preds, boxes_labels, n, midpoint, giou, eps, out);
-  YB_CHECK_CUDA(cudaGetLastError());
+  YB_LAUNCHED();
   return 0;
 }
 
@@ -486,7 +486,7 @@ int yb_build_targets(const float* targets, int nt, const float* anchors, const y
   P.cap = cap;
   P.counts = counts;
   build_targets_kernel<<<nl, 1024, 0, ST(stream)>>>(P);
-  YB_CHECK_CUDA(cudaGetLastError());
+  YB_LAUNCHED();
   return 0;
 }
 
@@ -506,12 +506,12 @@ int yb_loss_fwd(const yb_loss_level* levels, int nl, int B, int na, int no, int6
     const long warps = (long)nl * cap;
     const int blocks = (int)std::max<long>(1, std::min<long>((warps + 7) / 8, (long)sm_count() * 8));
     loss_rows_kernel<<<blocks, 256, 0, ST(stream)>>>(P);
-    YB_CHECK_CUDA(cudaGetLastError());
+    YB_LAUNCHED();
   }
   loss_obj_kernel<<<P.obj_rows, 256, 0, ST(stream)>>>(P);
-  YB_CHECK_CUDA(cudaGetLastError());
+  YB_LAUNCHED();
   loss_finalize_kernel<<<1, 256, 0, ST(stream)>>>(P);
-  YB_CHECK_CUDA(cudaGetLastError());
+  YB_LAUNCHED();
   return 0;
 }
 
@@ -531,7 +531,7 @@ int yb_loss_bwd(const yb_loss_level* levels, int nl, int B, int na, int no, int6
   for (int i = 0; i < nl; ++i) pix += (long)B * levels[i].H * levels[i].W;
   const int blocks = (int)std::max<long>(1, std::min<long>((pix + 7) / 8, (long)sm_count() * 16));
   loss_bwd_kernel<<<blocks, 256, 0, ST(stream)>>>(P);
-  YB_CHECK_CUDA(cudaGetLastError());
+  YB_LAUNCHED();
   return 0;
 }
 

@@ -356,7 +356,7 @@ int yb_decode_level(const float* p, int B, int na, int H, int W, int no, float s
   const int blocks = (int)std::max<long>(1, std::min<long>((cells + 7) / 8, (long)nms_sm_count() * 32));
   decode_kernel<<<blocks, 256, 0, ST(stream)>>>(p, cells, na, H, W, no, stride, anchors_px, is_pred, out, rows_per_image,
                                                 level_off);
-  YB_CHECK_CUDA(cudaGetLastError());
+  YB_LAUNCHED();
   return 0;
 }
 
@@ -396,7 +396,7 @@ int yb_nms_batched(const float* boxes, int B, int64_t N, float iou_threshold, fl
     attr = smem;
   }
   nms_image_kernel<<<B, kNmsThreads, smem, ST(stream)>>>(P);
-  YB_CHECK_CUDA(cudaGetLastError());
+  YB_LAUNCHED();
   return 0;
 }
 

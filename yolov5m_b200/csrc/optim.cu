@@ -147,20 +147,20 @@ extern "C" {
 
 int yb_cast_bf16(const float* src, void* dst, int64_t n, void* stream) {
   cast_bf16_kernel<<<blocks_for(n / 4 + 1), 256, 0, ST(stream)>>>(src, reinterpret_cast<bf16*>(dst), n);
-  YB_CHECK_CUDA(cudaGetLastError());
+  YB_LAUNCHED();
   return 0;
 }
 
 int yb_repack_dgrad(const float* src, void* dst, const int64_t* table, int nlayers, int64_t total, void* stream) {
   repack_dgrad_kernel<<<blocks_for(total), 256, 0, ST(stream)>>>(src, reinterpret_cast<bf16*>(dst),
                                                                  reinterpret_cast<const long long*>(table), nlayers, total);
-  YB_CHECK_CUDA(cudaGetLastError());
+  YB_LAUNCHED();
   return 0;
 }
 
 int yb_repack_stem(const float* w6, void* w3, int Cout, void* stream) {
   repack_stem_kernel<<<(Cout * 144 + 255) / 256, 256, 0, ST(stream)>>>(w6, reinterpret_cast<bf16*>(w3), Cout);
-  YB_CHECK_CUDA(cudaGetLastError());
+  YB_LAUNCHED();
   return 0;
 }
 
@@ -169,15 +169,15 @@ int yb_grad_norm(const float* g, int64_t n, float grad_scale, float* partial, in
   const int blocks = std::min(blocks_for(n / 4 + 1, 4), partial_len);
   YB_REQUIRE(blocks >= 1, "grad_norm: partial_len");
   sqnorm_partial_kernel<<<blocks, 256, 0, ST(stream)>>>(g, n, partial);
-  YB_CHECK_CUDA(cudaGetLastError());
+  YB_LAUNCHED();
   sqnorm_final_kernel<<<1, 1, 0, ST(stream)>>>(partial, blocks, grad_scale, norm_out);
-  YB_CHECK_CUDA(cudaGetLastError());
+  YB_LAUNCHED();
   return 0;
 }
 
 int yb_counter_inc(int64_t* counter, void* stream) {
   counter_inc_kernel<<<1, 1, 0, ST(stream)>>>(reinterpret_cast<long long*>(counter));
-  YB_CHECK_CUDA(cudaGetLastError());
+  YB_LAUNCHED();
   return 0;
 }
 
@@ -190,7 +190,7 @@ int yb_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float 
   const float bc2s = (float)sqrt(1.0 - pow((double)beta2, (double)step));
   adam_step_kernel<<<blocks_for(n), 256, 0, ST(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2s,
                                                            reinterpret_cast<const long long*>(step_dev), grad_scale, max_norm, norm, reinterpret_cast<bf16*>(w_bf16));
-  YB_CHECK_CUDA(cudaGetLastError());
+  YB_LAUNCHED();
   return 0;
 }
 

@@ -172,6 +172,8 @@ class _Engine:
         self.dev = net._pflat.device
         self.L = _lib.lib()
         self.fwd_ops, self.bwd_ops, self.tape = [], [], []
+        self.prof = None
+        self.conv_flops = {"fwd": 0.0, "dgrad": 0.0, "wgrad": 0.0}  # algorithmic FLOPs of the reference convs per step
         self.plans = []
         self.bufs = []
         self.nbytes = 0
@@ -190,6 +192,27 @@ class _Engine:
             self.dy = None  # allocated after the forward build (max conv output size)
             self._dy_elems = 0
         self._build()
+
+    # -- timed launch wrappers (bench.py roofline: CUDA events around every tensor-core kernel launch when prof is a list)
+    def _conv(self, plan, st, flops, kind):
+        if self.prof is None:
+            _lib.check(self.L.yb_plan_run(plan, st))
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(self.L.yb_plan_run(plan, st))
+        e1.record()
+        self.prof.append((kind, flops, e0, e1))
+
+    def _wgrad(self, plan, st, flops, *args):
+        if self.prof is None:
+            _lib.check(self.L.yb_wgrad_plan_run(plan, *args, st))
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(self.L.yb_wgrad_plan_run(plan, *args, st))
+        e1.record()
+        self.prof.append(("wgrad", flops, e0, e1))
 
     # -- allocation helpers
     def buf(self, N, H, W, C, grad=None):
@@ -210,6 +233,8 @@ class _Engine:
         Ho, Wo = xin.H // (1 if r.is_stem else r.stride), xin.W // (1 if r.is_stem else r.stride)
         assert (out.H, out.W, out.C) == (Ho, Wo, r.cout), (r.name, out.H, out.W, out.C)
         C = r.cout
+        flops = 2.0 * xin.N * Ho * Wo * C * r.k * r.k * r.cin  # the reference conv (stem: 6x6 over 3 channels)
+        self.conv_flops["fwd"] += flops
         scale, shift = self._stat(C), self._stat(C)
         w_ptr = net._wstem.data_ptr() if r.is_stem else net._wfwd.data_ptr() + 2 * r.w_off
         gam, bet = net._pflat.data_ptr() + 4 * r.g_off, net._pflat.data_ptr() + 4 * r.b_off
@@ -226,7 +251,7 @@ class _Engine:
 
             def op(st, plan=plan):
                 _lib.check(L.yb_bn_finalize(None, 0, C, 1.0, gam, bet, BN_EPS, BN_MOMENTUM, rm, rv, None, sp, hp, None, None, 0, st))
-                _lib.check(L.yb_plan_run(plan, st))
+                self._conv(plan, st, flops, "fwd")
             self.fwd_ops.append(op)
             if up is not None:
                 self.fwd_ops.append(lambda st: _lib.check(L.yb_upsample2x_fwd(out.ptr, out.pitch, out.N, out.H, out.W, C,
@@ -245,14 +270,14 @@ class _Engine:
         upp, upl = (up.ptr, up.pitch) if up is not None else (None, 0)
 
         def op(st):
-            _lib.check(L.yb_plan_run(plan, st))
+            self._conv(plan, st, flops, "fwd")
             _lib.check(L.yb_bn_finalize(ptrs[0], nrows, C, count, gam, bet, BN_EPS, BN_MOMENTUM, rm, rv, nbt, ptrs[1], ptrs[2],
                                         ptrs[3], ptrs[4], 1, st))
             _lib.check(L.yb_bn_act_fwd(y.ptr, C, y.N, y.H, y.W, C, ptrs[1], ptrs[2], resp, resl, out.ptr, out.pitch, upp,
                                        upl, st))
         self.fwd_ops.append(op)
         self._dy_elems = max(self._dy_elems, y.npix * C)
-        self.tape.append(("cbl", r, xin, out, y, res, up, ptrs))
+        self.tape.append(("cbl", r, xin, out, y, res, up, ptrs, flops))
 
     def c3(self, mod, xin, out):
         c_ = mod.hidden
@@ -296,12 +321,14 @@ class _Engine:
                                               net._wfwd.data_ptr() + 2 * r.w_off, r.cout, 1, 1, out.data_ptr(), r.cout, 1,
                                               None, net._pflat.data_ptr() + 4 * r.bias_off, 0, None, 0, None, None, na, no))
         self.plans.append(plan)
-        self.fwd_ops.append(lambda st: _lib.check(L.yb_plan_run(plan, st)))
+        flops = 2.0 * xin.npix * r.cout * r.cin
+        self.conv_flops["fwd"] += flops
+        self.fwd_ops.append(lambda st: self._conv(plan, st, flops, "fwd"))
         self.outs.append(out)
         if self.train:
             dyh = torch.zeros(xin.N, xin.H, xin.W, HEAD_PAD, device=self.dev, dtype=torch.bfloat16)
             self.head_dy.append(dyh)
-            self.tape.append(("head", r, xin, dyh))
+            self.tape.append(("head", r, xin, dyh, flops))
 
     def _build(self):
         net, B, H, W = self.net, self.B, self.H, self.W
@@ -376,7 +403,9 @@ class _Engine:
         for rec in reversed(self.tape):
             kind = rec[0]
             if kind == "head":
-                _, r, xin, dyh = rec
+                _, r, xin, dyh, flops = rec
+                self.conv_flops["dgrad"] += flops
+                self.conv_flops["wgrad"] += flops
                 dyp = dyh.data_ptr()
                 npix = xin.npix
                 wplan = _lib.checkp(L.yb_conv_wgrad_plan(xin.ptr, xin.N, xin.H, xin.W, xin.C, xin.pitch, dyp, HEAD_PAD,
@@ -389,11 +418,11 @@ class _Engine:
                 xin.buf.gw[xin.c0:xin.c0 + xin.C] = True
                 rows = ctypes.c_int(0)
 
-                def op(st, g, r=r, dyp=dyp, npix=npix, wplan=wplan, dplan=dplan, rows=rows):
+                def op(st, g, r=r, dyp=dyp, npix=npix, wplan=wplan, dplan=dplan, rows=rows, flops=flops):
                     _lib.check(L.yb_colsum(dyp, HEAD_PAD, npix, HEAD_PAD, redp, ctypes.byref(rows), st))
                     _lib.check(L.yb_reduce_rows(redp, rows.value, 2 * HEAD_PAD, r.cout, g + 4 * r.bias_off, 0, st))
-                    _lib.check(L.yb_wgrad_plan_run(wplan, g + 4 * r.w_off, r.cout, None, 0, st))
-                    _lib.check(L.yb_plan_run(dplan, st))
+                    self._wgrad(wplan, st, flops, g + 4 * r.w_off, r.cout, None, 0)
+                    self._conv(dplan, st, flops, "dgrad")
                 self.bwd_ops.append(op)
             elif kind == "pool":
                 _, src, dst, am = rec
@@ -404,7 +433,10 @@ class _Engine:
                     L.yb_maxpool5_bwd(dst.gptr, dst.pitch, am.data_ptr(), src.N, src.H, src.W, src.C, src.gptr, src.pitch,
                                       acc, st)))
             else:
-                _, r, xin, out, y, res, up, ptrs = rec
+                _, r, xin, out, y, res, up, ptrs, flops = rec
+                self.conv_flops["wgrad"] += flops
+                if not r.is_stem:
+                    self.conv_flops["dgrad"] += flops
                 C, npix = r.cout, y.npix
                 k, s = (3, 1) if r.is_stem else (r.k, r.stride)
                 self._flush_pending(out)
@@ -442,15 +474,15 @@ class _Engine:
                 count = float(npix)
 
                 def op(st, g, r=r, out=out, y=y, ptrs=ptrs, C=C, npix=npix, wplan=wplan, dplan=dplan, mapp=mapp, rows=rows,
-                       count=count):
+                       count=count, flops=flops):
                     _lib.check(L.yb_bn_act_bwd_reduce(out.gptr, out.pitch, y.ptr, C, npix, C, ptrs[1], ptrs[2], ptrs[3],
                                                       ptrs[4], redp, ctypes.byref(rows), st))
                     _lib.check(L.yb_bn_bwd_finalize(redp, rows.value, C, count, g + 4 * r.g_off, g + 4 * r.b_off, coefp, 0, st))
                     _lib.check(L.yb_bn_act_bwd_apply(out.gptr, out.pitch, y.ptr, C, npix, C, ptrs[1], ptrs[2], ptrs[3],
                                                      ptrs[4], coefp, dy_ptr, C, st))
-                    _lib.check(L.yb_wgrad_plan_run(wplan, g + 4 * r.w_off, C, mapp, 0, st))
+                    self._wgrad(wplan, st, flops, g + 4 * r.w_off, C, mapp, 0)
                     if dplan is not None:
-                        _lib.check(L.yb_plan_run(dplan, st))
+                        self._conv(dplan, st, flops, "dgrad")
                 self.bwd_ops.append(op)
 
     # -- execution

@@ -91,7 +91,8 @@ class GradSync:
             dist.broadcast(self.model.flat_params, src, group=self.group)
             for b in self.model.buffers():
                 dist.broadcast(b, src, group=self.group)
-            self.model.refresh_packed(force=True)
+            if self.model.flat_params.is_cuda:
+                self.model.refresh_packed(force=True)
 
     def all_reduce(self, grads=None):
         if self.world == 1:
