@@ -67,10 +67,12 @@ void yb_plan_destroy(void* plan);
 /* ---- Conv2d weight gradient (autograd of model.py:16 / :162) ---------------------------------------------------
  * dw[co][(kh*ks+kw)*Cin+ci] (+)= sum_{n,ho,wo} dy[n,ho,wo,co] * x[n, ho*s+kh-p, wo*s+kw-p, ci]      (fp32 output)
  * x: conv input (N,H,W,Cin) bf16 NHWC; dy: (N,H/s,W/s,Cout) bf16 NHWC (Cout a multiple of 16; the head pads 255->256
- * and passes out_rows = 255).  workspace: fp32 scratch for the split-K partial tiles (>= Cout*ks*ks*Cin floats; more
- * lets the planner split the pixel reduction over more CTAs).  index_map (optional, int32 [Cout*ks*ks*Cin]): element
+ * and passes out_rows = 255).  workspace: fp32 scratch for the split-K partial tiles, at least
+ * yb_conv_wgrad_workspace_floats(Cin, Cout, ks) floats (one partial tile, channels padded to the 64-wide TMA boxes);
+ * more lets the planner split the pixel reduction over more CTAs.  index_map (optional, int32 [Cout*ks*ks*Cin]): element
  * i of the packed gradient is written to dw[index_map[i]] (skipped when negative) -- used to fold the space-to-depth
  * stem back to its 6x6 layout.  Deterministic: partials are reduced in a fixed order. */
+int64_t yb_conv_wgrad_workspace_floats(int Cin, int Cout, int ks);
 void* yb_conv_wgrad_plan(const void* x, int N, int H, int W, int Cin, int64_t x_pitch, const void* dy, int Cout,
                          int64_t dy_pitch, int ks, int stride, float* workspace, int64_t workspace_floats,
                          int max_splits);

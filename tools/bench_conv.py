@@ -45,6 +45,7 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--only", default="fwd,dgrad,wgrad")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--shapes", default=None, help="comma-separated indices into SHAPES (default: all)")
     a = ap.parse_args()
     L = _lib.lib()
     st = _lib.stream()
@@ -52,7 +53,8 @@ def main():
     rows = []
     tot = {"fwd": 0.0, "dgrad": 0.0, "wgrad": 0.0}
     totf = 0.0
-    for (cin, cout, k, s, ho, cnt) in SHAPES:
+    sel = SHAPES if a.shapes is None else [SHAPES[int(i)] for i in a.shapes.split(",")]
+    for (cin, cout, k, s, ho, cnt) in sel:
         B, hin = a.bs, ho * s
         x = torch.randn(B, hin, hin, cin, device="cuda").to(torch.bfloat16)
         y = torch.empty(B, ho, ho, cout, device="cuda", dtype=torch.bfloat16)

@@ -112,6 +112,10 @@ int yb_plan_run(void* plan, void* stream) {
 
 void yb_plan_destroy(void* plan) { delete reinterpret_cast<YbPlan*>(plan); }
 
+int64_t yb_conv_wgrad_workspace_floats(int Cin, int Cout, int ks) {
+  return (int64_t)wgrad_min_workspace_floats(Cin, Cout, ks);
+}
+
 void* yb_conv_wgrad_plan(const void* x, int N, int H, int W, int Cin, int64_t x_pitch, const void* dy, int Cout,
                          int64_t dy_pitch, int ks, int stride, float* workspace, int64_t workspace_floats,
                          int max_splits) {

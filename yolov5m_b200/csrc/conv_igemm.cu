@@ -326,7 +326,11 @@ static void choose_patch(int W, int H, int NB, int& PW, int& PH, int& PN) {
   }
 }
 
-static int pick_kc(int C) { return (C % 64 == 0) ? 64 : (C % 32 == 0 ? 32 : 16); }
+// channels per K chunk (= TMA box width, 2*KC bytes = swizzle span).  From 48 channels up always 64: a channel count that
+// is not a multiple of 64 is zero-padded by the TMA out-of-bounds fill (no bytes fetched), which keeps the pipeline at
+// full-width 128-byte rows and a third of the stages (C = 48: 1 chunk of 64 instead of 3 chunks of 16).  The matching
+// weight columns of the padded part belong to the next tap (or are out of bounds = 0) and meet zeros.
+static int pick_kc(int C) { return C >= 48 ? 64 : (C % 32 == 0 ? 32 : 16); }
 
 static int pick_block_n(int Cout) {
   const int c16 = (Cout + 15) / 16 * 16;
@@ -400,7 +404,7 @@ int conv_plan_fwd(ConvPlan& pl, const TView& in, const bf16* wp, int ks, int str
   YB_REQUIRE(in.H % stride == 0 && in.W % stride == 0, "conv fwd: odd input for stride 2");
   YB_REQUIRE(out.H == in.H / stride && out.W == in.W / stride && out.N == in.N, "conv fwd: geometry");
   kp.KC = pick_kc(in.C);
-  kp.chunks = in.C / kp.KC;
+  kp.chunks = (in.C + kp.KC - 1) / kp.KC;
   kp.W = out.W;
   kp.H = out.H;
   kp.NB = out.N;
@@ -451,7 +455,7 @@ int conv_plan_dgrad(ConvPlan& pl, const TView& dy, const bf16* wt, int ks, int s
   YB_REQUIRE(dy.C % 16 == 0 && dy.pitch % 8 == 0 && dx.pitch % 8 == 0, "conv dgrad: channel alignment");
   YB_REQUIRE(dy.H == dx.H / stride && dy.W == dx.W / stride && dy.N == dx.N, "conv dgrad: geometry");
   kp.KC = pick_kc(dy.C);
-  kp.chunks = dy.C / kp.KC;
+  kp.chunks = (dy.C + kp.KC - 1) / kp.KC;
   kp.NB = dx.N;
   const int pad = ks / 2;
   int nt = 0;

@@ -5,14 +5,19 @@
 //
 //   dW[co][tap][ci] = sum_{n,ho,wo} dy[n,ho,wo,co] * x[n, ho*s + kh - p, wo*s + kw - p, ci]
 //
-// GEMM view per tap: D[M = co][N = ci] += A[M][K = pixel] * B[N][K = pixel].  Both operands sit in
-// HBM as NHWC, i.e. the GEMM-K dimension (pixels) is the *slow* one: they are MN-major UMMA operands.
-// TMA drops [KP pixels x KC channels] boxes (KC*2 bytes = the swizzle span) into shared memory; the
-// canonical MN-major layout then is   ((KC,n),(8,k)) : ((1,LBO),(KC,SBO))   with
-//   SBO = 8 * KC * 2 bytes  (next group of 8 pixels inside a box),
-//   LBO = KP * KC * 2 bytes (next KC-channel box).
-// The reduction over pixels is split across CTAs (split-K); each work item writes an fp32 partial tile
-// and a second kernel reduces the partials in a fixed order (deterministic, no atomics).
+// GEMM view:  D[M = (tap, ci)][N = co] += A[M][K = pixel] * B[N][K = pixel]
+//   A = the conv input x, shifted per tap;  B = dy.  Both sit in HBM as NHWC, i.e. the GEMM-K dimension (pixels) is the
+//   slow one: both are MN-major UMMA operands.  TMA drops [KP pixels x 64 channels] boxes (128 bytes per pixel row = the
+//   swizzle span) into shared memory; channel counts that are not multiples of 64 are zero-padded by the TMA
+//   out-of-bounds fill (no bytes fetched for them).  Canonical MN-major SWIZZLE_128B layout of a stack of boxes:
+//       ((64, n), (8, k)) : ((1, LBO), (64, SBO)),  SBO = 8 * 128 B (next 8 pixels inside a box),  LBO = KP * 128 B (next box)
+//   An M tile (128 rows) = two boxes = two (tap, 64-channel chunk) pairs, so small-Cin layers waste no tensor-core rows
+//   on padding between taps, and the dy box(es) of a pipeline stage are shared by up to MT M tiles whose accumulators
+//   live side by side in TMEM (MT * BLOCK_N <= 512 columns): dy is fetched once per stage instead of once per tap.
+// The reduction over pixels is split across CTAs (split-K).  Work items that cover the same pixel range run
+// concurrently (item index = split * (m_groups * n_tiles) + ...), so x / dy tiles are served from L2 after the first
+// touch.  Each item writes an fp32 partial tile [Mpad][Npad]; a second kernel reduces the partials in a fixed order
+// (deterministic, no atomics) and transposes them into dW's [co][tap][ci] layout.
 //
 // CTA = 256 threads: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4..7 epilogue.
 #include "conv_wgrad.cuh"
@@ -23,21 +28,20 @@
 namespace yb {
 
 static constexpr int kThreads = 256;
-static constexpr int kMaxStages = 8;
+static constexpr int kMaxStages = 6;
 static constexpr int kBarRegion = 1024;
+static constexpr int kBoxC = 64;  // channels per TMA box (128-byte swizzle span)
 
 struct WItem {
-  int mt, nt, tap, sp;
+  int sp, mg, nt;
 };
 
 __device__ __forceinline__ WItem decode_item(const WgradKParams& p, int t) {
   WItem c;
-  c.sp = t % p.splits;
-  t /= p.splits;
-  c.tap = t % p.ntaps;
-  t /= p.ntaps;
   c.nt = t % p.n_tiles;
-  c.mt = t / p.n_tiles;
+  t /= p.n_tiles;
+  c.mg = t % p.m_groups;
+  c.sp = t / p.m_groups;
   return c;
 }
 
@@ -47,29 +51,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tfull_bar = empty_bar + kMaxStages;
-  uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  uint8_t* a_smem = smem + kBarRegion;  // A stages first: over-reads of unused M rows stay inside the CTA's smem
-  uint8_t* b_smem = a_smem + (size_t)p.stages * p.a_stage_bytes;
+  uint64_t* tempty_bar = tfull_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 1);
+  uint8_t* stage_smem = smem + kBarRegion;  // per stage: [2*MT x boxes][nb dy boxes]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total = p.m_tiles * p.n_tiles * p.ntaps * p.splits;
+  const int total = p.splits * p.m_groups * p.n_tiles;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
-    }
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, 4);
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.tmA);
-    for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.tmB[i]);
+    tma_prefetch_desc(&p.tmDY);
+    for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.tmX[i]);
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
@@ -84,11 +85,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
       uint32_t ph = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
         const WItem it = decode_item(p, t);
-        const ConvTap tap = p.taps[it.tap];
         const int pt0 = (int)(((long)it.sp * p.ptiles) / p.splits);
         const int pt1 = (int)(((long)(it.sp + 1) * p.ptiles) / p.splits);
-        const int a_boxes = min(p.a_boxes, (p.Cout - it.mt * 128 + p.KCA - 1) / p.KCA);
-        const uint32_t tx = (uint32_t)(a_boxes * p.KCA + p.b_boxes * p.KCB) * 2u * p.KP;
+        const int box0 = it.mg * p.MT * 2;
+        const int box1 = min(p.boxes_total, box0 + p.MT * 2);
+        const uint32_t tx = (uint32_t)(box1 - box0 + p.nb) * p.box_bytes;
         for (int pt = pt0; pt < pt1; ++pt) {
           int m = pt;
           const int w0 = (m % p.tiles_w) * p.PW;
@@ -97,13 +98,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
           const int n0 = (m / p.tiles_h) * p.PN;
           mbar_wait(&empty_bar[s], ph ^ 1);
           mbar_expect_tx(&full_bar[s], tx);
-          uint8_t* as = a_smem + (size_t)s * p.a_stage_bytes;
-          uint8_t* bs = b_smem + (size_t)s * p.b_stage_bytes;
-          for (int j = 0; j < a_boxes; ++j)
-            tma_load_4d(&p.tmA, &full_bar[s], as + (size_t)j * p.KP * 2 * p.KCA, it.mt * 128 + j * p.KCA, w0, h0, n0);
-          for (int j = 0; j < p.b_boxes; ++j)
-            tma_load_4d(&p.tmB[tap.map], &full_bar[s], bs + (size_t)j * p.KP * 2 * p.KCB,
-                        it.nt * p.BLOCK_N + j * p.KCB, w0 + tap.dw, h0 + tap.dh, n0);
+          uint8_t* as = stage_smem + (size_t)s * p.stage_bytes;
+          uint8_t* bs = as + (size_t)2 * p.MT * p.box_bytes;
+          for (int j = 0; j < p.nb; ++j)
+            tma_load_4d(&p.tmDY, &full_bar[s], bs + (size_t)j * p.box_bytes, it.nt * p.BLOCK_N + j * kBoxC, w0, h0, n0);
+          int tapi = box0 / p.cboxes, cb = box0 - tapi * p.cboxes;
+          for (int b = box0; b < box1; ++b) {
+            const ConvTap tap = p.taps[tapi];
+            tma_load_4d(&p.tmX[tap.map], &full_bar[s], as + (size_t)(b - box0) * p.box_bytes, cb * kBoxC, w0 + tap.dw,
+                        h0 + tap.dh, n0);
+            if (++cb == p.cboxes) {
+              cb = 0;
+              ++tapi;
+            }
+          }
           if (++s == p.stages) {
             s = 0;
             ph ^= 1;
@@ -115,9 +123,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128, p.BLOCK_N, 1, 1);  // both operands MN-major
-      const uint32_t rbA = 2u * p.KCA, rbB = 2u * p.KCB;
-      const uint32_t ltA = swizzle_layout_type(rbA), ltB = swizzle_layout_type(rbB);
-      const uint32_t lboA = (uint32_t)p.KP * rbA, lboB = (uint32_t)p.KP * rbB;
+      const uint32_t lt = swizzle_layout_type(128);
+      const uint32_t lbo = p.box_bytes;
       const int kinner = p.KP / 16;
       int s = 0;
       uint32_t ph = 0;
@@ -126,20 +133,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
         const WItem it = decode_item(p, t);
         const int pt0 = (int)(((long)it.sp * p.ptiles) / p.splits);
         const int pt1 = (int)(((long)(it.sp + 1) * p.ptiles) / p.splits);
-        const int ab = iter & 1;
-        const uint32_t aph = (iter >> 1) & 1;
-        mbar_wait(&tempty_bar[ab], aph ^ 1);
+        const int mts = min(p.MT, p.m_tiles - it.mg * p.MT);
+        mbar_wait(tempty_bar, (iter & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + ab * 256;
         for (int pt = pt0; pt < pt1; ++pt) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(a_smem + (size_t)s * p.a_stage_bytes);
-          const uint32_t b_addr = smem_u32(b_smem + (size_t)s * p.b_stage_bytes);
-          for (int k = 0; k < kinner; ++k) {
-            const uint64_t da = make_smem_desc(a_addr + k * 16 * rbA, lboA, 8 * rbA, ltA);
-            const uint64_t db = make_smem_desc(b_addr + k * 16 * rbB, lboB, 8 * rbB, ltB);
-            umma_bf16(d_tmem, da, db, idesc, (pt != pt0 || k != 0) ? 1u : 0u);
+          const uint32_t a_addr = smem_u32(stage_smem + (size_t)s * p.stage_bytes);
+          const uint32_t b_addr = a_addr + 2u * p.MT * p.box_bytes;
+          for (int mt = 0; mt < mts; ++mt) {
+            const uint32_t d_tmem = tmem_base + mt * p.BLOCK_N;
+            const uint32_t at = a_addr + (uint32_t)mt * 2u * p.box_bytes;
+            for (int k = 0; k < kinner; ++k) {
+              const uint64_t da = make_smem_desc(at + k * 2048, lbo, 1024, lt);
+              const uint64_t db = make_smem_desc(b_addr + k * 2048, lbo, 1024, lt);
+              umma_bf16(d_tmem, da, db, idesc, (pt != pt0 || k != 0) ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[s]);
           if (++s == p.stages) {
@@ -147,7 +156,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
             ph ^= 1;
           }
         }
-        umma_commit(&tfull_bar[ab]);
+        umma_commit(tfull_bar);
       }
     }
   } else if (warp >= 4) {
@@ -157,29 +166,34 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
     int iter = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++iter) {
       const WItem it = decode_item(p, t);
-      const int co = it.mt * 128 + r;
-      const int ab = iter & 1;
-      const uint32_t aph = (iter >> 1) & 1;
-      float* dst = p.partial + ((size_t)it.sp * p.Cout + co) * p.ldo + p.taps[it.tap].kbase + it.nt * p.BLOCK_N;
-      const int ncols = min(p.BLOCK_N, p.Cin - it.nt * p.BLOCK_N);
-      mbar_wait(&tfull_bar[ab], aph);  // the plan guarantees pt1 > pt0 (splits <= pixel tiles)
+      const int mts = min(p.MT, p.m_tiles - it.mg * p.MT);
+      const int box0 = it.mg * p.MT * 2;
+      const int ncols = min(p.BLOCK_N, ((p.Cout + 15) & ~15) - it.nt * p.BLOCK_N);
+      mbar_wait(tfull_bar, iter & 1);  // the plan guarantees pt1 > pt0 (splits <= pixel tiles)
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 256;
-      for (int cc = 0; cc * 16 < ncols; ++cc) {
-        uint32_t vr[16];
-        tmem_ld16(t_addr + cc * 16, vr);
-        tmem_ld_wait();
-        if (co < p.Cout) {
-          float4* o = reinterpret_cast<float4*>(dst + cc * 16);
+      for (int mt = 0; mt < mts; ++mt) {
+        const int box = box0 + mt * 2 + (r >> 6);
+        const int tapi = box / p.cboxes;
+        const int ci = (box - tapi * p.cboxes) * kBoxC + (r & 63);
+        const bool valid = box < p.boxes_total && ci < p.Cin;
+        float* dst = p.partial + ((size_t)it.sp * p.Mpad + (size_t)tapi * p.Cin_pad + ci) * p.Npad + it.nt * p.BLOCK_N;
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + mt * p.BLOCK_N;
+        for (int cc = 0; cc * 16 < ncols; ++cc) {
+          uint32_t vr[16];
+          tmem_ld16(t_addr + cc * 16, vr);
+          tmem_ld_wait();
+          if (valid) {
+            float4* o = reinterpret_cast<float4*>(dst + cc * 16);
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            o[j] = make_float4(__uint_as_float(vr[4 * j]), __uint_as_float(vr[4 * j + 1]), __uint_as_float(vr[4 * j + 2]),
-                               __uint_as_float(vr[4 * j + 3]));
+            for (int j = 0; j < 4; ++j)
+              o[j] = make_float4(__uint_as_float(vr[4 * j]), __uint_as_float(vr[4 * j + 1]),
+                                 __uint_as_float(vr[4 * j + 2]), __uint_as_float(vr[4 * j + 3]));
+          }
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[ab]);
+      if (lane == 0) mbar_arrive(tempty_bar);
     }
   }
 
@@ -191,48 +205,51 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
   }
 }
 
-// out[map ? map[i] : i] (+)= sum_s partial[s][i]   (fixed summation order => deterministic)
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, long n, long nfull,
-                                    float* __restrict__ out,
+// out[map ? map[i] : i] (+)= sum_s partial[s][tap*Cin_pad + ci][co],  i = co*ldo + tap*Cin + ci
+// Block = 32 (co) x 32 threads; the 32 rows of threads are split into KR k-rows x SL split-lanes (KR * SL = 32): lane sl
+// sums splits sl, sl+SL, ... in order, then a fixed shared-memory tree combines the lanes -> deterministic for a given
+// plan.  Small outputs (many splits) use many split-lanes so that the reduction still fills the machine; reads are
+// coalesced along co, the transposed store goes through shared memory.
+__global__ void __launch_bounds__(1024) wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int Mpad, int Npad, int Cin,
+                                    int Cin_pad, int ldo, int out_rows, int SL, float* __restrict__ out,
                                     const int* __restrict__ map, int accumulate) {
-  const long stride = (long)gridDim.x * blockDim.x;
-  if (map == nullptr) {
-    const long n4 = n >> 2;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-      float4 acc = reinterpret_cast<const float4*>(partial)[i];
-      for (int s = 1; s < splits; ++s) {
-        const float4 v = reinterpret_cast<const float4*>(partial + (size_t)s * nfull)[i];
-        acc.x += v.x;
-        acc.y += v.y;
-        acc.z += v.z;
-        acc.w += v.w;
-      }
-      float4* o = reinterpret_cast<float4*>(out) + i;
-      if (accumulate) {
-        const float4 c = *o;
-        acc.x += c.x;
-        acc.y += c.y;
-        acc.z += c.z;
-        acc.w += c.w;
-      }
-      *o = acc;
+  __shared__ float red[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int KR = 32 / SL;
+  const int kk = ty / SL, sl = ty - kk * SL;
+  const int k = blockIdx.x * KR + kk, co = blockIdx.y * 32 + tx;
+  const size_t sstride = (size_t)Mpad * Npad;
+  float acc = 0.f;
+  if (k < ldo && co < out_rows) {
+    const int tapi = k / Cin;
+    const float* src = partial + ((size_t)tapi * Cin_pad + (k - tapi * Cin)) * Npad + co;
+    int s = sl;
+    for (; s + 3 * SL < splits; s += 4 * SL) {
+      const float v0 = src[(size_t)s * sstride], v1 = src[(size_t)(s + SL) * sstride];
+      const float v2 = src[(size_t)(s + 2 * SL) * sstride], v3 = src[(size_t)(s + 3 * SL) * sstride];
+      acc = (((acc + v0) + v1) + v2) + v3;
     }
-  } else {
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-      const int d = map[i];
-      if (d < 0) continue;
-      float acc = partial[i];
-      for (int s = 1; s < splits; ++s) acc += partial[(size_t)s * nfull + i];
-      out[d] = accumulate ? out[d] + acc : acc;
-    }
+    for (; s < splits; s += SL) acc += src[(size_t)s * sstride];
+  }
+  red[ty][tx] = acc;
+  __syncthreads();
+  for (int off = SL >> 1; off > 0; off >>= 1) {
+    if (sl < off) red[ty][tx] += red[ty + off][tx];
+    __syncthreads();
+  }
+  // transposed store: thread (a = ty, b = tx) -> co = co0 + a, k-row b (b < KR); totals sit in red[b * SL][a]
+  const int co2 = blockIdx.y * 32 + ty, k2 = blockIdx.x * KR + tx;
+  if (tx < KR && k2 < ldo && co2 < out_rows) {
+    const float v = red[tx * SL][ty];
+    long i = (long)co2 * ldo + k2;
+    if (map != nullptr) i = map[i];
+    if (i >= 0) out[i] = accumulate ? out[i] + v : v;
   }
 }
 
 // ------------------------------------------------------------------------------------------------ host
-static int pick_kc(int C) { return (C % 64 == 0) ? 64 : (C % 32 == 0 ? 32 : 16); }
-
 // pixel patch with PW*PH*PN a multiple of 16 and <= maxp, minimising the padded pixel count
-static void choose_kpatch(int W, int H, int NB, int maxp, int& PW, int& PH, int& PN) {
+static bool choose_kpatch(int W, int H, int NB, int maxp, int& PW, int& PH, int& PN) {
   double best = -1;
   for (int pw = 1; pw <= std::min(W, 256); ++pw)
     for (int ph = 1; ph <= std::min(H, 256) && pw * ph <= maxp; ++ph)
@@ -255,61 +272,101 @@ static void choose_kpatch(int W, int H, int NB, int maxp, int& PW, int& PH, int&
     PW = 16;
     PH = 1;
     PN = 1;
+    return maxp >= 16;
   }
+  return true;
 }
 
-static int make_map(CUtensorMap* m, const TView& v, int KC, int PW, int PH, int PN, int py, int px, int sy, int sx) {
+static int make_map(CUtensorMap* m, const TView& v, int PW, int PH, int PN, int py, int px, int sy, int sx) {
   const bf16* base = reinterpret_cast<const bf16*>(v.ptr) + ((long)py * v.W + px) * v.pitch;
   uint64_t dims[4] = {(uint64_t)v.C, (uint64_t)(v.W / sx), (uint64_t)(v.H / sy), (uint64_t)v.N};
   uint64_t strides[3] = {(uint64_t)v.pitch * sx * 2, (uint64_t)v.pitch * v.W * sy * 2,
                          (uint64_t)v.pitch * v.W * v.H * 2};
-  uint32_t box[4] = {(uint32_t)KC, (uint32_t)PW, (uint32_t)PH, (uint32_t)PN};
-  return encode_tmap(m, base, 4, dims, strides, box, 2 * KC, 2);
+  uint32_t box[4] = {(uint32_t)kBoxC, (uint32_t)PW, (uint32_t)PH, (uint32_t)PN};
+  return encode_tmap(m, base, 4, dims, strides, box, 128, 2);
 }
 
 int wgrad_max_grid();
 
-size_t wgrad_workspace_floats(int Cout, int Cin, int ks, int splits) { return (size_t)splits * Cout * ks * ks * Cin; }
+static int pick_block_n(int Cout, int& n_tiles) {
+  const int c64 = (Cout + kBoxC - 1) / kBoxC;  // dy boxes in total
+  n_tiles = (c64 + 3) / 4;                     // <= 4 boxes (256 columns) per N tile
+  return (c64 + n_tiles - 1) / n_tiles * kBoxC;
+}
+
+size_t wgrad_min_workspace_floats(int Cin, int Cout, int ks) {
+  int n_tiles;
+  const int bn = pick_block_n(Cout, n_tiles);
+  const size_t cin_pad = (size_t)(Cin + kBoxC - 1) / kBoxC * kBoxC;
+  return (size_t)ks * ks * cin_pad * n_tiles * bn;
+}
 
 int wgrad_plan(WgradPlan& pl, const TView& x, const TView& dy, int ks, int stride, float* partial, size_t partial_floats,
                int max_splits) {
   memset(&pl, 0, sizeof(pl));
   WgradKParams& kp = pl.kp;
   YB_REQUIRE((ks == 1 || ks == 3) && (stride == 1 || stride == 2), "wgrad: ks=%d stride=%d unsupported", ks, stride);
-  YB_REQUIRE(x.C % 16 == 0 && dy.C % 16 == 0 && x.pitch % 8 == 0 && dy.pitch % 8 == 0, "wgrad: channel alignment");
+  YB_REQUIRE(x.C % 8 == 0 && dy.C % 8 == 0 && x.pitch % 8 == 0 && dy.pitch % 8 == 0, "wgrad: channel alignment");
   YB_REQUIRE(dy.H == x.H / stride && dy.W == x.W / stride && dy.N == x.N, "wgrad: geometry");
+  YB_REQUIRE(x.H % stride == 0 && x.W % stride == 0, "wgrad: odd input for stride 2");
   kp.Cout = dy.C;
   kp.Cin = x.C;
-  kp.KCA = pick_kc(dy.C);
-  kp.KCB = pick_kc(x.C);
-  kp.a_boxes = 128 / kp.KCA;
-  kp.m_tiles = (dy.C + 127) / 128;
-  {
-    const int parts = (x.C + 255) / 256;
-    int bn = ((x.C + parts - 1) / parts + kp.KCB - 1) / kp.KCB * kp.KCB;
-    kp.BLOCK_N = bn;
-    kp.n_tiles = (x.C + bn - 1) / bn;
-    kp.b_boxes = bn / kp.KCB;
-  }
-  YB_REQUIRE(kp.BLOCK_N % 16 == 0 && kp.BLOCK_N <= 256, "wgrad: BLOCK_N=%d", kp.BLOCK_N);
-  YB_REQUIRE(x.C % kp.BLOCK_N == 0, "wgrad: Cin=%d not a multiple of the N tile %d", x.C, kp.BLOCK_N);
-  // stage = (128 + BLOCK_N) channels x KP pixels x 2 bytes: shrink the pixel patch until >= 3 stages fit
+  kp.ntaps = ks * ks;
+  kp.cboxes = (x.C + kBoxC - 1) / kBoxC;
+  kp.Cin_pad = kp.cboxes * kBoxC;
+  kp.boxes_total = kp.ntaps * kp.cboxes;
+  kp.m_tiles = (kp.boxes_total + 1) / 2;
+  kp.BLOCK_N = pick_block_n(dy.C, kp.n_tiles);
+  kp.nb = kp.BLOCK_N / kBoxC;
+  kp.Mpad = kp.ntaps * kp.Cin_pad;
+  kp.Npad = kp.n_tiles * kp.BLOCK_N;
+  kp.ldo = kp.ntaps * x.C;
+  // pixel patch (GEMM-K chunk) and the number of M tiles that share one dy stage: minimise the L2 -> shared-memory
+  // bytes per MMA (nb + 2*MT boxes feed MT tiles) under >= 2 (preferably >= 3) pipeline stages of shared memory
+  const size_t budget = 227 * 1024 - 1024 - kBarRegion;
+  const int mt_max = std::max(1, std::min(512 / kp.BLOCK_N, kp.m_tiles));
+  double best = -1;
+  const double real_px = (double)dy.W * dy.H * dy.N;
   for (int maxp = 128; maxp >= 16; maxp -= 16) {
-    choose_kpatch(dy.W, dy.H, dy.N, maxp, kp.PW, kp.PH, kp.PN);
-    kp.KP = kp.PW * kp.PH * kp.PN;
-    if ((size_t)(128 + kp.BLOCK_N) * 2 * kp.KP * 3 <= 220 * 1024) break;
+    int PW, PH, PN;
+    if (!choose_kpatch(dy.W, dy.H, dy.N, maxp, PW, PH, PN)) continue;
+    const int KP = PW * PH * PN;
+    if (KP % 16 || KP > 256) continue;
+    const double padded = (double)((dy.W + PW - 1) / PW) * PW * ((dy.H + PH - 1) / PH) * PH * ((dy.N + PN - 1) / PN) * PN;
+    for (int mt = mt_max; mt >= 1; --mt) {
+      const size_t stage = (size_t)(kp.nb + 2 * mt) * KP * 128;
+      const int stages = (int)std::min<size_t>(kMaxStages, budget / stage);
+      if (stages < 2) continue;
+      const int groups = (kp.m_tiles + mt - 1) / mt;
+      const double boxes_per_tile = (double)(groups * kp.nb + 2 * kp.m_tiles) / kp.m_tiles;
+      const double score = boxes_per_tile * (padded / real_px) * (1.0 + 12.0 / KP) * (stages >= 3 ? 1.0 : 1.3);
+      if (best < 0 || score < best) {
+        best = score;
+        kp.PW = PW;
+        kp.PH = PH;
+        kp.PN = PN;
+        kp.KP = KP;
+        kp.MT = mt;
+        kp.stages = stages;
+      }
+    }
   }
-  YB_REQUIRE(kp.KP % 16 == 0 && kp.KP <= 256, "wgrad: pixel patch %dx%dx%d", kp.PW, kp.PH, kp.PN);
+  YB_REQUIRE(best >= 0, "wgrad: no pixel patch fits in shared memory (W=%d H=%d N=%d)", dy.W, dy.H, dy.N);
+  kp.m_groups = (kp.m_tiles + kp.MT - 1) / kp.MT;
+  kp.MT = (kp.m_tiles + kp.m_groups - 1) / kp.m_groups;  // balance the groups
+  kp.box_bytes = (uint32_t)kp.KP * 128u;
+  kp.stage_bytes = (uint32_t)(kp.nb + 2 * kp.MT) * kp.box_bytes;
+  kp.stages = (int)std::min<size_t>(kMaxStages, budget / kp.stage_bytes);
   kp.tiles_w = (dy.W + kp.PW - 1) / kp.PW;
   kp.tiles_h = (dy.H + kp.PH - 1) / kp.PH;
   kp.tiles_n = (dy.N + kp.PN - 1) / kp.PN;
   kp.ptiles = kp.tiles_w * kp.tiles_h * kp.tiles_n;
-  if (make_map(&kp.tmA, dy, kp.KCA, kp.PW, kp.PH, kp.PN, 0, 0, 1, 1)) return -1;
+  if (make_map(&kp.tmDY, dy, kp.PW, kp.PH, kp.PN, 0, 0, 1, 1)) return -1;
   const int pad = ks / 2;
   int nt = 0;
   if (stride == 1) {
-    if (make_map(&kp.tmB[0], x, kp.KCB, kp.PW, kp.PH, kp.PN, 0, 0, 1, 1)) return -1;
-    for (int i = 1; i < 4; ++i) kp.tmB[i] = kp.tmB[0];
+    if (make_map(&kp.tmX[0], x, kp.PW, kp.PH, kp.PN, 0, 0, 1, 1)) return -1;
+    for (int i = 1; i < 4; ++i) kp.tmX[i] = kp.tmX[0];
     for (int kh = 0; kh < ks; ++kh)
       for (int kw = 0; kw < ks; ++kw) {
         kp.taps[nt] = ConvTap{0, (int8_t)(kw - pad), (int8_t)(kh - pad), 0, (int32_t)((kh * ks + kw) * x.C)};
@@ -318,7 +375,7 @@ int wgrad_plan(WgradPlan& pl, const TView& x, const TView& dy, int ks, int strid
   } else {
     for (int py = 0; py < 2; ++py)
       for (int px = 0; px < 2; ++px)
-        if (make_map(&kp.tmB[py * 2 + px], x, kp.KCB, kp.PW, kp.PH, kp.PN, py, px, 2, 2)) return -1;
+        if (make_map(&kp.tmX[py * 2 + px], x, kp.PW, kp.PH, kp.PN, py, px, 2, 2)) return -1;
     for (int kh = 0; kh < ks; ++kh)
       for (int kw = 0; kw < ks; ++kw) {
         const int oy = kh - pad, ox = kw - pad;
@@ -328,26 +385,15 @@ int wgrad_plan(WgradPlan& pl, const TView& x, const TView& dy, int ks, int strid
         ++nt;
       }
   }
-  kp.ntaps = nt;
-  kp.ldo = nt * x.C;
-  kp.a_stage_bytes = 128u * 2u * kp.KP;
-  kp.b_stage_bytes = (uint32_t)kp.BLOCK_N * 2u * kp.KP;
-  kp.a_stage_bytes = (kp.a_stage_bytes + 1023u) & ~1023u;
-  kp.b_stage_bytes = (kp.b_stage_bytes + 1023u) & ~1023u;
-  const size_t budget = 227 * 1024 - 1024 - kBarRegion;
-  int stages = (int)(budget / (kp.a_stage_bytes + kp.b_stage_bytes));
-  stages = std::min(stages, kMaxStages);
-  YB_REQUIRE(stages >= 2, "wgrad: tile does not fit in shared memory");
-  kp.stages = stages;
-  pl.smem = (int)(1024 + kBarRegion + (size_t)stages * (kp.a_stage_bytes + kp.b_stage_bytes));
-  pl.smem = std::max(pl.smem, 120 * 1024);
-  // split-K: fill the machine, at least ~4 pixel tiles per item
-  const int base_items = kp.m_tiles * kp.n_tiles * kp.ntaps;
+  pl.smem = (int)(1024 + kBarRegion + (size_t)kp.stages * kp.stage_bytes);
+  pl.smem = std::max(pl.smem, 120 * 1024);  // one CTA per SM: each CTA allocates all 512 TMEM columns
+  // split-K: two waves of work items, >= 8 pixel tiles per item (never an empty split)
+  const int base_items = kp.m_groups * kp.n_tiles;
   const int sms = wgrad_max_grid();
-  int splits = std::max(1, (2 * sms + base_items - 1) / base_items);
-  splits = std::min(splits, std::max(1, kp.ptiles / 4));  // >= 4 pixel tiles per item (never an empty split)
+  int splits = std::max(1, (2 * sms) / base_items);
+  splits = std::min(splits, std::max(1, kp.ptiles / 8));
   if (max_splits > 0) splits = std::min(splits, max_splits);
-  const size_t per_split = (size_t)kp.Cout * kp.ldo;
+  const size_t per_split = (size_t)kp.Mpad * kp.Npad;
   splits = (int)std::min<size_t>(splits, partial_floats / per_split);
   YB_REQUIRE(splits >= 1, "wgrad: workspace too small (%zu floats, need >= %zu)", partial_floats, per_split);
   kp.splits = splits;
@@ -373,13 +419,17 @@ int wgrad_run(const WgradPlan& pl, float* out, int out_rows, const int* map, int
     YB_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
+  YB_REQUIRE(out_rows > 0 && out_rows <= pl.kp.Cout, "wgrad: out_rows=%d", out_rows);
   conv_wgrad_kernel<<<pl.grid, kThreads, pl.smem, st>>>(pl.kp);
   YB_LAUNCHED();
-  YB_REQUIRE(out_rows > 0 && out_rows <= pl.kp.Cout, "wgrad: out_rows=%d", out_rows);
-  const long n = (long)out_rows * pl.kp.ldo;
-  const long nfull = (long)pl.kp.Cout * pl.kp.ldo;
-  const int blocks = (int)std::min<long>((n / 4 + 255) / 256 + 1, 4L * wgrad_max_grid());
-  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(pl.kp.partial, pl.kp.splits, n, nfull, out, map, accumulate);
+  const WgradKParams& kp = pl.kp;
+  // split-lanes: enough threads to fill the machine even when the output is tiny and the split count large
+  int SL = 1;
+  while (SL < 32 && SL * 2 <= kp.splits && (long)kp.ldo * out_rows * SL < 148L * 2048) SL *= 2;
+  const int KR = 32 / SL;
+  dim3 grid((kp.ldo + KR - 1) / KR, (out_rows + 31) / 32);
+  wgrad_reduce_kernel<<<grid, 1024, 0, st>>>(kp.partial, kp.splits, kp.Mpad, kp.Npad, kp.Cin, kp.Cin_pad, kp.ldo, out_rows,
+                                              SL, out, map, accumulate);
   YB_LAUNCHED();
   return 0;
 }

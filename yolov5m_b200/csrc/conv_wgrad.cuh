@@ -5,20 +5,22 @@
 namespace yb {
 
 struct WgradKParams {
-  CUtensorMap tmA;     // dy  (Cout, Wo, Ho, N), box (KCA, PW, PH, PN)
-  CUtensorMap tmB[4];  // x   (Cin, W/s, H/s, N) per input parity, box (KCB, PW, PH, PN)
+  CUtensorMap tmDY;    // dy  (Cout, Wo, Ho, N), box (64, PW, PH, PN)
+  CUtensorMap tmX[4];  // x   (Cin, W/s, H/s, N) per input parity, box (64, PW, PH, PN)
   ConvTap taps[16];    // kbase = tap * Cin (column of the tap inside one dW row)
   int32_t ntaps;
-  int32_t KCA, KCB;          // channels per TMA box (16/32/64 <-> 32/64/128-byte swizzle)
-  int32_t a_boxes, b_boxes;  // boxes per 128-row M tile / per N tile
-  int32_t BLOCK_N;
+  int32_t cboxes;            // 64-channel boxes per tap = ceil(Cin / 64)
+  int32_t boxes_total;       // ntaps * cboxes; M tile t = boxes 2t, 2t+1
+  int32_t m_tiles, MT, m_groups;  // 128-row M tiles, tiles per work item (TMEM accumulators), items along M
+  int32_t nb, BLOCK_N, n_tiles;   // dy boxes per N tile, N tile width (multiple of 64, <= 256), N tiles
   int32_t KP, PW, PH, PN;    // pixels per pipeline stage (GEMM-K chunk) and its patch shape
   int32_t tiles_w, tiles_h, tiles_n, ptiles;
-  int32_t m_tiles, n_tiles, splits;
-  int32_t Cout, Cin, ldo;    // ldo = ntaps * Cin = row length of dW
+  int32_t splits;
+  int32_t Cout, Cin, Cin_pad, ldo;  // ldo = ntaps * Cin = row length of dW
+  int32_t Mpad, Npad;        // partial tile: [Mpad = ntaps*Cin_pad][Npad = n_tiles*BLOCK_N]
   int32_t stages;
-  uint32_t a_stage_bytes, b_stage_bytes;
-  float* partial;            // [splits][Cout][ldo]
+  uint32_t box_bytes, stage_bytes;
+  float* partial;            // [splits][Mpad][Npad]
 };
 
 struct WgradPlan {
@@ -30,8 +32,10 @@ struct WgradPlan {
 // x: conv input (N,H,W,Cin); dy: grad of the conv output (N,H/s,W/s,Cout).
 int wgrad_plan(WgradPlan& pl, const TView& x, const TView& dy, int ks, int stride, float* partial,
                size_t partial_floats, int max_splits);
-// runs the split-K GEMM and the ordered reduction: out[map ? map[i] : i] (+)= sum_s partial[s][i], i over [Cout][ldo]
-// (i over the first out_rows rows of [Cout][ldo])
+// runs the split-K GEMM and the ordered reduction + transpose:
+//   out[map ? map[i] : i] (+)= sum_s partial[s][tap*Cin_pad+ci][co],  i = co*ldo + tap*Cin + ci,  co < out_rows
 int wgrad_run(const WgradPlan& pl, float* out, int out_rows, const int* map, int accumulate, cudaStream_t st);
+// minimum workspace (one split) for a layer
+size_t wgrad_min_workspace_floats(int Cin, int Cout, int ks);
 
 }  // namespace yb

@@ -28,6 +28,14 @@ static inline int ew_blocks(long n, int threads = 256, int per_sm = 8) {
   return (int)std::max<long>(1, std::min<long>(b, (long)sms * per_sm));
 }
 
+// resident-CTA-exact grid for a grid-stride kernel: #SMs x occupancy (one full wave, no tail), capped by the work
+template <typename K>
+static int ew_wave_grid(K kernel, int threads, long work_items) {
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, 0) != cudaSuccess || occ <= 0) occ = 2;
+  return ew_blocks(work_items, threads, occ);
+}
+
 struct V8 {
   float v[8];
 };
@@ -50,6 +58,21 @@ __device__ __forceinline__ void st8(bf16* p, const V8& a) {
   for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(a.v[2 * j], a.v[2 * j + 1]);
   *reinterpret_cast<uint4*>(p) = r;
 }
+__device__ __forceinline__ V8 cvt8(const uint4& r) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+  V8 o;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __bfloat1622float2(h[j]);
+    o.v[2 * j] = f.x;
+    o.v[2 * j + 1] = f.y;
+  }
+  return o;
+}
+__device__ __forceinline__ uint4 ldraw(const bf16* p) { return *reinterpret_cast<const uint4*>(p); }
+// SiLU / its derivative with the fast reciprocal (2 ulp): these passes are HBM-bound, keep the ALU work minimal
+__device__ __forceinline__ float sigmoid_fast(float z) { return __fdividef(1.f, 1.f + __expf(-z)); }
+__device__ __forceinline__ float silu_fast(float z) { return z * sigmoid_fast(z); }
 __device__ __forceinline__ V8 ldf8(const float* p) {
   const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
   V8 o;
@@ -59,22 +82,47 @@ __device__ __forceinline__ V8 ldf8(const float* p) {
 }
 
 // ------------------------------------------------------------------------------------------------ BN finalize
-// one thread per channel.  training: mean/var from the per-CTA partial sums written by the conv epilogue.
-__global__ void bn_finalize_kernel(const float* __restrict__ stats, int rows, int C, double count,
+// block = 32 channels x 32 row-lanes: the [rows][2][C] partials are summed in double (fixed order: row-lane strided, then a
+// shared-memory tree) so the result is deterministic; 128-byte coalesced reads.
+__device__ __forceinline__ void colsum2_block(const float* __restrict__ part, int rows, int C, int c, bool cvalid,
+                                              double& s_out, double& q_out) {
+  __shared__ double sh_s[32][33], sh_q[32][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  double s = 0.0, q = 0.0;
+  if (cvalid) {
+    for (int r = ry; r < rows; r += 32) {
+      s += (double)part[(size_t)r * 2 * C + c];
+      q += (double)part[(size_t)r * 2 * C + C + c];
+    }
+  }
+  sh_s[ry][cx] = s;
+  sh_q[ry][cx] = q;
+  __syncthreads();
+  for (int off = 16; off > 0; off >>= 1) {
+    if (ry < off) {
+      sh_s[ry][cx] += sh_s[ry + off][cx];
+      sh_q[ry][cx] += sh_q[ry + off][cx];
+    }
+    __syncthreads();
+  }
+  s_out = sh_s[0][cx];
+  q_out = sh_q[0][cx];
+}
+
+// training: mean/var from the per-CTA partial sums written by the conv epilogue.
+__global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restrict__ stats, int rows, int C, double count,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                    float momentum, float* running_mean, float* running_var, long long* nbt,
                                    float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
                                    float* __restrict__ invstd_out, int training) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && training && nbt != nullptr) *nbt += 1;
-  if (c >= C) return;
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const bool cvalid = c < C;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && training && nbt != nullptr) *nbt += 1;
+  double s = 0.0, q = 0.0;
+  if (training) colsum2_block(stats, rows, C, c, cvalid, s, q);
+  if (!cvalid || threadIdx.x >= 32) return;
   float mean, var;
   if (training) {
-    double s = 0.0, q = 0.0;
-    for (int r = 0; r < rows; ++r) {
-      s += (double)stats[(size_t)r * 2 * C + c];
-      q += (double)stats[(size_t)r * 2 * C + C + c];
-    }
     const double m = s / count;
     double v = q / count - m * m;
     if (v < 0.0) v = 0.0;
@@ -98,21 +146,24 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, int rows, in
 }
 
 // ------------------------------------------------------------------------------------------------ BN apply + SiLU
-__global__ void bn_act_fwd_kernel(const bf16* __restrict__ y, long y_pitch, int H, int W, int C, long npix,
+// kEwThreads = 192 = 2^6 * 3: for every channel count of the network (C/8 in {2,6,12,24,48,96,192}) the grid-stride
+// (gridDim * 192) is a multiple of C/8, so a thread keeps ONE channel vector for its whole life: the per-channel
+// parameters are loaded once, the pixel index advances by a constant, and kEwUnroll independent 16-byte loads are in
+// flight per thread and operand.  FIXED = false is the generic (any C % 8 == 0) path.
+static constexpr int kEwThreads = 192;
+static constexpr int kEwUnroll = 4;
+
+template <bool FIXED>
+__global__ void __launch_bounds__(kEwThreads) bn_act_fwd_kernel(const bf16* __restrict__ y, long y_pitch, int H, int W, int C, long npix,
                                   const float* __restrict__ scale, const float* __restrict__ shift,
                                   const bf16* __restrict__ res, long res_pitch, bf16* __restrict__ out, long out_pitch,
                                   bf16* __restrict__ out_up, long up_pitch) {
-  const int cv = C >> 3;
-  const long total = npix * cv;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const long pix = i / cv;
-    const int c = (int)(i - pix * cv) << 3;
-    V8 v = ld8(y + pix * y_pitch + c);
-    const V8 sc = ldf8(scale + c), sh = ldf8(shift + c);
+  const unsigned cv = C >> 3;
+  auto finish = [&](long pix, unsigned c, V8 v, const V8& sc, const V8& sh, const uint4* rraw) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v.v[j] = silu_f(fmaf(v.v[j], sc.v[j], sh.v[j]));
-    if (res != nullptr) {
-      const V8 r = ld8(res + pix * res_pitch + c);
+    for (int j = 0; j < 8; ++j) v.v[j] = silu_fast(fmaf(v.v[j], sc.v[j], sh.v[j]));
+    if (rraw != nullptr) {
+      const V8 r = cvt8(*rraw);
 #pragma unroll
       for (int j = 0; j < 8; ++j) v.v[j] += r.v[j];
     }
@@ -125,6 +176,40 @@ __global__ void bn_act_fwd_kernel(const bf16* __restrict__ y, long y_pitch, int 
       st8(u + up_pitch, v);
       st8(u + 2 * W * up_pitch, v);
       st8(u + (2 * W + 1) * up_pitch, v);
+    }
+  };
+  if (FIXED) {
+    const unsigned T = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned c = (tid % cv) << 3;
+    const long pstep = T / cv;
+    const V8 sc = ldf8(scale + c), sh = ldf8(shift + c);
+    long pix = tid / cv;
+    for (; pix + (kEwUnroll - 1) * pstep < npix; pix += kEwUnroll * pstep) {
+      uint4 yr[kEwUnroll], rr[kEwUnroll];
+#pragma unroll
+      for (int u = 0; u < kEwUnroll; ++u) yr[u] = ldraw(y + (pix + u * pstep) * y_pitch + c);
+      if (res != nullptr) {
+#pragma unroll
+        for (int u = 0; u < kEwUnroll; ++u) rr[u] = ldraw(res + (pix + u * pstep) * res_pitch + c);
+      }
+#pragma unroll
+      for (int u = 0; u < kEwUnroll; ++u) finish(pix + u * pstep, c, cvt8(yr[u]), sc, sh, res != nullptr ? &rr[u] : nullptr);
+    }
+    for (; pix < npix; pix += pstep) {
+      const uint4 yr = ldraw(y + pix * y_pitch + c);
+      uint4 rr = make_uint4(0, 0, 0, 0);
+      if (res != nullptr) rr = ldraw(res + pix * res_pitch + c);
+      finish(pix, c, cvt8(yr), sc, sh, res != nullptr ? &rr : nullptr);
+    }
+  } else {
+    const long total = npix * cv;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+      const long pix = i / cv;
+      const unsigned c = (unsigned)(i - pix * cv) << 3;
+      const uint4 yr = ldraw(y + pix * y_pitch + c);
+      uint4 rr = make_uint4(0, 0, 0, 0);
+      if (res != nullptr) rr = ldraw(res + pix * res_pitch + c);
+      finish(pix, c, cvt8(yr), ldf8(scale + c), ldf8(shift + c), res != nullptr ? &rr : nullptr);
     }
   }
 }
@@ -193,14 +278,14 @@ __global__ void add_into_kernel(const bf16* __restrict__ src, long src_pitch, bf
 
 // ------------------------------------------------------------------------------------------------ BN + SiLU backward
 __device__ __forceinline__ float dsilu_f(float z) {
-  const float s = 1.f / (1.f + __expf(-z));
-  return s * (1.f + z * (1.f - s));
+  const float s = sigmoid_fast(z);
+  return s * fmaf(z, 1.f - s, 1.f);
 }
 
 // pass 1: per-channel sums of dz and dz*xhat, dz = da * silu'(y*scale+shift), xhat = (y-mean)*invstd.
 // block = (rows x cv) threads; every block owns a contiguous pixel range; partial[block][2][C].
 // mode 1: plain column sums of `da` (head bias gradient): partial[block][0][C] only.
-__global__ void bn_act_bwd_reduce_kernel(const bf16* __restrict__ da, long da_pitch, const bf16* __restrict__ y,
+__global__ void __launch_bounds__(256, 3) bn_act_bwd_reduce_kernel(const bf16* __restrict__ da, long da_pitch, const bf16* __restrict__ y,
                                          long y_pitch, long npix, int C, const float* __restrict__ scale,
                                          const float* __restrict__ shift, const float* __restrict__ mean,
                                          const float* __restrict__ invstd, float* __restrict__ partial, int rows_pb,
@@ -219,20 +304,38 @@ __global__ void bn_act_bwd_reduce_kernel(const bf16* __restrict__ da, long da_pi
     if (mode == 0) {
       sc = ldf8(scale + c); sh = ldf8(shift + c); mu = ldf8(mean + c); is = ldf8(invstd + c);
     }
-    for (long p = p0 + row; p < p1; p += rows_pb) {
-      const V8 g = ld8(da + p * da_pitch + c);
+    auto accum = [&](const uint4& graw, const uint4& yraw) {
+      const V8 g = cvt8(graw);
       if (mode == 0) {
-        const V8 yv = ld8(y + p * y_pitch + c);
+        const V8 yv = cvt8(yraw);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float dz = g.v[j] * dsilu_f(fmaf(yv.v[j], sc.v[j], sh.v[j]));
           s1[j] += dz;
-          s2[j] += dz * ((yv.v[j] - mu.v[j]) * is.v[j]);
+          s2[j] = fmaf(dz, (yv.v[j] - mu.v[j]) * is.v[j], s2[j]);
         }
       } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) s1[j] += g.v[j];
       }
+    };
+    long p = p0 + row;
+    for (; p + (kEwUnroll - 1) * (long)rows_pb < p1; p += kEwUnroll * (long)rows_pb) {
+      uint4 gr[kEwUnroll], yr[kEwUnroll];
+#pragma unroll
+      for (int u = 0; u < kEwUnroll; ++u) gr[u] = ldraw(da + (p + u * (long)rows_pb) * da_pitch + c);
+      if (mode == 0) {
+#pragma unroll
+        for (int u = 0; u < kEwUnroll; ++u) yr[u] = ldraw(y + (p + u * (long)rows_pb) * y_pitch + c);
+      }
+#pragma unroll
+      for (int u = 0; u < kEwUnroll; ++u) accum(gr[u], yr[u]);
+    }
+    for (; p < p1; p += rows_pb) {
+      const uint4 gr = ldraw(da + p * da_pitch + c);
+      uint4 yr = make_uint4(0, 0, 0, 0);
+      if (mode == 0) yr = ldraw(y + p * y_pitch + c);
+      accum(gr, yr);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -249,16 +352,14 @@ __global__ void bn_act_bwd_reduce_kernel(const bf16* __restrict__ da, long da_pi
 }
 
 // dgamma = sum dz*xhat, dbeta = sum dz; coef[0][c] = dbeta/m, coef[1][c] = dgamma/m
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int rows, int C, double count,
+__global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __restrict__ partial, int rows, int C, double count,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef,
                                        int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0, q = 0.0;
-  for (int r = 0; r < rows; ++r) {
-    s += (double)partial[(size_t)r * 2 * C + c];
-    q += (double)partial[(size_t)r * 2 * C + C + c];
-  }
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const bool cvalid = c < C;
+  double s, q;
+  colsum2_block(partial, rows, C, c, cvalid, s, q);
+  if (!cvalid || threadIdx.x >= 32) return;
   if (dbeta) dbeta[c] = accumulate ? dbeta[c] + (float)s : (float)s;
   if (dgamma) dgamma[c] = accumulate ? dgamma[c] + (float)q : (float)q;
   if (coef) {
@@ -268,28 +369,57 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int ro
 }
 
 // pass 2: dy = scale * (dz - coef0 - xhat*coef1)
-__global__ void bn_act_bwd_apply_kernel(const bf16* __restrict__ da, long da_pitch, const bf16* __restrict__ y,
+template <bool FIXED>
+__global__ void __launch_bounds__(kEwThreads) bn_act_bwd_apply_kernel(const bf16* __restrict__ da, long da_pitch, const bf16* __restrict__ y,
                                         long y_pitch, long npix, int C, const float* __restrict__ scale,
                                         const float* __restrict__ shift, const float* __restrict__ mean,
                                         const float* __restrict__ invstd, const float* __restrict__ coef,
                                         bf16* __restrict__ dy, long dy_pitch) {
-  const int cv = C >> 3;
-  const long total = npix * cv;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const long pix = i / cv;
-    const int c = (int)(i - pix * cv) << 3;
-    const V8 g = ld8(da + pix * da_pitch + c);
-    const V8 yv = ld8(y + pix * y_pitch + c);
-    const V8 sc = ldf8(scale + c), sh = ldf8(shift + c), mu = ldf8(mean + c), is = ldf8(invstd + c);
-    const V8 c0 = ldf8(coef + c), c1 = ldf8(coef + C + c);
+  const unsigned cv = C >> 3;
+  struct Par {
+    V8 sc, sh, mu, is, c0, c1;
+  };
+  auto load_par = [&](unsigned c) {
+    Par q;
+    q.sc = ldf8(scale + c); q.sh = ldf8(shift + c); q.mu = ldf8(mean + c); q.is = ldf8(invstd + c);
+    q.c0 = ldf8(coef + c); q.c1 = ldf8(coef + C + c);
+    return q;
+  };
+  auto finish = [&](long pix, unsigned c, const uint4& graw, const uint4& yraw, const Par& q) {
+    const V8 g = cvt8(graw), yv = cvt8(yraw);
     V8 o;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float dz = g.v[j] * dsilu_f(fmaf(yv.v[j], sc.v[j], sh.v[j]));
-      const float xh = (yv.v[j] - mu.v[j]) * is.v[j];
-      o.v[j] = sc.v[j] * (dz - c0.v[j] - xh * c1.v[j]);
+      const float dz = g.v[j] * dsilu_f(fmaf(yv.v[j], q.sc.v[j], q.sh.v[j]));
+      const float xh = (yv.v[j] - q.mu.v[j]) * q.is.v[j];
+      o.v[j] = q.sc.v[j] * (dz - q.c0.v[j] - xh * q.c1.v[j]);
     }
     st8(dy + pix * dy_pitch + c, o);
+  };
+  if (FIXED) {
+    const unsigned T = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned c = (tid % cv) << 3;
+    const long pstep = T / cv;
+    const Par q = load_par(c);
+    long pix = tid / cv;
+    for (; pix + (kEwUnroll - 1) * pstep < npix; pix += kEwUnroll * pstep) {
+      uint4 gr[kEwUnroll], yr[kEwUnroll];
+#pragma unroll
+      for (int u = 0; u < kEwUnroll; ++u) {
+        gr[u] = ldraw(da + (pix + u * pstep) * da_pitch + c);
+        yr[u] = ldraw(y + (pix + u * pstep) * y_pitch + c);
+      }
+#pragma unroll
+      for (int u = 0; u < kEwUnroll; ++u) finish(pix + u * pstep, c, gr[u], yr[u], q);
+    }
+    for (; pix < npix; pix += pstep) finish(pix, c, ldraw(da + pix * da_pitch + c), ldraw(y + pix * y_pitch + c), q);
+  } else {
+    const long total = npix * cv;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+      const long pix = i / cv;
+      const unsigned c = (unsigned)(i - pix * cv) << 3;
+      finish(pix, c, ldraw(da + pix * da_pitch + c), ldraw(y + pix * y_pitch + c), load_par(c));
+    }
   }
 }
 
@@ -470,7 +600,7 @@ int yb_bn_finalize(const float* stats, int rows, int C, double count, const floa
                    float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked, float* scale,
                    float* shift, float* mean, float* invstd, int training, void* stream) {
   YB_REQUIRE(training ? (stats != nullptr && rows > 0) : (running_mean && running_var), "bn_finalize: missing inputs");
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(stats, rows, C, count, gamma, beta, eps, momentum,
+  bn_finalize_kernel<<<(C + 31) / 32, 1024, 0, ST(stream)>>>(stats, rows, C, count, gamma, beta, eps, momentum,
                                                                running_mean, running_var,
                                                                reinterpret_cast<long long*>(num_batches_tracked), scale,
                                                                shift, mean, invstd, training);
@@ -484,9 +614,14 @@ int yb_bn_act_fwd(const void* y, int64_t y_pitch, int N, int H, int W, int C, co
   YB_REQUIRE(C % 8 == 0 && y_pitch % 8 == 0 && out_pitch % 8 == 0 && res_pitch % 8 == 0 && up_pitch % 8 == 0,
              "bn_act_fwd: C and pitches must be multiples of 8");
   const long npix = (long)N * H * W;
-  bn_act_fwd_kernel<<<ew_blocks(npix * (C / 8)), 256, 0, ST(stream)>>>(CB16(y), y_pitch, H, W, C, npix, scale, shift,
-                                                                        CB16(res), res_pitch, B16(out), out_pitch,
-                                                                        B16(out_up), up_pitch);
+  static const int occ_grid = ew_wave_grid(bn_act_fwd_kernel<true>, kEwThreads, 1L << 40);
+  const int grid = std::min(occ_grid, ew_blocks(npix * (C / 8), kEwThreads, 64));
+  if (kEwThreads % (C / 8) == 0)
+    bn_act_fwd_kernel<true><<<grid, kEwThreads, 0, ST(stream)>>>(CB16(y), y_pitch, H, W, C, npix, scale, shift, CB16(res),
+                                                                 res_pitch, B16(out), out_pitch, B16(out_up), up_pitch);
+  else
+    bn_act_fwd_kernel<false><<<grid, kEwThreads, 0, ST(stream)>>>(CB16(y), y_pitch, H, W, C, npix, scale, shift, CB16(res),
+                                                                  res_pitch, B16(out), out_pitch, B16(out_up), up_pitch);
   LAUNCH_OK();
   return 0;
 }
@@ -520,6 +655,7 @@ int yb_add_into(const void* src, int64_t src_pitch, void* dst, int64_t dst_pitch
   return 0;
 }
 
+static constexpr int kReduceRows = 444;
 static int reduce_geometry(int C, long npix, int& threads, int& rows_pb, int& grid, size_t& smem) {
   const int cv = C / 8;
   YB_REQUIRE(C % 8 == 0 && cv <= 256, "bwd_reduce: C=%d unsupported", C);
@@ -528,11 +664,11 @@ static int reduce_geometry(int C, long npix, int& threads, int& rows_pb, int& gr
   threads = ((rows_pb * cv + 31) / 32) * 32;
   smem = (size_t)rows_pb * 2 * C * sizeof(float);
   const long want = (npix + (long)rows_pb * 16 - 1) / ((long)rows_pb * 16);  // >= 16 pixels per thread row
-  grid = (int)std::max<long>(1, std::min<long>(want, 592));
+  grid = (int)std::max<long>(1, std::min<long>(want, kReduceRows));  // one resident wave: 148 SMs x 3 CTAs
   return 0;
 }
 
-int yb_bwd_reduce_max_rows(void) { return 592; }
+int yb_bwd_reduce_max_rows(void) { return kReduceRows; }
 
 int yb_bn_act_bwd_reduce(const void* da, int64_t da_pitch, const void* y, int64_t y_pitch, int64_t npix, int C,
                          const float* scale, const float* shift, const float* mean, const float* invstd, float* partial,
@@ -571,7 +707,7 @@ int yb_colsum(const void* x, int64_t x_pitch, int64_t npix, int C, float* partia
 
 int yb_bn_bwd_finalize(const float* partial, int rows, int C, double count, float* dgamma, float* dbeta, float* coef,
                        int accumulate, void* stream) {
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(partial, rows, C, count, dgamma, dbeta, coef,
+  bn_bwd_finalize_kernel<<<(C + 31) / 32, 1024, 0, ST(stream)>>>(partial, rows, C, count, dgamma, dbeta, coef,
                                                                    accumulate);
   LAUNCH_OK();
   return 0;
@@ -581,9 +717,14 @@ int yb_bn_act_bwd_apply(const void* da, int64_t da_pitch, const void* y, int64_t
                         const float* scale, const float* shift, const float* mean, const float* invstd,
                         const float* coef, void* dy, int64_t dy_pitch, void* stream) {
   YB_REQUIRE(C % 8 == 0 && da_pitch % 8 == 0 && y_pitch % 8 == 0 && dy_pitch % 8 == 0, "bn_act_bwd_apply: alignment");
-  bn_act_bwd_apply_kernel<<<ew_blocks(npix * (C / 8)), 256, 0, ST(stream)>>>(CB16(da), da_pitch, CB16(y), y_pitch, npix, C,
-                                                                              scale, shift, mean, invstd, coef, B16(dy),
-                                                                              dy_pitch);
+  static const int occ_grid = ew_wave_grid(bn_act_bwd_apply_kernel<true>, kEwThreads, 1L << 40);
+  const int grid = std::min(occ_grid, ew_blocks(npix * (C / 8), kEwThreads, 64));
+  if (kEwThreads % (C / 8) == 0)
+    bn_act_bwd_apply_kernel<true><<<grid, kEwThreads, 0, ST(stream)>>>(CB16(da), da_pitch, CB16(y), y_pitch, npix, C, scale,
+                                                                       shift, mean, invstd, coef, B16(dy), dy_pitch);
+  else
+    bn_act_bwd_apply_kernel<false><<<grid, kEwThreads, 0, ST(stream)>>>(CB16(da), da_pitch, CB16(y), y_pitch, npix, C, scale,
+                                                                        shift, mean, invstd, coef, B16(dy), dy_pitch);
   LAUNCH_OK();
   return 0;
 }
