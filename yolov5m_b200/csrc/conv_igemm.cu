@@ -3,11 +3,13 @@
 // Replaces, for the reference's hot path, every nn.Conv2d fprop/dgrad that cuDNN would run
 // (reference model.py:16 CBL conv, model.py:162 head conv; autograd dgrad of the same).
 //
-// CTA = 256 threads, one CTA per SM, persistent over output tiles:
+// CTA = 512 threads, one CTA per SM, persistent over output tiles:
 //   warp 0      TMA producer   (one elected lane): A = shifted NHWC patch [128 px x KC ch], B = weights [BLOCK_N x KC]
 //   warp 1      MMA issuer     (one elected lane): tcgen05.mma kind::f16, M=128, N=BLOCK_N, K=16, fp32 accum in TMEM
 //   warp 2      TMEM allocator (512 columns = 2 accumulator buffers of <=256 columns)
-//   warps 4..7  epilogue       TMEM -> registers -> (BN batch-stat partials) -> scale/shift/SiLU/residual -> global
+//   warps 4..15 epilogue       TMEM -> registers -> (BN batch-stat partials) -> scale/shift/SiLU/residual -> global
+//               (three warps per TMEM lane quarter, interleaved over the 16-column chunks: the epilogue is a long
+//               dependent chain -- tcgen05.ld, shuffle butterfly, stores -- and one warp per scheduler cannot hide it)
 // Pipelines: smem ring full/empty mbarriers (TMA <-> MMA), TMEM full/empty mbarriers (MMA <-> epilogue).
 #include "conv_igemm.cuh"
 
@@ -16,7 +18,9 @@
 
 namespace yb {
 
-static constexpr int kThreads = 256;
+static constexpr int kThreads = 512;
+static constexpr int kEpiGroups = 3;                  // epilogue warps per TMEM lane quarter
+static constexpr int kEpiThreads = 4 * kEpiGroups * 32;
 static constexpr int kMaxStages = 12;
 static constexpr int kBarRegion = 1024;
 
@@ -60,7 +64,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], 4 * kEpiGroups);
     }
     fence_mbar_init();
   }
@@ -70,7 +74,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
   if (p.stats != nullptr && warp >= 4) {
-    for (int i = threadIdx.x - 128; i < 4 * 2 * p.Cout; i += 128) s_stats[i] = 0.f;
+    for (int i = threadIdx.x - 128; i < 4 * 2 * p.Cout; i += kEpiThreads) s_stats[i] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -144,6 +148,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int eg = (warp - 4) >> 2;  // which of the kEpiGroups warps of that quarter: takes chunks eg, eg + kEpiGroups, ...
     const int r = q * 32 + lane;
     const int pn = r / (p.PH * p.PW);
     const int phh = (r / p.PW) % p.PH;
@@ -162,7 +167,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 256;
       const int nchunks = p.BLOCK_N / 16;
-      for (int cc = 0; cc < nchunks; ++cc) {
+      for (int cc = eg; cc < nchunks; cc += kEpiGroups) {
         const int col0 = tc.nt * p.BLOCK_N + cc * 16;
         if (col0 >= p.Cout) break;
         uint32_t vr[16];
@@ -280,9 +285,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       if (lane == 0) mbar_arrive(&tempty_bar[ab]);
     }
     if (p.stats != nullptr) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       float* dst = p.stats + (size_t)blockIdx.x * 2 * p.Cout;
-      for (int i = threadIdx.x - 128; i < 2 * p.Cout; i += 128) {
+      for (int i = threadIdx.x - 128; i < 2 * p.Cout; i += kEpiThreads) {
         dst[i] = ((s_stats[i] + s_stats[2 * p.Cout + i]) + s_stats[4 * p.Cout + i]) + s_stats[6 * p.Cout + i];
       }
     }

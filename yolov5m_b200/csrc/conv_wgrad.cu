@@ -19,7 +19,7 @@
 // touch.  Each item writes an fp32 partial tile [Mpad][Npad]; a second kernel reduces the partials in a fixed order
 // (deterministic, no atomics) and transposes them into dW's [co][tap][ci] layout.
 //
-// CTA = 256 threads: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4..7 epilogue.
+// CTA = 512 threads: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4..15 epilogue.
 #include "conv_wgrad.cuh"
 
 #include <algorithm>
@@ -27,7 +27,8 @@
 
 namespace yb {
 
-static constexpr int kThreads = 256;
+static constexpr int kThreads = 512;
+static constexpr int kEpiGroups = 3;  // epilogue warps per TMEM lane quarter (interleaved over 16-column chunks)
 static constexpr int kMaxStages = 6;
 static constexpr int kBarRegion = 1024;
 static constexpr int kBoxC = 64;  // channels per TMA box (128-byte swizzle span)
@@ -65,7 +66,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
       mbar_init(&empty_bar[i], 1);
     }
     mbar_init(tfull_bar, 1);
-    mbar_init(tempty_bar, 4);
+    mbar_init(tempty_bar, 4 * kEpiGroups);
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
@@ -162,6 +163,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue: TMEM -> fp32 partial tile
     const int q = warp & 3;
+    const int eg = (warp - 4) >> 2;
     const int r = q * 32 + lane;
     int iter = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++iter) {
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
         const bool valid = box < p.boxes_total && ci < p.Cin;
         float* dst = p.partial + ((size_t)it.sp * p.Mpad + (size_t)tapi * p.Cin_pad + ci) * p.Npad + it.nt * p.BLOCK_N;
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + mt * p.BLOCK_N;
-        for (int cc = 0; cc * 16 < ncols; ++cc) {
+        for (int cc = eg; cc * 16 < ncols; cc += kEpiGroups) {
           uint32_t vr[16];
           tmem_ld16(t_addr + cc * 16, vr);
           tmem_ld_wait();
@@ -395,6 +397,11 @@ int wgrad_plan(WgradPlan& pl, const TView& x, const TView& dy, int ks, int strid
   if (max_splits > 0) splits = std::min(splits, max_splits);
   const size_t per_split = (size_t)kp.Mpad * kp.Npad;
   splits = (int)std::min<size_t>(splits, partial_floats / per_split);
+  {  // avoid a mostly empty last wave: items = base_items * splits should fill whole multiples of the SM count
+    const int items = base_items * splits;
+    const int waves = (items + sms - 1) / sms;
+    if (waves > 1 && items < waves * sms * 0.85) splits = std::max(1, (waves - 1) * sms / base_items);
+  }
   YB_REQUIRE(splits >= 1, "wgrad: workspace too small (%zu floats, need >= %zu)", partial_floats, per_split);
   kp.splits = splits;
   kp.partial = partial;
