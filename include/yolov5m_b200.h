@@ -62,6 +62,10 @@ void* yb_conv_fwd_plan(const void* x, int N, int H, int W, int Cin, int64_t x_pi
 void* yb_conv_dgrad_plan(const void* dy, int N, int H, int W, int Cout, int64_t dy_pitch, const void* wt_packed, int Cin,
                          int ks, int stride, void* dx, int64_t dx_pitch, const void* addend, int64_t addend_pitch);
 int yb_plan_run(void* plan, void* stream);
+/* Kernel selection for 3x3 convolutions planned AFTER the call (tuning / test knob; default 0, or $YB_CONV_PATCH):
+ * 0 = heuristic, 1 = halo-patch kernel (conv_patch.cu) wherever legal, 2 = same plus multi-tile super-tiles on small
+ * problems, -1 = generic kernel (conv_igemm.cu) only.  Results are identical up to fp32 summation order. */
+void yb_set_conv_patch_mode(int mode);
 void yb_plan_destroy(void* plan);
 
 /* ---- Conv2d weight gradient (autograd of model.py:16 / :162) ---------------------------------------------------

@@ -150,3 +150,49 @@ def test_conv_dgrad(case):
                                  _lib.stream()))
     torch.cuda.synchronize()
     assert rel(dx.float().cpu().permute(0, 3, 1, 2), ref) < TOL
+
+
+# ---- halo-patch kernel (csrc/conv_patch.cu) forced on: same checks, every super-tile shape / stride / epilogue option
+PATCH_FWD = [
+    # N, H, W, Cin, Cout, ks, stride
+    (2, 32, 32, 48, 48, 3, 1),     # BLOCK_N 48: 2x2 super-tile, one padded K chunk
+    (1, 64, 48, 16, 48, 3, 1),     # stem-like: 16 real channels in a 64-wide chunk
+    (2, 32, 40, 96, 96, 3, 1),     # BLOCK_N 96: two tiles per weight stage, 2 K chunks (second half padded)
+    (2, 24, 40, 192, 192, 3, 1),   # single tile, H not a multiple of 16
+    (1, 20, 20, 384, 384, 3, 1),   # partial tiles in both directions, 2 N tiles
+    (2, 64, 64, 48, 96, 3, 2),     # stride 2: four parity patches
+    (3, 22, 22, 192, 384, 3, 2),   # odd 11x11 output grid
+]
+
+
+@pytest.fixture
+def patch_mode():
+    L = _lib.lib()
+    L.yb_set_conv_patch_mode(2)
+    yield
+    L.yb_set_conv_patch_mode(0)
+
+
+@pytest.mark.parametrize("case", PATCH_FWD)
+def test_conv_patch_fwd(case, patch_mode):
+    test_conv_fwd_raw(case)
+
+
+def test_conv_patch_fused_epilogue(patch_mode):
+    test_conv_fwd_fused_epilogue()
+
+
+PATCH_DG = [
+    (2, 32, 32, 48, 48, 3, 1),
+    (2, 32, 40, 96, 48, 3, 1),
+    (2, 24, 40, 192, 192, 3, 1),
+    (1, 20, 20, 384, 384, 3, 1),
+    (2, 64, 64, 48, 96, 3, 2),
+    (2, 32, 32, 96, 192, 3, 2),
+    (3, 22, 22, 192, 384, 3, 2),
+]
+
+
+@pytest.mark.parametrize("case", PATCH_DG)
+def test_conv_patch_dgrad(case, patch_mode):
+    test_conv_dgrad(case)

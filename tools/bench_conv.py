@@ -46,8 +46,11 @@ def main():
     ap.add_argument("--only", default="fwd,dgrad,wgrad")
     ap.add_argument("--out", default=None)
     ap.add_argument("--shapes", default=None, help="comma-separated indices into SHAPES (default: all)")
+    ap.add_argument("--patch", type=int, default=None, help="yb_set_conv_patch_mode (-1 generic only, 0 auto, 1 force)")
     a = ap.parse_args()
     L = _lib.lib()
+    if a.patch is not None:
+        L.yb_set_conv_patch_mode(a.patch)
     st = _lib.stream()
     ws = torch.empty(64 << 20, device="cuda", dtype=torch.float32)
     rows = []

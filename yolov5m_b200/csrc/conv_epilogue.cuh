@@ -1,0 +1,125 @@
+// Shared epilogue of the tcgen05 convolution kernels (conv_igemm.cu, conv_patch.cu): one 16-column chunk of one
+// accumulator row per thread.  TMEM -> registers -> (BN batch-stat partials) -> scale/shift/SiLU/residual -> global.
+#pragma once
+#include "conv_igemm.cuh"
+
+namespace yb {
+
+// P: kernel parameter struct with the epilogue fields of ConvKParams (stats, scale, shift, act, addend, out_kind, out,
+// Cout, H, W, head_na, head_no).  t_addr: TMEM address of column 0 of this chunk for this warp's lane quarter.
+// (n, h, w): output pixel of this thread's row; opix / apix: element offsets of that pixel in out / addend.
+template <class P>
+__device__ __forceinline__ void conv_epilogue_chunk(const P& p, uint32_t t_addr, int col0, bool valid, int n, int h, int w,
+                                                    int64_t opix, int64_t apix, float* my_stats, int lane) {
+    uint32_t vr[16];
+    tmem_ld16(t_addr, vr);
+    tmem_ld_wait();
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(vr[j]);
+
+    if (p.stats != nullptr) {
+      // per-column sum / sum-of-squares over the 32 rows of this warp: butterfly transpose-reduce
+      float a8[8], b8[8];
+      const bool u16 = lane & 16;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float lo = valid ? v[j] : 0.f, hi = valid ? v[j + 8] : 0.f;
+        const float keep = u16 ? hi : lo, send = u16 ? lo : hi;
+        const float rs = __shfl_xor_sync(0xffffffffu, send, 16);
+        const float rq = __shfl_xor_sync(0xffffffffu, send * send, 16);
+        a8[j] = keep + rs;
+        b8[j] = keep * keep + rq;
+      }
+      float a4[4], b4[4];
+      const bool u8 = lane & 8;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float ka = u8 ? a8[j + 4] : a8[j], sa = u8 ? a8[j] : a8[j + 4];
+        const float kb = u8 ? b8[j + 4] : b8[j], sb = u8 ? b8[j] : b8[j + 4];
+        a4[j] = ka + __shfl_xor_sync(0xffffffffu, sa, 8);
+        b4[j] = kb + __shfl_xor_sync(0xffffffffu, sb, 8);
+      }
+      float a2[2], b2[2];
+      const bool u4 = lane & 4;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const float ka = u4 ? a4[j + 2] : a4[j], sa = u4 ? a4[j] : a4[j + 2];
+        const float kb = u4 ? b4[j + 2] : b4[j], sb = u4 ? b4[j] : b4[j + 2];
+        a2[j] = ka + __shfl_xor_sync(0xffffffffu, sa, 4);
+        b2[j] = kb + __shfl_xor_sync(0xffffffffu, sb, 4);
+      }
+      const bool u2 = lane & 2;
+      float a1 = (u2 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, u2 ? a2[0] : a2[1], 2);
+      float b1 = (u2 ? b2[1] : b2[0]) + __shfl_xor_sync(0xffffffffu, u2 ? b2[0] : b2[1], 2);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+      b1 += __shfl_xor_sync(0xffffffffu, b1, 1);
+      // lane l now holds column ((l>>4)&1)*8 + ((l>>3)&1)*4 + ((l>>2)&1)*2 + ((l>>1)&1)
+      if ((lane & 1) == 0) {
+        const int cj = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+        const int col = col0 + cj;
+        if (col < p.Cout) {
+          my_stats[col] += a1;
+          my_stats[p.Cout + col] += b1;
+        }
+      }
+    }
+
+    if (valid) {
+      if (p.scale != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (col0 + j < p.Cout) v[j] = fmaf(v[j], __ldg(p.scale + col0 + j), __ldg(p.shift + col0 + j));
+      } else if (p.shift != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (col0 + j < p.Cout) v[j] += __ldg(p.shift + col0 + j);
+      }
+      if (p.act) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = silu_f(v[j]);
+      }
+      if (p.addend != nullptr) {
+        const uint4* ap = reinterpret_cast<const uint4*>(p.addend + apix + col0);
+        uint4 r0 = __ldg(ap), r1 = __ldg(ap + 1);
+        const bf16* e0 = reinterpret_cast<const bf16*>(&r0);
+        const bf16* e1 = reinterpret_cast<const bf16*>(&r1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[j] += __bfloat162float(e0[j]);
+          v[8 + j] += __bfloat162float(e1[j]);
+        }
+      }
+      if (p.out_kind == OUT_BF16) {
+        uint4 o0, o1;
+        __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+        __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          h0[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+          h1[j] = __floats2bfloat162_rn(v[8 + 2 * j], v[8 + 2 * j + 1]);
+        }
+        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + opix + col0);
+        op[0] = o0;
+        op[1] = o1;
+      } else if (p.out_kind == OUT_F32) {
+        float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + opix + col0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      } else {  // OUT_HEAD_F32
+        float* ob = reinterpret_cast<float*>(p.out);
+        const int64_t hw = (int64_t)p.H * p.W;
+        const int64_t pix = (int64_t)h * p.W + w;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int col = col0 + j;
+          if (col < p.Cout) {
+            const int a = col / p.head_no, o = col - a * p.head_no;
+            ob[(((int64_t)n * p.head_na + a) * hw + pix) * p.head_no + o] = v[j];
+          }
+        }
+      }
+    }
+}
+
+}  // namespace yb

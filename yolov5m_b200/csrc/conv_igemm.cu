@@ -12,6 +12,7 @@
 //               dependent chain -- tcgen05.ld, shuffle butterfly, stores -- and one warp per scheduler cannot hide it)
 // Pipelines: smem ring full/empty mbarriers (TMA <-> MMA), TMEM full/empty mbarriers (MMA <-> epilogue).
 #include "conv_igemm.cuh"
+#include "conv_epilogue.cuh"
 
 #include <algorithm>
 #include <cstring>
@@ -109,11 +110,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
+      // The issue loop is ONE thread: keep it to a few instructions per MMA (descriptor = constant high part + 14-bit
+      // start-address field in 16-byte units, advanced by integer adds) or small-N tiles become issue-bound.
       const uint32_t idesc = make_idesc_bf16(128, p.BLOCK_N, 0, 0);
       const uint32_t row_bytes = 2u * p.KC;
       const uint32_t lt = swizzle_layout_type(row_bytes);
       const uint32_t sbo = 8u * row_bytes;
       const int kinner = p.KC / 16;
+      const uint64_t desc_hi = make_smem_desc(0, 16, sbo, lt);
+      const uint64_t a_desc0 = desc_hi | (uint64_t)(smem_u32(a_smem) >> 4);
+      const uint64_t b_desc0 = desc_hi | (uint64_t)(smem_u32(b_smem) >> 4);
+      const uint32_t a_step = p.a_stage_bytes >> 4, b_step = p.b_stage_bytes >> 4;
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
@@ -126,16 +133,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         mbar_wait(&tempty_bar[ab], aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + ab * 256;
+        uint32_t acc = 0;
         for (int ks = 0; ks < nk; ++ks) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(a_smem + (size_t)s * p.a_stage_bytes);
-          const uint32_t b_addr = smem_u32(b_smem + (size_t)s * p.b_stage_bytes);
-          for (int k = 0; k < kinner; ++k) {
-            const uint64_t da = make_smem_desc(a_addr + k * 32, 16, sbo, lt);
-            const uint64_t db = make_smem_desc(b_addr + k * 32, 16, sbo, lt);
-            umma_bf16(d_tmem, da, db, idesc, (ks | k) != 0 ? 1u : 0u);
+          const uint64_t da = a_desc0 + (uint64_t)(s * a_step), db = b_desc0 + (uint64_t)(s * b_step);
+          if (kinner == 4) {
+            umma_bf16(d_tmem, da, db, idesc, acc);
+            umma_bf16(d_tmem, da + 2, db + 2, idesc, 1u);
+            umma_bf16(d_tmem, da + 4, db + 4, idesc, 1u);
+            umma_bf16(d_tmem, da + 6, db + 6, idesc, 1u);
+          } else {
+            for (int k = 0; k < kinner; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, k ? 1u : acc);
           }
+          acc = 1u;
           umma_commit(&empty_bar[s]);
           if (++s == p.stages) {
             s = 0;
@@ -170,115 +181,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       for (int cc = eg; cc < nchunks; cc += kEpiGroups) {
         const int col0 = tc.nt * p.BLOCK_N + cc * 16;
         if (col0 >= p.Cout) break;
-        uint32_t vr[16];
-        tmem_ld16(t_addr + cc * 16, vr);
-        tmem_ld_wait();
-        float v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(vr[j]);
-
-        if (p.stats != nullptr) {
-          // per-column sum / sum-of-squares over the 32 rows of this warp: butterfly transpose-reduce
-          float a8[8], b8[8];
-          const bool u16 = lane & 16;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float lo = valid ? v[j] : 0.f, hi = valid ? v[j + 8] : 0.f;
-            const float keep = u16 ? hi : lo, send = u16 ? lo : hi;
-            const float rs = __shfl_xor_sync(0xffffffffu, send, 16);
-            const float rq = __shfl_xor_sync(0xffffffffu, send * send, 16);
-            a8[j] = keep + rs;
-            b8[j] = keep * keep + rq;
-          }
-          float a4[4], b4[4];
-          const bool u8 = lane & 8;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float ka = u8 ? a8[j + 4] : a8[j], sa = u8 ? a8[j] : a8[j + 4];
-            const float kb = u8 ? b8[j + 4] : b8[j], sb = u8 ? b8[j] : b8[j + 4];
-            a4[j] = ka + __shfl_xor_sync(0xffffffffu, sa, 8);
-            b4[j] = kb + __shfl_xor_sync(0xffffffffu, sb, 8);
-          }
-          float a2[2], b2[2];
-          const bool u4 = lane & 4;
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const float ka = u4 ? a4[j + 2] : a4[j], sa = u4 ? a4[j] : a4[j + 2];
-            const float kb = u4 ? b4[j + 2] : b4[j], sb = u4 ? b4[j] : b4[j + 2];
-            a2[j] = ka + __shfl_xor_sync(0xffffffffu, sa, 4);
-            b2[j] = kb + __shfl_xor_sync(0xffffffffu, sb, 4);
-          }
-          const bool u2 = lane & 2;
-          float a1 = (u2 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, u2 ? a2[0] : a2[1], 2);
-          float b1 = (u2 ? b2[1] : b2[0]) + __shfl_xor_sync(0xffffffffu, u2 ? b2[0] : b2[1], 2);
-          a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
-          b1 += __shfl_xor_sync(0xffffffffu, b1, 1);
-          // lane l now holds column ((l>>4)&1)*8 + ((l>>3)&1)*4 + ((l>>2)&1)*2 + ((l>>1)&1)
-          if ((lane & 1) == 0) {
-            const int cj = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-            const int col = col0 + cj;
-            if (col < p.Cout) {
-              my_stats[col] += a1;
-              my_stats[p.Cout + col] += b1;
-            }
-          }
-        }
-
-        if (valid) {
-          if (p.scale != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (col0 + j < p.Cout) v[j] = fmaf(v[j], __ldg(p.scale + col0 + j), __ldg(p.shift + col0 + j));
-          } else if (p.shift != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (col0 + j < p.Cout) v[j] += __ldg(p.shift + col0 + j);
-          }
-          if (p.act) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = silu_f(v[j]);
-          }
-          if (p.addend != nullptr) {
-            const uint4* ap = reinterpret_cast<const uint4*>(p.addend + apix + col0);
-            uint4 r0 = __ldg(ap), r1 = __ldg(ap + 1);
-            const bf16* e0 = reinterpret_cast<const bf16*>(&r0);
-            const bf16* e1 = reinterpret_cast<const bf16*>(&r1);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              v[j] += __bfloat162float(e0[j]);
-              v[8 + j] += __bfloat162float(e1[j]);
-            }
-          }
-          if (p.out_kind == OUT_BF16) {
-            uint4 o0, o1;
-            __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&o0);
-            __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&o1);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              h0[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-              h1[j] = __floats2bfloat162_rn(v[8 + 2 * j], v[8 + 2 * j + 1]);
-            }
-            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + opix + col0);
-            op[0] = o0;
-            op[1] = o1;
-          } else if (p.out_kind == OUT_F32) {
-            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + opix + col0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {  // OUT_HEAD_F32
-            float* ob = reinterpret_cast<float*>(p.out);
-            const int64_t hw = (int64_t)p.H * p.W;
-            const int64_t pix = (int64_t)h * p.W + w;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int col = col0 + j;
-              if (col < p.Cout) {
-                const int a = col / p.head_no, o = col - a * p.head_no;
-                ob[(((int64_t)n * p.head_na + a) * hw + pix) * p.head_no + o] = v[j];
-              }
-            }
-          }
-        }
+        conv_epilogue_chunk(p, t_addr + cc * 16, col0, valid, n, h, w, opix, apix, my_stats, lane);
       }
       tc_fence_before();
       __syncwarp();
@@ -402,6 +305,11 @@ static int finish_plan(ConvPlan& pl, const bf16* wmat, int wrows, long wcols, co
 int conv_plan_fwd(ConvPlan& pl, const TView& in, const bf16* wp, int ks, int stride, const TView& out,
                   const ConvEpilogue& ep) {
   memset(&pl, 0, sizeof(pl));
+  {  // 3x3 on maps that tile well into 16x8-pixel tiles: halo-patch kernel (conv_patch.cu)
+    const int rc = conv_patch_plan_fwd(pl, in, wp, ks, stride, out, ep);
+    if (rc <= 0) return rc;
+    pl.kind = 0;
+  }
   ConvKParams& kp = pl.kp;
   YB_REQUIRE((ks == 1 || ks == 3) && (stride == 1 || stride == 2), "conv fwd: ks=%d stride=%d unsupported", ks, stride);
   YB_REQUIRE(in.C % 16 == 0 && in.pitch % 8 == 0 && (ep.out_kind != OUT_BF16 || out.pitch % 8 == 0),
@@ -454,6 +362,11 @@ int conv_plan_fwd(ConvPlan& pl, const TView& in, const bf16* wp, int ks, int str
 int conv_plan_dgrad(ConvPlan& pl, const TView& dy, const bf16* wt, int ks, int stride, const TView& dx,
                     const ConvEpilogue& ep) {
   memset(&pl, 0, sizeof(pl));
+  {
+    const int rc = conv_patch_plan_dgrad(pl, dy, wt, ks, stride, dx, ep);
+    if (rc <= 0) return rc;
+    pl.kind = 0;
+  }
   ConvKParams& kp = pl.kp;
   YB_REQUIRE((ks == 1 || ks == 3) && (stride == 1 || stride == 2), "conv dgrad: ks=%d stride=%d unsupported", ks,
              stride);
@@ -521,6 +434,7 @@ int conv_plan_dgrad(ConvPlan& pl, const TView& dy, const bf16* wt, int ks, int s
 int conv_stats_rows(const ConvPlan& pl) { return pl.grid; }
 
 int conv_run(const ConvPlan& pl, cudaStream_t st) {
+  if (pl.kind == 1) return conv_patch_run(pl, st);
   static bool attr_set = false;
   if (!attr_set) {
     YB_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

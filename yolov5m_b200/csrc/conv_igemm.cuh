@@ -58,8 +58,49 @@ struct ConvKParams {
   int32_t head_na, head_no;  // OUT_HEAD_F32: out[((n*na+a)*H*W + h*W + w)*no + o], column = a*no+o
 };
 
+// ---- "patch" variant (conv_patch.cu): 3x3 convolutions with tap reuse from one halo patch in shared memory ----------
+struct PTap {
+  int32_t row_off;  // (oh * pitch + ow): first patch row of this tap for tile (0,0)
+  int32_t kbase;    // first column of this tap inside the B (weight) matrix
+};
+struct PPatch {
+  int32_t map;                 // A tensor map (input parity for stride 2)
+  int32_t ox, oy;              // patch origin relative to the super-tile origin (w0, h0) in that map's pixel grid
+  int32_t pitch;               // patch width in pixels (= TMA box width; rows of the patch are `pitch` pixels apart)
+  int32_t tap_begin, tap_end;  // taps served by this patch
+  uint32_t bytes;              // TMA box bytes (pitch * height * 128)
+};
+struct PatchKParams {
+  CUtensorMap tmA[4];
+  CUtensorMap tmB;
+  PTap taps[16];
+  PPatch patches[4];
+  ConvGroup groups[4];  // tap_begin/tap_end index PATCHES here
+  int32_t ngroups;
+  int32_t chunks;            // 64-channel K chunks (the last one zero-padded by TMA OOB fill)
+  int32_t TH, TW;            // 128-pixel tiles (16 rows x 8 cols) per super-tile, vertically / horizontally
+  int32_t tiles_w, tiles_h, tiles_c;  // super-tiles per image row / column, N tiles
+  int32_t W, H, NB;          // output pixel grid (per group)
+  int32_t Cout, BLOCK_N;
+  int32_t sa, sb;            // pipeline depth of the patch ring / weight ring
+  uint32_t a_stage_bytes, b_stage_bytes, b_tx_bytes;
+  // epilogue (same meaning as ConvKParams)
+  int32_t out_kind;
+  void* out;
+  int64_t os_n, os_h, os_w;
+  const float* scale;
+  const float* shift;
+  int32_t act;
+  const bf16* addend;
+  int64_t as_n, as_h, as_w;
+  float* stats;
+  int32_t head_na, head_no;
+};
+
 struct ConvPlan {
   ConvKParams kp;
+  PatchKParams pp;
+  int kind;  // 0 = conv_igemm_kernel (kp), 1 = conv_patch_kernel (pp)
   int grid;
   int smem;
 };
@@ -82,6 +123,13 @@ int conv_plan_fwd(ConvPlan& pl, const TView& in, const bf16* wp, int ks, int str
 int conv_plan_dgrad(ConvPlan& pl, const TView& dy, const bf16* wt, int ks, int stride, const TView& dx,
                     const ConvEpilogue& ep);
 int conv_run(const ConvPlan& pl, cudaStream_t st);
+// patch variant: returns 1 when the shape is not eligible (caller falls back to the generic kernel), 0 ok, <0 error
+int conv_patch_plan_fwd(ConvPlan& pl, const TView& in, const bf16* wp, int ks, int stride, const TView& out,
+                        const ConvEpilogue& ep);
+int conv_patch_plan_dgrad(ConvPlan& pl, const TView& dy, const bf16* wt, int ks, int stride, const TView& dx,
+                          const ConvEpilogue& ep);
+int conv_patch_run(const ConvPlan& pl, cudaStream_t st);
+void set_patch_mode(int m);
 int conv_stats_rows(const ConvPlan& pl);  // number of per-CTA partial rows written to ep.stats (= grid)
 int conv_max_grid();
 

@@ -1,0 +1,525 @@
+// 3x3 implicit-GEMM convolution with tap reuse from ONE halo patch in shared memory (tcgen05 + TMA, sm_100a).
+//
+// Same math and epilogue as conv_igemm.cu (reference model.py:16 CBL conv fprop and its autograd dgrad), different
+// operand traffic.  conv_igemm.cu fetches a shifted [128 px x 64 ch] A tile per tap: nine trips through L2 for the same
+// activations, and on B200 the L2 -> SM path (not the tensor pipe) bounds that kernel (profiles/).  Here a
+// work item is a super-tile of TH x TW tiles of 16 rows x 8 columns of output pixels.  Per 64-channel chunk ONE TMA box
+// brings the halo patch [(16*TH + halo) x (8*TW + halo) px x 64 ch] into shared memory (SWIZZLE_128B, 128 bytes per
+// pixel row), and every tap of every tile is an MMA whose A descriptor simply STARTS at a different 128-byte row of that
+// patch:   start = patch + ((16*ty + oh) * pitch + 8*tx + ow) * 128,   SBO = pitch * 128   (8-row groups = image rows).
+// tcgen05 applies the 128-byte swizzle on absolute shared-memory address bits, so a descriptor may start at any row of a
+// TMA-written tile (verified on hardware: tools/umma_shift_probe.cu).  The weight slice of a (tap, chunk) is fetched once
+// per super-tile and shared by its TH*TW accumulators (TH*TW*BLOCK_N <= 256 TMEM columns, double buffered).
+// Stride 2: fprop = four input-parity patches (1/2/2/4 taps); dgrad = four output-parity groups with one patch each.
+//
+// CTA = 512 threads, one CTA per SM, persistent:
+//   warp 0 patch producer (TMA), warp 3 weight producer (TMA), warp 1 MMA issuer, warp 2 TMEM allocator,
+//   warps 4..15 epilogue (conv_epilogue.cuh).
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "conv_epilogue.cuh"
+#include "conv_igemm.cuh"
+
+namespace yb {
+
+static constexpr int kThreads = 512;
+static constexpr int kEpiGroups = 3;
+static constexpr int kEpiThreads = 4 * kEpiGroups * 32;
+static constexpr int kMaxSA = 4, kMaxSB = 12;
+static constexpr int kBarRegion = 1024;
+
+struct STile {
+  int g, n, hb, wb, nt;
+};
+
+__device__ __forceinline__ STile decode_stile(const PatchKParams& p, int t) {
+  STile c;
+  c.nt = t % p.tiles_c;
+  int m = t / p.tiles_c;
+  c.wb = m % p.tiles_w;
+  m /= p.tiles_w;
+  c.hb = m % p.tiles_h;
+  m /= p.tiles_h;
+  c.n = m % p.NB;
+  c.g = m / p.NB;
+  return c;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_constant__ PatchKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* afull = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* aempty = afull + kMaxSA;
+  uint64_t* bfull = aempty + kMaxSA;
+  uint64_t* bempty = bfull + kMaxSB;
+  uint64_t* tfull_bar = bempty + kMaxSB;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint8_t* a_smem = smem + kBarRegion;
+  uint8_t* b_smem = a_smem + (size_t)p.sa * p.a_stage_bytes;
+  float* s_stats = reinterpret_cast<float*>(b_smem + (size_t)p.sb * p.b_stage_bytes);  // [4][2][Cout]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total = p.ngroups * p.NB * p.tiles_h * p.tiles_w * p.tiles_c;
+  const int T = p.TH * p.TW;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.sa; ++i) {
+      mbar_init(&afull[i], 1);
+      mbar_init(&aempty[i], 1);
+    }
+    for (int i = 0; i < p.sb; ++i) {
+      mbar_init(&bfull[i], 1);
+      mbar_init(&bempty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4 * kEpiGroups);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmB);
+    for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.tmA[i]);
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  if (p.stats != nullptr && warp >= 4) {
+    for (int i = threadIdx.x - 128; i < 4 * 2 * p.Cout; i += kEpiThreads) s_stats[i] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ patch producer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const STile tc = decode_stile(p, t);
+        const ConvGroup& grp = p.groups[tc.g];
+        const int w0 = tc.wb * p.TW * 8, h0 = tc.hb * p.TH * 16;
+        for (int pi = grp.tap_begin; pi < grp.tap_end; ++pi) {
+          const PPatch& pa = p.patches[pi];
+          for (int ch = 0; ch < p.chunks; ++ch) {
+            mbar_wait(&aempty[s], ph ^ 1);
+            mbar_expect_tx(&afull[s], pa.bytes);
+            tma_load_4d(&p.tmA[pa.map], &afull[s], a_smem + (size_t)s * p.a_stage_bytes, ch * 64, w0 + pa.ox, h0 + pa.oy,
+                        tc.n);
+            if (++s == p.sa) {
+              s = 0;
+              ph ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ weight producer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const STile tc = decode_stile(p, t);
+        const ConvGroup& grp = p.groups[tc.g];
+        const int c0 = tc.nt * p.BLOCK_N;
+        for (int pi = grp.tap_begin; pi < grp.tap_end; ++pi) {
+          const PPatch& pa = p.patches[pi];
+          for (int ch = 0; ch < p.chunks; ++ch) {
+            for (int tp = pa.tap_begin; tp < pa.tap_end; ++tp) {
+              mbar_wait(&bempty[s], ph ^ 1);
+              mbar_expect_tx(&bfull[s], p.b_tx_bytes);
+              tma_load_2d(&p.tmB, &bfull[s], b_smem + (size_t)s * p.b_stage_bytes, p.taps[tp].kbase + ch * 64, c0);
+              if (++s == p.sb) {
+                s = 0;
+                ph ^= 1;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      // The issue loop is ONE thread: a handful of instructions per MMA (descriptor = constant high part + 14-bit
+      // start-address field in 16-byte units, advanced by integer adds), or small-N tiles become issue-bound.
+      const uint32_t idesc = make_idesc_bf16(128, p.BLOCK_N, 0, 0);
+      const uint64_t b_desc0 = make_smem_desc(smem_u32(b_smem), 16, 1024, 2);
+      const uint32_t a_step = p.a_stage_bytes >> 4, b_step = p.b_stage_bytes >> 4;
+      const uint32_t a_base16 = smem_u32(a_smem) >> 4;
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+        const STile tc = decode_stile(p, t);
+        const ConvGroup& grp = p.groups[tc.g];
+        const int ab = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[ab], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + ab * 256;
+        uint32_t acc = 0;
+        for (int pi = grp.tap_begin; pi < grp.tap_end; ++pi) {
+          const PPatch& pa = p.patches[pi];
+          const uint64_t a_hi = make_smem_desc(0, 16, (uint32_t)pa.pitch * 128u, 2);
+          // tile (ty, tx) starts (16*ty*pitch + 8*tx) pixel rows (x 128 B = x 8 descriptor units) into the patch
+          uint32_t tile_off[4];
+#pragma unroll
+          for (int tt = 0; tt < 4; ++tt) {
+            const int ty = tt / p.TW, tx = tt - ty * p.TW;
+            tile_off[tt] = (uint32_t)(ty * 16 * pa.pitch + tx * 8) * 8u;
+          }
+          for (int ch = 0; ch < p.chunks; ++ch) {
+            mbar_wait(&afull[sa], pha);
+            tc_fence_after();
+            const uint64_t a_desc = a_hi | (uint64_t)(a_base16 + sa * a_step);
+            for (int tp = pa.tap_begin; tp < pa.tap_end; ++tp) {
+              const uint64_t a_tap = a_desc + (uint64_t)((uint32_t)p.taps[tp].row_off * 8u);
+              mbar_wait(&bfull[sb], phb);
+              tc_fence_after();
+              const uint64_t db = b_desc0 + (uint64_t)(sb * b_step);
+#pragma unroll
+              for (int tt = 0; tt < 4; ++tt) {
+                if (tt >= T) break;
+                const uint64_t da = a_tap + tile_off[tt];
+                const uint32_t d_tmem = d_base + (uint32_t)tt * p.BLOCK_N;
+                umma_bf16(d_tmem, da, db, idesc, acc);
+                umma_bf16(d_tmem, da + 2, db + 2, idesc, 1u);
+                umma_bf16(d_tmem, da + 4, db + 4, idesc, 1u);
+                umma_bf16(d_tmem, da + 6, db + 6, idesc, 1u);
+              }
+              acc = 1u;
+              umma_commit(&bempty[sb]);
+              if (++sb == p.sb) {
+                sb = 0;
+                phb ^= 1;
+              }
+            }
+            umma_commit(&aempty[sa]);
+            if (++sa == p.sa) {
+              sa = 0;
+              pha ^= 1;
+            }
+          }
+        }
+        umma_commit(&tfull_bar[ab]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp & 3;
+    const int eg = (warp - 4) >> 2;
+    const int r = q * 32 + lane;
+    const int phh = r >> 3, pw = r & 7;
+    float* my_stats = s_stats + (size_t)q * 2 * p.Cout;
+    const int nchunks = p.BLOCK_N / 16;
+    int it = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      const STile tc = decode_stile(p, t);
+      const int ab = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      mbar_wait(&tfull_bar[ab], aph);
+      tc_fence_after();
+      for (int idx = eg; idx < T * nchunks; idx += kEpiGroups) {
+        const int tt = idx / nchunks, cc = idx - tt * nchunks;
+        const int col0 = tc.nt * p.BLOCK_N + cc * 16;
+        if (col0 >= p.Cout) continue;
+        const int ty = tt / p.TW, tx = tt - ty * p.TW;
+        const int h = (tc.hb * p.TH + ty) * 16 + phh, w = (tc.wb * p.TW + tx) * 8 + pw;
+        const bool valid = h < p.H && w < p.W;
+        const int64_t opix = p.groups[tc.g].out_off + tc.n * p.os_n + h * p.os_h + w * p.os_w;
+        const int64_t apix = p.groups[tc.g].add_off + tc.n * p.as_n + h * p.as_h + w * p.as_w;
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 256 + tt * p.BLOCK_N + cc * 16;
+        conv_epilogue_chunk(p, t_addr, col0, valid, tc.n, h, w, opix, apix, my_stats, lane);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[ab]);
+    }
+    if (p.stats != nullptr) {
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      float* dst = p.stats + (size_t)blockIdx.x * 2 * p.Cout;
+      for (int i = threadIdx.x - 128; i < 2 * p.Cout; i += kEpiThreads) {
+        dst[i] = ((s_stats[i] + s_stats[2 * p.Cout + i]) + s_stats[4 * p.Cout + i]) + s_stats[6 * p.Cout + i];
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+static int pick_block_n(int Cout) {
+  const int c16 = (Cout + 15) / 16 * 16;
+  if (c16 <= 256) return c16;
+  const int parts = (c16 + 255) / 256;
+  return ((c16 + parts - 1) / parts + 15) / 16 * 16;
+}
+
+// tensor map over (a parity sub-grid of) an NHWC view with a [64 ch x bw x bh x 1] box
+static int make_patch_map(CUtensorMap* m, const TView& v, int bw, int bh, int py, int px, int sy, int sx) {
+  const bf16* base = reinterpret_cast<const bf16*>(v.ptr) + ((long)py * v.W + px) * v.pitch;
+  uint64_t dims[4] = {(uint64_t)v.C, (uint64_t)(v.W / sx), (uint64_t)(v.H / sy), (uint64_t)v.N};
+  uint64_t strides[3] = {(uint64_t)v.pitch * sx * 2, (uint64_t)v.pitch * v.W * sy * 2,
+                         (uint64_t)v.pitch * v.W * v.H * 2};
+  uint32_t box[4] = {64u, (uint32_t)bw, (uint32_t)bh, 1u};
+  return encode_tmap(m, base, 4, dims, strides, box, 128, 2);
+}
+
+// 0 = auto (heuristic), 1 = use the patch kernel wherever it is legal, 2 = additionally allow multi-tile super-tiles on
+// small problems (tests), -1 = never.  Initialised from $YB_CONV_PATCH, changed with yb_set_conv_patch_mode().
+static int g_patch_mode = -2;
+static int patch_mode() {
+  if (g_patch_mode == -2) {
+    const char* e = getenv("YB_CONV_PATCH");
+    g_patch_mode = e ? atoi(e) : 0;
+  }
+  return g_patch_mode;
+}
+void set_patch_mode(int m) { g_patch_mode = m; }
+
+// common tail: super-tile shape, pipeline depths, epilogue fields.  Wg/Hg: output grid of one group.
+static int finish_patch_plan(ConvPlan& pl, const bf16* wmat, int wrows, long wcols, int Kc, const TView& out,
+                             const ConvEpilogue& ep, int max_patch_w_halo, int max_patch_h_halo) {
+  PatchKParams& kp = pl.pp;
+  pl.kind = 1;
+  kp.Cout = wrows;
+  kp.BLOCK_N = pick_block_n(wrows);
+  kp.tiles_c = (wrows + kp.BLOCK_N - 1) / kp.BLOCK_N;
+  kp.chunks = (Kc + 63) / 64;
+  {
+    uint64_t dims[2] = {(uint64_t)wcols, (uint64_t)wrows};
+    uint64_t strides[1] = {(uint64_t)wcols * 2};
+    uint32_t box[2] = {64u, (uint32_t)kp.BLOCK_N};
+    if (encode_tmap(&kp.tmB, wmat, 2, dims, strides, box, 128, 2)) return -1;
+  }
+  kp.b_stage_bytes = ((uint32_t)kp.BLOCK_N * 128u + 1023u) & ~1023u;
+  kp.b_tx_bytes = (uint32_t)kp.BLOCK_N * 128u;
+  kp.out_kind = ep.out_kind;
+  kp.out = out.ptr;
+  kp.scale = ep.scale;
+  kp.shift = ep.shift;
+  kp.act = ep.act;
+  kp.addend = ep.addend;
+  kp.stats = ep.stats;
+  kp.head_na = ep.head_na;
+  kp.head_no = ep.head_no;
+  (void)max_patch_w_halo;
+  (void)max_patch_h_halo;
+  return 0;
+}
+
+// choose TH x TW: minimise the TMA bytes per useful output tile (patch bytes + nine weight slices, shared by the
+// TH*TW accumulators of a super-tile; padding to whole super-tiles counts as waste) under the TMEM (256 columns per
+// buffer) and shared-memory budgets, keeping >= ~4 super-tiles per SM so the persistent loop stays balanced
+static bool choose_supertile(PatchKParams& kp, int Wg, int Hg, int NB, int ngroups, int halo_w, int halo_h, size_t stats_bytes) {
+  const size_t budget = 227 * 1024 - 1024 - kBarRegion - stats_bytes;
+  const int cands[4][2] = {{2, 2}, {1, 2}, {2, 1}, {1, 1}};
+  double best = -1;
+  for (int i = 0; i < 4; ++i) {
+    const int TH = cands[i][0], TW = cands[i][1], T = TH * TW;
+    if (T * kp.BLOCK_N > 256) continue;
+    const size_t a_bytes = (((size_t)(16 * TH + halo_h) * (8 * TW + halo_w) * 128) + 1023) & ~(size_t)1023;
+    if (2 * a_bytes + 3 * (size_t)kp.b_stage_bytes > budget) continue;
+    const int tw = (Wg + 8 * TW - 1) / (8 * TW), th = (Hg + 16 * TH - 1) / (16 * TH);
+    const long stiles = (long)tw * th * NB * ngroups * kp.tiles_c;
+    if (T > 1 && stiles < 4L * conv_max_grid() && patch_mode() < 2) continue;
+    const double eff = (double)Wg * Hg / ((double)tw * 8 * TW * th * 16 * TH);
+    const double cost = ((double)a_bytes + 9.0 * kp.b_stage_bytes) / T / eff;
+    if (best < 0 || cost < best) {
+      best = cost;
+      kp.TH = TH;
+      kp.TW = TW;
+      kp.a_stage_bytes = (uint32_t)a_bytes;
+      kp.tiles_w = tw;
+      kp.tiles_h = th;
+    }
+  }
+  if (best < 0) return false;
+  // measured (profiles/conv_layers_r1f_*.json): with a single tile per weight stage the generic kernel (fuller 128-pixel
+  // tiles, no 16x8 padding) is as fast or faster -- the patch kernel pays off where several accumulators share the weights
+  if (kp.TH * kp.TW == 1 && patch_mode() == 0) return false;
+  const size_t a_bytes = kp.a_stage_bytes;
+  const int sa_fit = (int)std::min<size_t>(kMaxSA, (budget - 4 * (size_t)kp.b_stage_bytes) / a_bytes);
+  kp.sa = std::max(2, std::min(sa_fit, 3));
+  kp.sb = (int)std::min<size_t>(kMaxSB, (budget - (size_t)kp.sa * a_bytes) / kp.b_stage_bytes);
+  return kp.sb >= 3;
+}
+
+static bool patch_eligible(int Wg, int Hg) {
+  const int m = patch_mode();
+  if (m < 0) return false;
+  if (m > 0) return true;
+  // tiles are 16 x 8 pixels: skip maps where the padding to whole tiles wastes more than ~20 % of the MMA work
+  const double eff = (double)Wg * Hg / ((double)((Wg + 7) / 8 * 8) * ((Hg + 15) / 16 * 16));
+  return eff >= 0.8;
+}
+
+static void set_out_strides(PatchKParams& kp, const TView& o, int step, const ConvEpilogue& ep) {
+  kp.os_n = (int64_t)o.pitch * o.W * o.H;
+  kp.os_h = (int64_t)o.pitch * o.W * step;
+  kp.os_w = o.pitch * step;
+  if (ep.addend) {
+    kp.as_n = (int64_t)ep.addend_pitch * o.W * o.H;
+    kp.as_h = (int64_t)ep.addend_pitch * o.W * step;
+    kp.as_w = ep.addend_pitch * step;
+  }
+}
+
+int conv_patch_plan_fwd(ConvPlan& pl, const TView& in, const bf16* wp, int ks, int stride, const TView& out,
+                        const ConvEpilogue& ep) {
+  if (ks != 3 || (stride != 1 && stride != 2) || ep.out_kind != OUT_BF16) return 1;
+  if (in.C % 8 || in.pitch % 8 || out.pitch % 8 || out.C % 16) return 1;
+  if (in.H % stride || in.W % stride || out.H != in.H / stride || out.W != in.W / stride || out.N != in.N) return 1;
+  if (!patch_eligible(out.W, out.H)) return 1;
+  memset(&pl.pp, 0, sizeof(pl.pp));
+  PatchKParams& kp = pl.pp;
+  kp.W = out.W;
+  kp.H = out.H;
+  kp.NB = out.N;
+  kp.ngroups = 1;
+  if (finish_patch_plan(pl, wp, out.C, 9L * in.C, in.C, out, ep, 0, 0)) return -1;
+  const size_t stats_bytes = ep.stats ? (size_t)4 * 2 * out.C * sizeof(float) : 0;
+  const int halo = stride == 1 ? 2 : 1;
+  if (!choose_supertile(kp, out.W, out.H, out.N, 1, halo, halo, stats_bytes)) return 1;
+  const int SW = 8 * kp.TW, SH = 16 * kp.TH;
+  int nt = 0, np = 0;
+  if (stride == 1) {
+    PPatch& pa = kp.patches[np++];
+    pa.map = 0;
+    pa.ox = -1;
+    pa.oy = -1;
+    pa.pitch = SW + 2;
+    pa.bytes = (uint32_t)(SW + 2) * (SH + 2) * 128u;
+    pa.tap_begin = 0;
+    if (make_patch_map(&kp.tmA[0], in, SW + 2, SH + 2, 0, 0, 1, 1)) return -1;
+    for (int i = 1; i < 4; ++i) kp.tmA[i] = kp.tmA[0];
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw) kp.taps[nt++] = PTap{kh * pa.pitch + kw, (kh * 3 + kw) * in.C};
+    pa.tap_end = nt;
+  } else {
+    // input pixel (2*ho + kh - 1, 2*wo + kw - 1): k = 0 -> parity 1 at block offset -1; k = 1 -> parity 0 at 0; k = 2 -> parity 1 at 0
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        PPatch& pa = kp.patches[np];
+        pa.map = np;
+        pa.ox = px ? -1 : 0;
+        pa.oy = py ? -1 : 0;
+        const int bw = SW + (px ? 1 : 0), bh = SH + (py ? 1 : 0);
+        pa.pitch = bw;
+        pa.bytes = (uint32_t)bw * bh * 128u;
+        pa.tap_begin = nt;
+        if (make_patch_map(&kp.tmA[np], in, bw, bh, py, px, 2, 2)) return -1;
+        for (int kh = 0; kh < 3; ++kh) {
+          if (((kh - 1) & 1) != py) continue;
+          for (int kw = 0; kw < 3; ++kw) {
+            if (((kw - 1) & 1) != px) continue;
+            const int oh = py ? (kh == 0 ? 0 : 1) : 0, ow = px ? (kw == 0 ? 0 : 1) : 0;
+            kp.taps[nt++] = PTap{oh * bw + ow, (kh * 3 + kw) * in.C};
+          }
+        }
+        pa.tap_end = nt;
+        ++np;
+      }
+  }
+  kp.groups[0] = ConvGroup{0, np, 0, 0};
+  set_out_strides(kp, out, 1, ep);
+  const long total = (long)kp.NB * kp.tiles_h * kp.tiles_w * kp.tiles_c;
+  pl.grid = (int)std::min<long>(total, conv_max_grid());
+  pl.smem = (int)(1024 + kBarRegion + (size_t)kp.sa * kp.a_stage_bytes + (size_t)kp.sb * kp.b_stage_bytes + stats_bytes);
+  pl.smem = std::max(pl.smem, 120 * 1024);
+  return 0;
+}
+
+int conv_patch_plan_dgrad(ConvPlan& pl, const TView& dy, const bf16* wt, int ks, int stride, const TView& dx,
+                          const ConvEpilogue& ep) {
+  if (ks != 3 || (stride != 1 && stride != 2) || ep.out_kind != OUT_BF16) return 1;
+  if (dy.C % 8 || dy.pitch % 8 || dx.pitch % 8 || dx.C % 16) return 1;
+  if (dx.H % stride || dx.W % stride || dy.H != dx.H / stride || dy.W != dx.W / stride || dy.N != dx.N) return 1;
+  const int Wg = dx.W / stride, Hg = dx.H / stride;
+  if (!patch_eligible(Wg, Hg)) return 1;
+  memset(&pl.pp, 0, sizeof(pl.pp));
+  PatchKParams& kp = pl.pp;
+  kp.W = Wg;
+  kp.H = Hg;
+  kp.NB = dx.N;
+  kp.ngroups = stride == 1 ? 1 : 4;
+  if (finish_patch_plan(pl, wt, dx.C, 9L * dy.C, dy.C, dx, ep, 0, 0)) return -1;
+  const int halo = stride == 1 ? 2 : 1;
+  if (!choose_supertile(kp, Wg, Hg, dx.N, kp.ngroups, halo, halo, 0)) return 1;
+  const int SW = 8 * kp.TW, SH = 16 * kp.TH;
+  int nt = 0;
+  if (stride == 1) {
+    // dx[h,w] = sum_{kh,kw} dy[h + 1 - kh, w + 1 - kw] * W[:, :, kh, kw]
+    PPatch& pa = kp.patches[0];
+    pa.map = 0;
+    pa.ox = -1;
+    pa.oy = -1;
+    pa.pitch = SW + 2;
+    pa.bytes = (uint32_t)(SW + 2) * (SH + 2) * 128u;
+    pa.tap_begin = 0;
+    if (make_patch_map(&kp.tmA[0], dy, SW + 2, SH + 2, 0, 0, 1, 1)) return -1;
+    for (int i = 1; i < 4; ++i) kp.tmA[i] = kp.tmA[0];
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw) kp.taps[nt++] = PTap{(2 - kh) * pa.pitch + (2 - kw), (kh * 3 + kw) * dy.C};
+    pa.tap_end = nt;
+    kp.groups[0] = ConvGroup{0, 1, 0, 0};
+  } else {
+    // output parity classes dx[2*hb+py, 2*wb+px]; contributing kh: (py + 1 - kh) even, dy row = hb + (py + 1 - kh) / 2
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        const int g = py * 2 + px;
+        PPatch& pa = kp.patches[g];
+        pa.map = g;
+        pa.ox = 0;
+        pa.oy = 0;
+        const int bw = SW + px, bh = SH + py;
+        pa.pitch = bw;
+        pa.bytes = (uint32_t)bw * bh * 128u;
+        pa.tap_begin = nt;
+        if (make_patch_map(&kp.tmA[g], dy, bw, bh, 0, 0, 1, 1)) return -1;
+        for (int kh = 0; kh < 3; ++kh) {
+          if (((py + 1 - kh) & 1) != 0) continue;
+          for (int kw = 0; kw < 3; ++kw) {
+            if (((px + 1 - kw) & 1) != 0) continue;
+            const int dh = (py + 1 - kh) / 2, dw = (px + 1 - kw) / 2;  // 0 or 1
+            kp.taps[nt++] = PTap{dh * bw + dw, (kh * 3 + kw) * dy.C};
+          }
+        }
+        pa.tap_end = nt;
+        kp.groups[g].tap_begin = g;
+        kp.groups[g].tap_end = g + 1;
+        kp.groups[g].out_off = ((int64_t)py * dx.W + px) * dx.pitch;
+        kp.groups[g].add_off = ((int64_t)py * dx.W + px) * ep.addend_pitch;
+      }
+  }
+  set_out_strides(kp, dx, stride, ep);
+  const long total = (long)kp.ngroups * kp.NB * kp.tiles_h * kp.tiles_w * kp.tiles_c;
+  pl.grid = (int)std::min<long>(total, conv_max_grid());
+  pl.smem = (int)(1024 + kBarRegion + (size_t)kp.sa * kp.a_stage_bytes + (size_t)kp.sb * kp.b_stage_bytes);
+  pl.smem = std::max(pl.smem, 120 * 1024);
+  return 0;
+}
+
+int conv_patch_run(const ConvPlan& pl, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  conv_patch_kernel<<<pl.grid, kThreads, pl.smem, st>>>(pl.pp);
+  YB_LAUNCHED();
+  return 0;
+}
+
+}  // namespace yb

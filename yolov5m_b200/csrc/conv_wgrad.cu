@@ -123,10 +123,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
+      // ONE thread issues: descriptors are advanced by integer adds on the 14-bit start-address field (16-byte units)
       const uint32_t idesc = make_idesc_bf16(128, p.BLOCK_N, 1, 1);  // both operands MN-major
       const uint32_t lt = swizzle_layout_type(128);
-      const uint32_t lbo = p.box_bytes;
       const int kinner = p.KP / 16;
+      const uint64_t desc0 = make_smem_desc(smem_u32(stage_smem), p.box_bytes, 1024, lt);
+      const uint32_t stage_step = p.stage_bytes >> 4, tile_step = (2u * p.box_bytes) >> 4;
+      const uint32_t b_off = (2u * p.MT * p.box_bytes) >> 4;
       int s = 0;
       uint32_t ph = 0;
       int iter = 0;
@@ -137,20 +140,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
         const int mts = min(p.MT, p.m_tiles - it.mg * p.MT);
         mbar_wait(tempty_bar, (iter & 1) ^ 1);
         tc_fence_after();
+        uint32_t acc = 0;
         for (int pt = pt0; pt < pt1; ++pt) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(stage_smem + (size_t)s * p.stage_bytes);
-          const uint32_t b_addr = a_addr + 2u * p.MT * p.box_bytes;
+          const uint64_t a_desc = desc0 + (uint64_t)(s * stage_step);
+          const uint64_t b_desc = a_desc + b_off;
           for (int mt = 0; mt < mts; ++mt) {
             const uint32_t d_tmem = tmem_base + mt * p.BLOCK_N;
-            const uint32_t at = a_addr + (uint32_t)mt * 2u * p.box_bytes;
-            for (int k = 0; k < kinner; ++k) {
-              const uint64_t da = make_smem_desc(at + k * 2048, lbo, 1024, lt);
-              const uint64_t db = make_smem_desc(b_addr + k * 2048, lbo, 1024, lt);
-              umma_bf16(d_tmem, da, db, idesc, (pt != pt0 || k != 0) ? 1u : 0u);
+            uint64_t da = a_desc + (uint64_t)(mt * tile_step), db = b_desc;
+            umma_bf16(d_tmem, da, db, idesc, acc);
+            for (int k = 1; k < kinner; ++k) {
+              da += 128;  // 16 pixels x 128 B = 2048 B
+              db += 128;
+              umma_bf16(d_tmem, da, db, idesc, 1u);
             }
           }
+          acc = 1u;
           umma_commit(&empty_bar[s]);
           if (++s == p.stages) {
             s = 0;
