@@ -162,6 +162,9 @@ PATCH_FWD = [
     (1, 20, 20, 384, 384, 3, 1),   # partial tiles in both directions, 2 N tiles
     (2, 64, 64, 48, 96, 3, 2),     # stride 2: four parity patches
     (3, 22, 22, 192, 384, 3, 2),   # odd 11x11 output grid
+    (2, 32, 32, 48, 48, 1, 1),     # 1x1 through the patch kernel: four tiles per weight stage
+    (2, 32, 48, 192, 96, 1, 1),
+    (1, 40, 40, 384, 192, 1, 1),
 ]
 
 
@@ -183,6 +186,8 @@ def test_conv_patch_fused_epilogue(patch_mode):
 
 
 PATCH_DG = [
+    (2, 32, 32, 48, 48, 1, 1),
+    (2, 32, 48, 96, 192, 1, 1),
     (2, 32, 32, 48, 48, 3, 1),
     (2, 32, 40, 96, 48, 3, 1),
     (2, 24, 40, 192, 192, 3, 1),

@@ -9,7 +9,8 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libyolov5m_b200.so")
 STAMP = os.path.join(HERE, ".build_stamp")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+EXTRA = os.environ.get("YB_NVCC_EXTRA", "").split()
+FLAGS = EXTRA + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
 

@@ -168,6 +168,22 @@ __host__ __device__ __forceinline__ uint32_t swizzle_layout_type(int row_bytes) 
   return row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
 }
 
+// Division by a launch-time constant without the ~30-instruction integer-division sequence (the TMA / MMA roles are single
+// threads: per-tile index decoding is on their critical path).  Exact for n * d < 2^32.
+struct FDiv {
+  uint32_t mul, d;
+};
+__host__ inline FDiv make_fdiv(int d) {
+  FDiv f;
+  f.d = (uint32_t)d;
+  f.mul = d <= 1 ? 0u : (uint32_t)((0x100000000ull + (uint32_t)d - 1) / (uint32_t)d);
+  return f;
+}
+__device__ __forceinline__ void fdivmod(int n, const FDiv& f, int& q, int& r) {
+  q = f.d <= 1 ? n : (int)__umulhi((uint32_t)n, f.mul);
+  r = n - q * (int)f.d;
+}
+
 __device__ __forceinline__ float silu_f(float z) { return z / (1.0f + __expf(-z)); }
 
 // ---------------------------------------------------------------- host: TMA descriptor encode (driver entry point)

@@ -5,11 +5,47 @@
 
 namespace yb {
 
-// P: kernel parameter struct with the epilogue fields of ConvKParams (stats, scale, shift, act, addend, out_kind, out,
+// Kernel parameters live in constant bank 0 (the parameter struct is > 1.5 KB with its tensor maps); the compiler
+// re-materialises every p.field use as an LDC inside the per-tile loops, and those constant loads miss often enough to
+// show up as the top long-scoreboard stall of the epilogue (profiles/).  The hot loops therefore work on REGISTER copies:
+// keep_in_reg() launders a value through an empty asm so it cannot be folded back into a constant-bank operand.
+__device__ __forceinline__ void keep_in_reg(int& x) { asm volatile("" : "+r"(x)); }
+__device__ __forceinline__ void keep_in_reg(uint32_t& x) { asm volatile("" : "+r"(x)); }
+__device__ __forceinline__ void keep_in_reg(int64_t& x) { asm volatile("" : "+l"(x)); }
+template <class T>
+__device__ __forceinline__ void keep_in_reg(T*& x) {
+  unsigned long long v = reinterpret_cast<unsigned long long>(x);
+  asm volatile("" : "+l"(v));
+  x = reinterpret_cast<T*>(v);
+}
+__device__ __forceinline__ void keep_in_reg(FDiv& f) {
+  keep_in_reg(f.mul);
+  keep_in_reg(f.d);
+}
+
+struct EpiArgs {
+  float* stats;
+  const float* scale;
+  const float* shift;
+  const bf16* addend;
+  void* out;
+  int act, out_kind, Cout, H, W, head_na, head_no;
+};
+template <class P>
+__device__ __forceinline__ EpiArgs load_epi_args(const P& p) {
+  EpiArgs e;
+  e.stats = p.stats; e.scale = p.scale; e.shift = p.shift; e.addend = p.addend; e.out = p.out;
+  e.act = p.act; e.out_kind = p.out_kind; e.Cout = p.Cout; e.H = p.H; e.W = p.W; e.head_na = p.head_na; e.head_no = p.head_no;
+  keep_in_reg(e.stats); keep_in_reg(e.scale); keep_in_reg(e.shift); keep_in_reg(e.addend); keep_in_reg(e.out);
+  keep_in_reg(e.act); keep_in_reg(e.out_kind); keep_in_reg(e.Cout); keep_in_reg(e.H); keep_in_reg(e.W);
+  keep_in_reg(e.head_na); keep_in_reg(e.head_no);
+  return e;
+}
+
+// P: EpiArgs (register copy of the epilogue fields of ConvKParams (stats, scale, shift, act, addend, out_kind, out,
 // Cout, H, W, head_na, head_no).  t_addr: TMEM address of column 0 of this chunk for this warp's lane quarter.
 // (n, h, w): output pixel of this thread's row; opix / apix: element offsets of that pixel in out / addend.
-template <class P>
-__device__ __forceinline__ void conv_epilogue_chunk(const P& p, uint32_t t_addr, int col0, bool valid, int n, int h, int w,
+__device__ __forceinline__ void conv_epilogue_chunk(const EpiArgs& p, uint32_t t_addr, int col0, bool valid, int n, int h, int w,
                                                     int64_t opix, int64_t apix, float* my_stats, int lane) {
     uint32_t vr[16];
     tmem_ld16(t_addr, vr);

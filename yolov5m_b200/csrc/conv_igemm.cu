@@ -29,16 +29,21 @@ struct TileCoord {
   int g, nb, hb, wb, nt;
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int t) {
+struct TileDec {
+  FDiv c, w, h, n;
+};
+__device__ __forceinline__ TileDec load_tile_dec(const ConvKParams& p) {
+  TileDec d{p.fd_c, p.fd_w, p.fd_h, p.fd_n};
+  keep_in_reg(d.c); keep_in_reg(d.w); keep_in_reg(d.h); keep_in_reg(d.n);
+  return d;
+}
+__device__ __forceinline__ TileCoord decode_tile(const TileDec& d, int t) {
   TileCoord c;
-  c.nt = t % p.tiles_c;
-  int m = t / p.tiles_c;
-  c.wb = m % p.tiles_w;
-  m /= p.tiles_w;
-  c.hb = m % p.tiles_h;
-  m /= p.tiles_h;
-  c.nb = m % p.tiles_n;
-  c.g = m / p.tiles_n;
+  int m;
+  fdivmod(t, d.c, m, c.nt);
+  fdivmod(m, d.w, m, c.wb);
+  fdivmod(m, d.h, m, c.hb);
+  fdivmod(m, d.n, c.g, c.nb);
   return c;
 }
 
@@ -50,6 +55,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   uint64_t* tfull_bar = empty_bar + kMaxStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  ConvTap* s_taps = reinterpret_cast<ConvTap*>(smem + 512);      // [16] shared copies: indexed constant-bank loads are slow
+  ConvGroup* s_groups = reinterpret_cast<ConvGroup*>(smem + 640);  // [4]
   uint8_t* a_smem = smem + kBarRegion;
   uint8_t* b_smem = a_smem + (size_t)p.stages * p.a_stage_bytes;
   float* s_stats = reinterpret_cast<float*>(b_smem + (size_t)p.stages * p.b_stage_bytes);  // [4][2][Cout]
@@ -58,6 +65,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.ngroups * p.tiles_n * p.tiles_h * p.tiles_w * p.tiles_c;
 
+  if (threadIdx.x < 16) s_taps[threadIdx.x] = p.taps[threadIdx.x];
+  if (threadIdx.x >= 32 && threadIdx.x < 36) s_groups[threadIdx.x - 32] = p.groups[threadIdx.x - 32];
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(&full_bar[i], 1);
@@ -85,21 +94,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
+      const TileDec td = load_tile_dec(p);
+      int PW = p.PW, PH = p.PH, PN = p.PN, BN = p.BLOCK_N, chunks = p.chunks, KC = p.KC, stages = p.stages;
+      uint32_t tx = p.a_tx_bytes + p.b_tx_bytes, a_sb = p.a_stage_bytes, b_sb = p.b_stage_bytes;
+      keep_in_reg(PW); keep_in_reg(PH); keep_in_reg(PN); keep_in_reg(BN); keep_in_reg(chunks); keep_in_reg(KC);
+      keep_in_reg(stages); keep_in_reg(tx); keep_in_reg(a_sb); keep_in_reg(b_sb);
       int s = 0;
       uint32_t ph = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const TileCoord tc = decode_tile(p, t);
-        const ConvGroup& grp = p.groups[tc.g];
-        const int w0 = tc.wb * p.PW, h0 = tc.hb * p.PH, n0 = tc.nb * p.PN, c0 = tc.nt * p.BLOCK_N;
+        const TileCoord tc = decode_tile(td, t);
+        const ConvGroup grp = s_groups[tc.g];
+        const int w0 = tc.wb * PW, h0 = tc.hb * PH, n0 = tc.nb * PN, c0 = tc.nt * BN;
         for (int tp = grp.tap_begin; tp < grp.tap_end; ++tp) {
-          const ConvTap tap = p.taps[tp];
-          for (int ch = 0; ch < p.chunks; ++ch) {
+          const ConvTap tap = s_taps[tp];
+          for (int ch = 0; ch < chunks; ++ch) {
             mbar_wait(&empty_bar[s], ph ^ 1);
-            mbar_expect_tx(&full_bar[s], p.a_tx_bytes + p.b_tx_bytes);
-            tma_load_4d(&p.tmA[tap.map], &full_bar[s], a_smem + (size_t)s * p.a_stage_bytes, ch * p.KC, w0 + tap.dw,
-                        h0 + tap.dh, n0);
-            tma_load_2d(&p.tmB, &full_bar[s], b_smem + (size_t)s * p.b_stage_bytes, tap.kbase + ch * p.KC, c0);
-            if (++s == p.stages) {
+            mbar_expect_tx(&full_bar[s], tx);
+            tma_load_4d(&p.tmA[tap.map], &full_bar[s], a_smem + (size_t)s * a_sb, ch * KC, w0 + tap.dw, h0 + tap.dh, n0);
+            tma_load_2d(&p.tmB, &full_bar[s], b_smem + (size_t)s * b_sb, tap.kbase + ch * KC, c0);
+            if (++s == stages) {
               s = 0;
               ph ^= 1;
             }
@@ -120,14 +133,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       const uint64_t desc_hi = make_smem_desc(0, 16, sbo, lt);
       const uint64_t a_desc0 = desc_hi | (uint64_t)(smem_u32(a_smem) >> 4);
       const uint64_t b_desc0 = desc_hi | (uint64_t)(smem_u32(b_smem) >> 4);
-      const uint32_t a_step = p.a_stage_bytes >> 4, b_step = p.b_stage_bytes >> 4;
+      uint32_t a_step = p.a_stage_bytes >> 4, b_step = p.b_stage_bytes >> 4;
+      const TileDec td = load_tile_dec(p);
+      int chunks = p.chunks, stages = p.stages;
+      keep_in_reg(a_step); keep_in_reg(b_step); keep_in_reg(chunks); keep_in_reg(stages);
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-        const TileCoord tc = decode_tile(p, t);
-        const ConvGroup& grp = p.groups[tc.g];
-        const int nk = (grp.tap_end - grp.tap_begin) * p.chunks;
+        const TileCoord tc = decode_tile(td, t);
+        const ConvGroup grp = s_groups[tc.g];
+        const int nk = (grp.tap_end - grp.tap_begin) * chunks;
         const int ab = it & 1;
         const uint32_t aph = (it >> 1) & 1;
         mbar_wait(&tempty_bar[ab], aph ^ 1);
@@ -148,7 +164,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
           }
           acc = 1u;
           umma_commit(&empty_bar[s]);
-          if (++s == p.stages) {
+          if (++s == stages) {
             s = 0;
             ph ^= 1;
           }
@@ -165,23 +181,35 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     const int phh = (r / p.PW) % p.PH;
     const int pw = r % p.PW;
     float* my_stats = s_stats + (size_t)q * 2 * p.Cout;
+    // register copies of everything the per-tile loop reads (see keep_in_reg)
+    const EpiArgs ea = load_epi_args(p);
+    const TileDec td = load_tile_dec(p);
+    int PW = p.PW, PH = p.PH, PN = p.PN, NB = p.NB, BN = p.BLOCK_N;
+    int64_t t_on = p.PN * p.os_n, t_oh = p.PH * p.os_h, t_ow = p.PW * p.os_w;  // element strides between tiles
+    int64_t t_an = p.PN * p.as_n, t_ah = p.PH * p.as_h, t_aw = p.PW * p.as_w;
+    int64_t o_thr = pn * p.os_n + phh * p.os_h + pw * p.os_w, a_thr = pn * p.as_n + phh * p.as_h + pw * p.as_w;
+    keep_in_reg(PW); keep_in_reg(PH); keep_in_reg(PN); keep_in_reg(NB); keep_in_reg(BN);
+    keep_in_reg(t_on); keep_in_reg(t_oh); keep_in_reg(t_ow); keep_in_reg(t_an); keep_in_reg(t_ah); keep_in_reg(t_aw);
+    keep_in_reg(o_thr); keep_in_reg(a_thr);
+    const bool row_ok = r < p.PW * p.PH * p.PN;
+    const int nchunks = BN / 16;
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-      const TileCoord tc = decode_tile(p, t);
-      const int n = tc.nb * p.PN + pn, h = tc.hb * p.PH + phh, w = tc.wb * p.PW + pw;
-      const bool valid = (r < p.PW * p.PH * p.PN) && n < p.NB && h < p.H && w < p.W;
-      const int64_t opix = p.groups[tc.g].out_off + n * p.os_n + h * p.os_h + w * p.os_w;
-      const int64_t apix = p.groups[tc.g].add_off + n * p.as_n + h * p.as_h + w * p.as_w;
+      const TileCoord tc = decode_tile(td, t);
+      const ConvGroup grp = s_groups[tc.g];
+      const int n = tc.nb * PN + pn, h = tc.hb * PH + phh, w = tc.wb * PW + pw;
+      const bool valid = row_ok && n < NB && h < ea.H && w < ea.W;
+      const int64_t opix = grp.out_off + tc.nb * t_on + tc.hb * t_oh + tc.wb * t_ow + o_thr;
+      const int64_t apix = grp.add_off + tc.nb * t_an + tc.hb * t_ah + tc.wb * t_aw + a_thr;
       const int ab = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       mbar_wait(&tfull_bar[ab], aph);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 256;
-      const int nchunks = p.BLOCK_N / 16;
       for (int cc = eg; cc < nchunks; cc += kEpiGroups) {
-        const int col0 = tc.nt * p.BLOCK_N + cc * 16;
-        if (col0 >= p.Cout) break;
-        conv_epilogue_chunk(p, t_addr + cc * 16, col0, valid, n, h, w, opix, apix, my_stats, lane);
+        const int col0 = tc.nt * BN + cc * 16;
+        if (col0 >= ea.Cout) break;
+        conv_epilogue_chunk(ea, t_addr + cc * 16, col0, valid, n, h, w, opix, apix, my_stats, lane);
       }
       tc_fence_before();
       __syncwarp();
@@ -272,6 +300,10 @@ static int finish_plan(ConvPlan& pl, const bf16* wmat, int wrows, long wcols, co
   kp.tiles_w = (kp.W + kp.PW - 1) / kp.PW;
   kp.tiles_h = (kp.H + kp.PH - 1) / kp.PH;
   kp.tiles_n = (kp.NB + kp.PN - 1) / kp.PN;
+  kp.fd_c = make_fdiv(kp.tiles_c);
+  kp.fd_w = make_fdiv(kp.tiles_w);
+  kp.fd_h = make_fdiv(kp.tiles_h);
+  kp.fd_n = make_fdiv(kp.tiles_n);
   kp.a_stage_bytes = 128u * 2u * kp.KC;
   kp.b_stage_bytes = ((uint32_t)kp.BLOCK_N * 2u * kp.KC + 1023u) & ~1023u;
   kp.a_tx_bytes = (uint32_t)(kp.PW * kp.PH * kp.PN) * 2u * kp.KC;

@@ -43,6 +43,7 @@ struct ConvKParams {
   int32_t tiles_w, tiles_h, tiles_n, tiles_c;
   int32_t W, H, NB;          // output pixel grid (per group)
   int32_t Cout, BLOCK_N;
+  FDiv fd_c, fd_w, fd_h, fd_n;  // tile index decoding
   int32_t stages;
   uint32_t a_stage_bytes, b_stage_bytes, a_tx_bytes, b_tx_bytes;
   // epilogue
@@ -82,6 +83,7 @@ struct PatchKParams {
   int32_t tiles_w, tiles_h, tiles_c;  // super-tiles per image row / column, N tiles
   int32_t W, H, NB;          // output pixel grid (per group)
   int32_t Cout, BLOCK_N;
+  FDiv fd_c, fd_w, fd_h, fd_n;  // super-tile index decoding
   int32_t sa, sb;            // pipeline depth of the patch ring / weight ring
   uint32_t a_stage_bytes, b_stage_bytes, b_tx_bytes;
   // epilogue (same meaning as ConvKParams)

@@ -34,16 +34,21 @@ struct STile {
   int g, n, hb, wb, nt;
 };
 
-__device__ __forceinline__ STile decode_stile(const PatchKParams& p, int t) {
+struct STileDec {
+  FDiv c, w, h, n;
+};
+__device__ __forceinline__ STileDec load_stile_dec(const PatchKParams& p) {
+  STileDec d{p.fd_c, p.fd_w, p.fd_h, p.fd_n};
+  keep_in_reg(d.c); keep_in_reg(d.w); keep_in_reg(d.h); keep_in_reg(d.n);
+  return d;
+}
+__device__ __forceinline__ STile decode_stile(const STileDec& d, int t) {
   STile c;
-  c.nt = t % p.tiles_c;
-  int m = t / p.tiles_c;
-  c.wb = m % p.tiles_w;
-  m /= p.tiles_w;
-  c.hb = m % p.tiles_h;
-  m /= p.tiles_h;
-  c.n = m % p.NB;
-  c.g = m / p.NB;
+  int m;
+  fdivmod(t, d.c, m, c.nt);
+  fdivmod(m, d.w, m, c.wb);
+  fdivmod(m, d.h, m, c.hb);
+  fdivmod(m, d.n, c.g, c.n);
   return c;
 }
 
@@ -57,6 +62,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
   uint64_t* tfull_bar = bempty + kMaxSB;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  PTap* s_taps = reinterpret_cast<PTap*>(smem + 512);          // [16] shared copies: indexed constant-bank loads are slow
+  PPatch* s_patches = reinterpret_cast<PPatch*>(smem + 640);   // [4] x 28 B
+  ConvGroup* s_groups = reinterpret_cast<ConvGroup*>(smem + 768);  // [4] x 24 B
   uint8_t* a_smem = smem + kBarRegion;
   uint8_t* b_smem = a_smem + (size_t)p.sa * p.a_stage_bytes;
   float* s_stats = reinterpret_cast<float*>(b_smem + (size_t)p.sb * p.b_stage_bytes);  // [4][2][Cout]
@@ -66,6 +74,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
   const int total = p.ngroups * p.NB * p.tiles_h * p.tiles_w * p.tiles_c;
   const int T = p.TH * p.TW;
 
+  if (threadIdx.x < 16) s_taps[threadIdx.x] = p.taps[threadIdx.x];
+  if (threadIdx.x >= 32 && threadIdx.x < 36) s_patches[threadIdx.x - 32] = p.patches[threadIdx.x - 32];
+  if (threadIdx.x >= 64 && threadIdx.x < 68) s_groups[threadIdx.x - 64] = p.groups[threadIdx.x - 64];
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.sa; ++i) {
       mbar_init(&afull[i], 1);
@@ -97,20 +108,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
   if (warp == 0) {
     // ------------------------------------------------------------------ patch producer
     if (lane == 0) {
+      const STileDec td = load_stile_dec(p);
+      int SW = p.TW * 8, SH = p.TH * 16, chunks = p.chunks, nsa = p.sa;
+      uint32_t a_sb = p.a_stage_bytes;
+      keep_in_reg(SW); keep_in_reg(SH); keep_in_reg(chunks); keep_in_reg(nsa); keep_in_reg(a_sb);
       int s = 0;
       uint32_t ph = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
-        const STile tc = decode_stile(p, t);
-        const ConvGroup& grp = p.groups[tc.g];
-        const int w0 = tc.wb * p.TW * 8, h0 = tc.hb * p.TH * 16;
+        const STile tc = decode_stile(td, t);
+        const ConvGroup grp = s_groups[tc.g];
+        const int w0 = tc.wb * SW, h0 = tc.hb * SH;
         for (int pi = grp.tap_begin; pi < grp.tap_end; ++pi) {
-          const PPatch& pa = p.patches[pi];
-          for (int ch = 0; ch < p.chunks; ++ch) {
+          const PPatch pa = s_patches[pi];
+          for (int ch = 0; ch < chunks; ++ch) {
             mbar_wait(&aempty[s], ph ^ 1);
             mbar_expect_tx(&afull[s], pa.bytes);
-            tma_load_4d(&p.tmA[pa.map], &afull[s], a_smem + (size_t)s * p.a_stage_bytes, ch * 64, w0 + pa.ox, h0 + pa.oy,
-                        tc.n);
-            if (++s == p.sa) {
+            tma_load_4d(&p.tmA[pa.map], &afull[s], a_smem + (size_t)s * a_sb, ch * 64, w0 + pa.ox, h0 + pa.oy, tc.n);
+            if (++s == nsa) {
               s = 0;
               ph ^= 1;
             }
@@ -121,20 +135,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
   } else if (warp == 3) {
     // ------------------------------------------------------------------ weight producer
     if (lane == 0) {
+      const STileDec td = load_stile_dec(p);
+      int BN = p.BLOCK_N, chunks = p.chunks, nsb = p.sb;
+      uint32_t b_sb = p.b_stage_bytes, b_tx = p.b_tx_bytes;
+      keep_in_reg(BN); keep_in_reg(chunks); keep_in_reg(nsb); keep_in_reg(b_sb); keep_in_reg(b_tx);
       int s = 0;
       uint32_t ph = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
-        const STile tc = decode_stile(p, t);
-        const ConvGroup& grp = p.groups[tc.g];
-        const int c0 = tc.nt * p.BLOCK_N;
+        const STile tc = decode_stile(td, t);
+        const ConvGroup grp = s_groups[tc.g];
+        const int c0 = tc.nt * BN;
         for (int pi = grp.tap_begin; pi < grp.tap_end; ++pi) {
-          const PPatch& pa = p.patches[pi];
-          for (int ch = 0; ch < p.chunks; ++ch) {
+          const PPatch pa = s_patches[pi];
+          for (int ch = 0; ch < chunks; ++ch) {
             for (int tp = pa.tap_begin; tp < pa.tap_end; ++tp) {
               mbar_wait(&bempty[s], ph ^ 1);
-              mbar_expect_tx(&bfull[s], p.b_tx_bytes);
-              tma_load_2d(&p.tmB, &bfull[s], b_smem + (size_t)s * p.b_stage_bytes, p.taps[tp].kbase + ch * 64, c0);
-              if (++s == p.sb) {
+              mbar_expect_tx(&bfull[s], b_tx);
+              tma_load_2d(&p.tmB, &bfull[s], b_smem + (size_t)s * b_sb, s_taps[tp].kbase + ch * 64, c0);
+              if (++s == nsb) {
                 s = 0;
                 ph ^= 1;
               }
@@ -150,14 +168,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
       // start-address field in 16-byte units, advanced by integer adds), or small-N tiles become issue-bound.
       const uint32_t idesc = make_idesc_bf16(128, p.BLOCK_N, 0, 0);
       const uint64_t b_desc0 = make_smem_desc(smem_u32(b_smem), 16, 1024, 2);
-      const uint32_t a_step = p.a_stage_bytes >> 4, b_step = p.b_stage_bytes >> 4;
+      uint32_t a_step = p.a_stage_bytes >> 4, b_step = p.b_stage_bytes >> 4;
       const uint32_t a_base16 = smem_u32(a_smem) >> 4;
+      const STileDec td = load_stile_dec(p);
+      int BN = p.BLOCK_N, chunks = p.chunks, nsa = p.sa, nsb = p.sb, TWl = p.TW;
+      keep_in_reg(a_step); keep_in_reg(b_step); keep_in_reg(BN); keep_in_reg(chunks); keep_in_reg(nsa); keep_in_reg(nsb);
+      keep_in_reg(TWl);
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
       int it = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-        const STile tc = decode_stile(p, t);
-        const ConvGroup& grp = p.groups[tc.g];
+        const STile tc = decode_stile(td, t);
+        const ConvGroup grp = s_groups[tc.g];
         const int ab = it & 1;
         const uint32_t aph = (it >> 1) & 1;
         mbar_wait(&tempty_bar[ab], aph ^ 1);
@@ -165,21 +187,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
         const uint32_t d_base = tmem_base + ab * 256;
         uint32_t acc = 0;
         for (int pi = grp.tap_begin; pi < grp.tap_end; ++pi) {
-          const PPatch& pa = p.patches[pi];
+          const PPatch pa = s_patches[pi];
           const uint64_t a_hi = make_smem_desc(0, 16, (uint32_t)pa.pitch * 128u, 2);
           // tile (ty, tx) starts (16*ty*pitch + 8*tx) pixel rows (x 128 B = x 8 descriptor units) into the patch
           uint32_t tile_off[4];
 #pragma unroll
           for (int tt = 0; tt < 4; ++tt) {
-            const int ty = tt / p.TW, tx = tt - ty * p.TW;
+            const int ty = tt / TWl, tx = tt - ty * TWl;
             tile_off[tt] = (uint32_t)(ty * 16 * pa.pitch + tx * 8) * 8u;
           }
-          for (int ch = 0; ch < p.chunks; ++ch) {
+          for (int ch = 0; ch < chunks; ++ch) {
             mbar_wait(&afull[sa], pha);
             tc_fence_after();
             const uint64_t a_desc = a_hi | (uint64_t)(a_base16 + sa * a_step);
             for (int tp = pa.tap_begin; tp < pa.tap_end; ++tp) {
-              const uint64_t a_tap = a_desc + (uint64_t)((uint32_t)p.taps[tp].row_off * 8u);
+              const uint64_t a_tap = a_desc + (uint64_t)((uint32_t)s_taps[tp].row_off * 8u);
               mbar_wait(&bfull[sb], phb);
               tc_fence_after();
               const uint64_t db = b_desc0 + (uint64_t)(sb * b_step);
@@ -187,7 +209,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
               for (int tt = 0; tt < 4; ++tt) {
                 if (tt >= T) break;
                 const uint64_t da = a_tap + tile_off[tt];
-                const uint32_t d_tmem = d_base + (uint32_t)tt * p.BLOCK_N;
+                const uint32_t d_tmem = d_base + (uint32_t)tt * BN;
                 umma_bf16(d_tmem, da, db, idesc, acc);
                 umma_bf16(d_tmem, da + 2, db + 2, idesc, 1u);
                 umma_bf16(d_tmem, da + 4, db + 4, idesc, 1u);
@@ -195,13 +217,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
               }
               acc = 1u;
               umma_commit(&bempty[sb]);
-              if (++sb == p.sb) {
+              if (++sb == nsb) {
                 sb = 0;
                 phb ^= 1;
               }
             }
             umma_commit(&aempty[sa]);
-            if (++sa == p.sa) {
+            if (++sa == nsa) {
               sa = 0;
               pha ^= 1;
             }
@@ -217,25 +239,34 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
     const int r = q * 32 + lane;
     const int phh = r >> 3, pw = r & 7;
     float* my_stats = s_stats + (size_t)q * 2 * p.Cout;
-    const int nchunks = p.BLOCK_N / 16;
+    // register copies of everything the per-tile loop reads (see keep_in_reg in conv_epilogue.cuh)
+    const EpiArgs ea = load_epi_args(p);
+    const STileDec td = load_stile_dec(p);
+    int BN = p.BLOCK_N, TWl = p.TW, THl = p.TH;
+    int64_t os_n = p.os_n, os_h = p.os_h, os_w = p.os_w, as_n = p.as_n, as_h = p.as_h, as_w = p.as_w;
+    keep_in_reg(BN); keep_in_reg(TWl); keep_in_reg(THl);
+    keep_in_reg(os_n); keep_in_reg(os_h); keep_in_reg(os_w); keep_in_reg(as_n); keep_in_reg(as_h); keep_in_reg(as_w);
+    const int nchunks = BN / 16;
     int it = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-      const STile tc = decode_stile(p, t);
+      const STile tc = decode_stile(td, t);
+      const ConvGroup grp = s_groups[tc.g];
+      const int64_t o_base = grp.out_off + tc.n * os_n, a_base = grp.add_off + tc.n * as_n;
       const int ab = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       mbar_wait(&tfull_bar[ab], aph);
       tc_fence_after();
       for (int idx = eg; idx < T * nchunks; idx += kEpiGroups) {
         const int tt = idx / nchunks, cc = idx - tt * nchunks;
-        const int col0 = tc.nt * p.BLOCK_N + cc * 16;
-        if (col0 >= p.Cout) continue;
-        const int ty = tt / p.TW, tx = tt - ty * p.TW;
-        const int h = (tc.hb * p.TH + ty) * 16 + phh, w = (tc.wb * p.TW + tx) * 8 + pw;
-        const bool valid = h < p.H && w < p.W;
-        const int64_t opix = p.groups[tc.g].out_off + tc.n * p.os_n + h * p.os_h + w * p.os_w;
-        const int64_t apix = p.groups[tc.g].add_off + tc.n * p.as_n + h * p.as_h + w * p.as_w;
-        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 256 + tt * p.BLOCK_N + cc * 16;
-        conv_epilogue_chunk(p, t_addr, col0, valid, tc.n, h, w, opix, apix, my_stats, lane);
+        const int col0 = tc.nt * BN + cc * 16;
+        if (col0 >= ea.Cout) continue;
+        const int ty = tt / TWl, tx = tt - ty * TWl;
+        const int h = (tc.hb * THl + ty) * 16 + phh, w = (tc.wb * TWl + tx) * 8 + pw;
+        const bool valid = h < ea.H && w < ea.W;
+        const int64_t opix = o_base + h * os_h + w * os_w;
+        const int64_t apix = a_base + h * as_h + w * as_w;
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 256 + tt * BN + cc * 16;
+        conv_epilogue_chunk(ea, t_addr, col0, valid, tc.n, h, w, opix, apix, my_stats, lane);
       }
       tc_fence_before();
       __syncwarp();
@@ -366,6 +397,10 @@ static bool patch_eligible(int Wg, int Hg) {
 }
 
 static void set_out_strides(PatchKParams& kp, const TView& o, int step, const ConvEpilogue& ep) {
+  kp.fd_c = make_fdiv(kp.tiles_c);
+  kp.fd_w = make_fdiv(kp.tiles_w);
+  kp.fd_h = make_fdiv(kp.tiles_h);
+  kp.fd_n = make_fdiv(kp.NB);
   kp.os_n = (int64_t)o.pitch * o.W * o.H;
   kp.os_h = (int64_t)o.pitch * o.W * step;
   kp.os_w = o.pitch * step;
@@ -378,7 +413,8 @@ static void set_out_strides(PatchKParams& kp, const TView& o, int step, const Co
 
 int conv_patch_plan_fwd(ConvPlan& pl, const TView& in, const bf16* wp, int ks, int stride, const TView& out,
                         const ConvEpilogue& ep) {
-  if (ks != 3 || (stride != 1 && stride != 2) || ep.out_kind != OUT_BF16) return 1;
+  if ((ks != 3 && ks != 1) || (stride != 1 && stride != 2) || ep.out_kind != OUT_BF16) return 1;
+  if (ks == 1 && stride != 1) return 1;
   if (in.C % 8 || in.pitch % 8 || out.pitch % 8 || out.C % 16) return 1;
   if (in.H % stride || in.W % stride || out.H != in.H / stride || out.W != in.W / stride || out.N != in.N) return 1;
   if (!patch_eligible(out.W, out.H)) return 1;
@@ -388,13 +424,26 @@ int conv_patch_plan_fwd(ConvPlan& pl, const TView& in, const bf16* wp, int ks, i
   kp.H = out.H;
   kp.NB = out.N;
   kp.ngroups = 1;
-  if (finish_patch_plan(pl, wp, out.C, 9L * in.C, in.C, out, ep, 0, 0)) return -1;
+  if (finish_patch_plan(pl, wp, out.C, (long)ks * ks * in.C, in.C, out, ep, 0, 0)) return -1;
   const size_t stats_bytes = ep.stats ? (size_t)4 * 2 * out.C * sizeof(float) : 0;
-  const int halo = stride == 1 ? 2 : 1;
+  const int halo = ks == 1 ? 0 : (stride == 1 ? 2 : 1);
   if (!choose_supertile(kp, out.W, out.H, out.N, 1, halo, halo, stats_bytes)) return 1;
   const int SW = 8 * kp.TW, SH = 16 * kp.TH;
   int nt = 0, np = 0;
-  if (stride == 1) {
+  if (ks == 1) {
+    // 1x1: no halo, one tap; the point is several 128-pixel tiles per weight stage and per TMEM hand-off
+    PPatch& pa = kp.patches[np++];
+    pa.map = 0;
+    pa.ox = 0;
+    pa.oy = 0;
+    pa.pitch = SW;
+    pa.bytes = (uint32_t)SW * SH * 128u;
+    pa.tap_begin = 0;
+    if (make_patch_map(&kp.tmA[0], in, SW, SH, 0, 0, 1, 1)) return -1;
+    for (int i = 1; i < 4; ++i) kp.tmA[i] = kp.tmA[0];
+    kp.taps[nt++] = PTap{0, 0};
+    pa.tap_end = nt;
+  } else if (stride == 1) {
     PPatch& pa = kp.patches[np++];
     pa.map = 0;
     pa.ox = -1;
@@ -443,7 +492,8 @@ int conv_patch_plan_fwd(ConvPlan& pl, const TView& in, const bf16* wp, int ks, i
 
 int conv_patch_plan_dgrad(ConvPlan& pl, const TView& dy, const bf16* wt, int ks, int stride, const TView& dx,
                           const ConvEpilogue& ep) {
-  if (ks != 3 || (stride != 1 && stride != 2) || ep.out_kind != OUT_BF16) return 1;
+  if ((ks != 3 && ks != 1) || (stride != 1 && stride != 2) || ep.out_kind != OUT_BF16) return 1;
+  if (ks == 1 && stride != 1) return 1;
   if (dy.C % 8 || dy.pitch % 8 || dx.pitch % 8 || dx.C % 16) return 1;
   if (dx.H % stride || dx.W % stride || dy.H != dx.H / stride || dy.W != dx.W / stride || dy.N != dx.N) return 1;
   const int Wg = dx.W / stride, Hg = dx.H / stride;
@@ -454,12 +504,25 @@ int conv_patch_plan_dgrad(ConvPlan& pl, const TView& dy, const bf16* wt, int ks,
   kp.H = Hg;
   kp.NB = dx.N;
   kp.ngroups = stride == 1 ? 1 : 4;
-  if (finish_patch_plan(pl, wt, dx.C, 9L * dy.C, dy.C, dx, ep, 0, 0)) return -1;
-  const int halo = stride == 1 ? 2 : 1;
+  if (finish_patch_plan(pl, wt, dx.C, (long)ks * ks * dy.C, dy.C, dx, ep, 0, 0)) return -1;
+  const int halo = ks == 1 ? 0 : (stride == 1 ? 2 : 1);
   if (!choose_supertile(kp, Wg, Hg, dx.N, kp.ngroups, halo, halo, 0)) return 1;
   const int SW = 8 * kp.TW, SH = 16 * kp.TH;
   int nt = 0;
-  if (stride == 1) {
+  if (ks == 1) {
+    PPatch& pa = kp.patches[0];
+    pa.map = 0;
+    pa.ox = 0;
+    pa.oy = 0;
+    pa.pitch = SW;
+    pa.bytes = (uint32_t)SW * SH * 128u;
+    pa.tap_begin = 0;
+    if (make_patch_map(&kp.tmA[0], dy, SW, SH, 0, 0, 1, 1)) return -1;
+    for (int i = 1; i < 4; ++i) kp.tmA[i] = kp.tmA[0];
+    kp.taps[nt++] = PTap{0, 0};
+    pa.tap_end = nt;
+    kp.groups[0] = ConvGroup{0, 1, 0, 0};
+  } else if (stride == 1) {
     // dx[h,w] = sum_{kh,kw} dy[h + 1 - kh, w + 1 - kw] * W[:, :, kh, kw]
     PPatch& pa = kp.patches[0];
     pa.map = 0;

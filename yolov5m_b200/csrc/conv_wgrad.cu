@@ -39,10 +39,9 @@ struct WItem {
 
 __device__ __forceinline__ WItem decode_item(const WgradKParams& p, int t) {
   WItem c;
-  c.nt = t % p.n_tiles;
-  t /= p.n_tiles;
-  c.mg = t % p.m_groups;
-  c.sp = t / p.m_groups;
+  int m;
+  fdivmod(t, p.fd_nt, m, c.nt);
+  fdivmod(m, p.fd_mg, c.sp, c.mg);
   return c;
 }
 
@@ -92,18 +91,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
         const int box1 = min(p.boxes_total, box0 + p.MT * 2);
         const uint32_t tx = (uint32_t)(box1 - box0 + p.nb) * p.box_bytes;
         for (int pt = pt0; pt < pt1; ++pt) {
-          int m = pt;
-          const int w0 = (m % p.tiles_w) * p.PW;
-          m /= p.tiles_w;
-          const int h0 = (m % p.tiles_h) * p.PH;
-          const int n0 = (m / p.tiles_h) * p.PN;
+          int m, wi, hi, ni;
+          fdivmod(pt, p.fd_tw, m, wi);
+          fdivmod(m, p.fd_th, ni, hi);
+          const int w0 = wi * p.PW, h0 = hi * p.PH, n0 = ni * p.PN;
           mbar_wait(&empty_bar[s], ph ^ 1);
           mbar_expect_tx(&full_bar[s], tx);
           uint8_t* as = stage_smem + (size_t)s * p.stage_bytes;
           uint8_t* bs = as + (size_t)2 * p.MT * p.box_bytes;
           for (int j = 0; j < p.nb; ++j)
             tma_load_4d(&p.tmDY, &full_bar[s], bs + (size_t)j * p.box_bytes, it.nt * p.BLOCK_N + j * kBoxC, w0, h0, n0);
-          int tapi = box0 / p.cboxes, cb = box0 - tapi * p.cboxes;
+          int tapi, cb;
+          fdivmod(box0, p.fd_cb, tapi, cb);
           for (int b = box0; b < box1; ++b) {
             const ConvTap tap = p.taps[tapi];
             tma_load_4d(&p.tmX[tap.map], &full_bar[s], as + (size_t)(b - box0) * p.box_bytes, cb * kBoxC, w0 + tap.dw,
@@ -181,8 +180,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
       tc_fence_after();
       for (int mt = 0; mt < mts; ++mt) {
         const int box = box0 + mt * 2 + (r >> 6);
-        const int tapi = box / p.cboxes;
-        const int ci = (box - tapi * p.cboxes) * kBoxC + (r & 63);
+        int tapi, cbi;
+        fdivmod(box, p.fd_cb, tapi, cbi);
+        const int ci = cbi * kBoxC + (r & 63);
         const bool valid = box < p.boxes_total && ci < p.Cin;
         float* dst = p.partial + ((size_t)it.sp * p.Mpad + (size_t)tapi * p.Cin_pad + ci) * p.Npad + it.nt * p.BLOCK_N;
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + mt * p.BLOCK_N;
@@ -411,6 +411,11 @@ int wgrad_plan(WgradPlan& pl, const TView& x, const TView& dy, int ks, int strid
   YB_REQUIRE(splits >= 1, "wgrad: workspace too small (%zu floats, need >= %zu)", partial_floats, per_split);
   kp.splits = splits;
   kp.partial = partial;
+  kp.fd_nt = make_fdiv(kp.n_tiles);
+  kp.fd_mg = make_fdiv(kp.m_groups);
+  kp.fd_tw = make_fdiv(kp.tiles_w);
+  kp.fd_th = make_fdiv(kp.tiles_h);
+  kp.fd_cb = make_fdiv(kp.cboxes);
   pl.grid = std::min(base_items * splits, sms);
   return 0;
 }

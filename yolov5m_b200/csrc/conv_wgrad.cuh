@@ -16,6 +16,7 @@ struct WgradKParams {
   int32_t KP, PW, PH, PN;    // pixels per pipeline stage (GEMM-K chunk) and its patch shape
   int32_t tiles_w, tiles_h, tiles_n, ptiles;
   int32_t splits;
+  FDiv fd_nt, fd_mg, fd_tw, fd_th, fd_cb;  // item / pixel-tile / box index decoding
   int32_t Cout, Cin, Cin_pad, ldo;  // ldo = ntaps * Cin = row length of dW
   int32_t Mpad, Npad;        // partial tile: [Mpad = ntaps*Cin_pad][Npad = n_tiles*BLOCK_N]
   int32_t stages;
