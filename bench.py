@@ -143,7 +143,8 @@ def run_ours(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     from yolov5m_b200.build import build
     build()
     import yolov5m_b200 as yb
@@ -252,14 +253,16 @@ def run_ours(a):
                "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e / a.steps}
 
     # ---- (3) roofline of the dominant kernel: CUDA events around every conv launch (separate instrumented steps)
+    #      every rank runs these steps (they contain the gradient all-reduce); only rank 0 records events
     roof, kern = None, None
+    eng = model.engine(B, S, S, True)
+    nprof = min(3, a.steps)
     if rank == 0:
-        eng = model.engine(B, S, S, True)
         eng.prof = []
-        nprof = min(3, a.steps)
-        for i in range(nprof):
-            step(dev_imgs[i % nbuf], dev_tgts[i % nbuf])
-        torch.cuda.synchronize()
+    for i in range(nprof):
+        step(dev_imgs[i % nbuf], dev_tgts[i % nbuf])
+    torch.cuda.synchronize()
+    if rank == 0:
         acc = {}
         for kind, flops, s0, s1 in eng.prof:
             d = acc.setdefault(kind, [0.0, 0.0, 0])
