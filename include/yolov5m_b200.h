@@ -66,6 +66,8 @@ int yb_plan_run(void* plan, void* stream);
  * 0 = heuristic, 1 = halo-patch kernel (conv_patch.cu) wherever legal, 2 = same plus multi-tile super-tiles on small
  * problems, -1 = generic kernel (conv_igemm.cu) only.  Results are identical up to fp32 summation order. */
 void yb_set_conv_patch_mode(int mode);
+/* same for the weight-gradient kernels planned after the call (conv_wgrad_patch.cu vs conv_wgrad.cu; $YB_WGRAD_PATCH) */
+void yb_set_wgrad_patch_mode(int mode);
 void yb_plan_destroy(void* plan);
 
 /* ---- Conv2d weight gradient (autograd of model.py:16 / :162) ---------------------------------------------------

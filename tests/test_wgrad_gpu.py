@@ -82,3 +82,21 @@ def test_wgrad_index_map_and_pitch():
     m = perm >= 0
     want[perm[m].long()] = packed[m]
     assert rel(dw.cpu(), want) < TOL
+
+
+# ---- halo-patch variant (csrc/conv_wgrad_patch.cu) forced on for every eligible shape
+@pytest.fixture
+def wpatch_mode():
+    L = _lib.lib()
+    L.yb_set_wgrad_patch_mode(1)
+    yield
+    L.yb_set_wgrad_patch_mode(0)
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c[5] == 3 and c[6] == 1] + [(2, 32, 48, 192, 192, 3, 1), (1, 40, 40, 96, 256, 3, 1)])
+def test_conv_wgrad_patch(case, wpatch_mode):
+    test_conv_wgrad(case)
+
+
+def test_wgrad_patch_index_map_and_pitch(wpatch_mode):
+    test_wgrad_index_map_and_pitch()

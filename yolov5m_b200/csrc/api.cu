@@ -6,6 +6,7 @@
 #include "conv_wgrad.cuh"
 
 namespace yb {
+void set_wgrad_patch_mode(int m);
 const char* last_error();
 long long launch_count();
 }
@@ -18,6 +19,7 @@ int yb_version(void) { return 1; }
 int64_t yb_launch_count(void) { return (int64_t)yb::launch_count(); }
 int yb_conv_max_partials(void) { return conv_max_grid(); }
 void yb_set_conv_patch_mode(int mode) { set_patch_mode(mode); }
+void yb_set_wgrad_patch_mode(int mode) { set_wgrad_patch_mode(mode); }
 
 int yb_conv2d_fwd(const void* x, int N, int H, int W, int Cin, int64_t x_pitch, const void* w_packed, int Cout,
                   int ks, int stride, void* y, int64_t y_pitch, int out_kind, const float* scale,

@@ -294,8 +294,6 @@ static int make_map(CUtensorMap* m, const TView& v, int PW, int PH, int PN, int 
   return encode_tmap(m, base, 4, dims, strides, box, 128, 2);
 }
 
-int wgrad_max_grid();
-
 static int pick_block_n(int Cout, int& n_tiles) {
   const int c64 = (Cout + kBoxC - 1) / kBoxC;  // dy boxes in total
   n_tiles = (c64 + 3) / 4;                     // <= 4 boxes (256 columns) per N tile
@@ -312,6 +310,11 @@ size_t wgrad_min_workspace_floats(int Cin, int Cout, int ks) {
 int wgrad_plan(WgradPlan& pl, const TView& x, const TView& dy, int ks, int stride, float* partial, size_t partial_floats,
                int max_splits) {
   memset(&pl, 0, sizeof(pl));
+  {
+    const int rc = wgrad_patch_plan(pl, x, dy, ks, stride, partial, partial_floats, max_splits);
+    if (rc <= 0) return rc;
+    pl.kind = 0;
+  }
   WgradKParams& kp = pl.kp;
   YB_REQUIRE((ks == 1 || ks == 3) && (stride == 1 || stride == 2), "wgrad: ks=%d stride=%d unsupported", ks, stride);
   YB_REQUIRE(x.C % 8 == 0 && dy.C % 8 == 0 && x.pitch % 8 == 0 && dy.pitch % 8 == 0, "wgrad: channel alignment");
@@ -438,9 +441,13 @@ int wgrad_run(const WgradPlan& pl, float* out, int out_rows, const int* map, int
     attr_set = true;
   }
   YB_REQUIRE(out_rows > 0 && out_rows <= pl.kp.Cout, "wgrad: out_rows=%d", out_rows);
-  conv_wgrad_kernel<<<pl.grid, kThreads, pl.smem, st>>>(pl.kp);
-  YB_LAUNCHED();
-  const WgradKParams& kp = pl.kp;
+  if (pl.kind == 1) {
+    if (wgrad_patch_launch(pl, st)) return -2;
+  } else {
+    conv_wgrad_kernel<<<pl.grid, kThreads, pl.smem, st>>>(pl.kp);
+    YB_LAUNCHED();
+  }
+  const WgradKParams& kp = pl.kp;  // the patch planner fills the reduce-relevant fields of kp as well
   // split-lanes: enough threads to fill the machine even when the output is tiny and the split count large
   int SL = 1;
   while (SL < 32 && SL * 2 <= kp.splits && (long)kp.ldo * out_rows * SL < 148L * 2048) SL *= 2;

@@ -24,11 +24,36 @@ struct WgradKParams {
   float* partial;            // [splits][Mpad][Npad]
 };
 
+// ---- "patch" variant (conv_wgrad_patch.cu): 3x3 / stride 1 with the nine shifted x operands read from ONE halo patch --
+struct WPatchKParams {
+  CUtensorMap tmDY;        // dy (Cout, W, H, N), box (64, PW, PH, 1)
+  CUtensorMap tmX;         // x  (Cin,  W, H, N), box (64, PW + 2, PH + 2, 1)
+  int32_t tap_off16[9];    // (kh * pitch + kw) * 128 / 16: start of tap (kh, kw) inside the patch, descriptor units
+  int32_t cboxes;          // 64-channel chunks of Cin (one patch each)
+  int32_t MT, m_groups;    // M tiles (pairs of taps) per work item, items per chunk; 5 tiles per chunk: (0,1)(2,3)(4,5)(6,7)(8,-)
+  int32_t nb, BLOCK_N, n_tiles;
+  int32_t PW, PH, KP, pitch;
+  int32_t a_step16, a_sbo;  // A start advance per K = 16 step (descriptor units) and byte stride between its two 8-pixel groups
+  int32_t tiles_w, tiles_h, ptiles, splits;
+  FDiv fd_nt, fd_mg, fd_cb, fd_tw, fd_th;
+  int32_t Cout, Cin, Cin_pad, Mpad, Npad;
+  int32_t stages;
+  uint32_t patch_tx, patch_bytes, box_bytes, stage_bytes;  // patch_tx = TMA box bytes, patch_bytes = aligned slot
+  float* partial;          // [splits][Mpad = 9 * Cin_pad][Npad]  (same layout as WgradKParams::partial)
+};
+
 struct WgradPlan {
   WgradKParams kp;
+  WPatchKParams pp;
+  int kind;  // 0 = conv_wgrad_kernel (kp), 1 = conv_wgrad_patch_kernel (pp)
   int grid;
   int smem;
 };
+// patch variant: 1 = shape not eligible (use the generic kernel), 0 = planned, < 0 error
+int wgrad_patch_plan(WgradPlan& pl, const TView& x, const TView& dy, int ks, int stride, float* partial,
+                     size_t partial_floats, int max_splits);
+int wgrad_patch_launch(const WgradPlan& pl, cudaStream_t st);
+int wgrad_max_grid();
 
 // x: conv input (N,H,W,Cin); dy: grad of the conv output (N,H/s,W/s,Cout).
 int wgrad_plan(WgradPlan& pl, const TView& x, const TView& dy, int ks, int stride, float* partial,
