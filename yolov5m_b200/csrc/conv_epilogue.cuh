@@ -117,7 +117,15 @@ __device__ __forceinline__ void conv_epilogue_chunk(const EpiArgs& p, uint32_t t
       }
       if (p.addend != nullptr) {
         const uint4* ap = reinterpret_cast<const uint4*>(p.addend + apix + col0);
-        uint4 r0 = __ldg(ap), r1 = __ldg(ap + 1);
+        uint4 r0, r1;
+        if ((reinterpret_cast<uintptr_t>(ap) & 31) == 0) {
+          asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                       : "=r"(r0.x), "=r"(r0.y), "=r"(r0.z), "=r"(r0.w), "=r"(r1.x), "=r"(r1.y), "=r"(r1.z), "=r"(r1.w)
+                       : "l"(ap));
+        } else {
+          r0 = __ldg(ap);
+          r1 = __ldg(ap + 1);
+        }
         const bf16* e0 = reinterpret_cast<const bf16*>(&r0);
         const bf16* e1 = reinterpret_cast<const bf16*>(&r1);
 #pragma unroll
@@ -135,9 +143,17 @@ __device__ __forceinline__ void conv_epilogue_chunk(const EpiArgs& p, uint32_t t
           h0[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
           h1[j] = __floats2bfloat162_rn(v[8 + 2 * j], v[8 + 2 * j + 1]);
         }
-        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + opix + col0);
-        op[0] = o0;
-        op[1] = o1;
+        // one 32-byte store per thread (st.global.v8, sm_100): a full L2 sector instead of two half-sector writes
+        // (every tensor of the network has a pitch that is a multiple of 16 channels; other pitches take the 2 x 16 B path)
+        bf16* op = reinterpret_cast<bf16*>(p.out) + opix + col0;
+        if ((reinterpret_cast<uintptr_t>(op) & 31) == 0) {
+          asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(op), "r"(o0.x), "r"(o0.y),
+                       "r"(o0.z), "r"(o0.w), "r"(o1.x), "r"(o1.y), "r"(o1.z), "r"(o1.w)
+                       : "memory");
+        } else {
+          reinterpret_cast<uint4*>(op)[0] = o0;
+          reinterpret_cast<uint4*>(op)[1] = o1;
+        }
       } else if (p.out_kind == OUT_F32) {
         float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + opix + col0);
 #pragma unroll
