@@ -191,11 +191,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
           tmem_ld16(t_addr + cc * 16, vr);
           tmem_ld_wait();
           if (valid) {
-            float4* o = reinterpret_cast<float4*>(dst + cc * 16);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              o[j] = make_float4(__uint_as_float(vr[4 * j]), __uint_as_float(vr[4 * j + 1]),
-                                 __uint_as_float(vr[4 * j + 2]), __uint_as_float(vr[4 * j + 3]));
+            // two 32-byte stores (st.global.v8): full L2 sectors; rows of the partial tile are Npad * 4 bytes apart
+            float* o = dst + cc * 16;
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o), "r"(vr[0]), "r"(vr[1]),
+                         "r"(vr[2]), "r"(vr[3]), "r"(vr[4]), "r"(vr[5]), "r"(vr[6]), "r"(vr[7])
+                         : "memory");
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o + 8), "r"(vr[8]), "r"(vr[9]),
+                         "r"(vr[10]), "r"(vr[11]), "r"(vr[12]), "r"(vr[13]), "r"(vr[14]), "r"(vr[15])
+                         : "memory");
           }
         }
       }
@@ -319,6 +322,7 @@ int wgrad_plan(WgradPlan& pl, const TView& x, const TView& dy, int ks, int strid
   YB_REQUIRE((ks == 1 || ks == 3) && (stride == 1 || stride == 2), "wgrad: ks=%d stride=%d unsupported", ks, stride);
   YB_REQUIRE(x.C % 8 == 0 && dy.C % 8 == 0 && x.pitch % 8 == 0 && dy.pitch % 8 == 0, "wgrad: channel alignment");
   YB_REQUIRE(dy.H == x.H / stride && dy.W == x.W / stride && dy.N == x.N, "wgrad: geometry");
+  YB_REQUIRE((reinterpret_cast<uintptr_t>(partial) & 31) == 0, "wgrad: workspace must be 32-byte aligned");
   YB_REQUIRE(x.H % stride == 0 && x.W % stride == 0, "wgrad: odd input for stride 2");
   kp.Cout = dy.C;
   kp.Cin = x.C;

@@ -180,11 +180,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_patch_kernel(const __g
           tmem_ld16(t_addr + cc * 16, vr);
           tmem_ld_wait();
           if (valid) {
-            float4* o = reinterpret_cast<float4*>(dst + cc * 16);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              o[j] = make_float4(__uint_as_float(vr[4 * j]), __uint_as_float(vr[4 * j + 1]),
-                                 __uint_as_float(vr[4 * j + 2]), __uint_as_float(vr[4 * j + 3]));
+            // two 32-byte stores (st.global.v8): full L2 sectors; rows of the partial tile are Npad * 4 bytes apart
+            float* o = dst + cc * 16;
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o), "r"(vr[0]), "r"(vr[1]),
+                         "r"(vr[2]), "r"(vr[3]), "r"(vr[4]), "r"(vr[5]), "r"(vr[6]), "r"(vr[7])
+                         : "memory");
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o + 8), "r"(vr[8]), "r"(vr[9]),
+                         "r"(vr[10]), "r"(vr[11]), "r"(vr[12]), "r"(vr[13]), "r"(vr[14]), "r"(vr[15])
+                         : "memory");
           }
         }
       }
