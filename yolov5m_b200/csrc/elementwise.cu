@@ -70,9 +70,29 @@ __device__ __forceinline__ V8 cvt8(const uint4& r) {
   return o;
 }
 __device__ __forceinline__ uint4 ldraw(const bf16* p) { return *reinterpret_cast<const uint4*>(p); }
-// SiLU / its derivative with the fast reciprocal (2 ulp): these passes are HBM-bound, keep the ALU work minimal
-__device__ __forceinline__ float sigmoid_fast(float z) { return __fdividef(1.f, 1.f + __expf(-z)); }
-__device__ __forceinline__ float silu_fast(float z) { return z * sigmoid_fast(z); }
+// SiLU / its derivative through ONE special-function op per element: sigmoid(z) = 0.5 * tanh(z / 2) + 0.5 with
+// tanh.approx.f32 (max relative error 2^-11, below the bf16 rounding of every value these passes store).  exp + reciprocal
+// would be two MUFU ops per element, and at 16 MUFU results / clock / SM that -- not HBM -- bounded these passes.
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float z) { return fmaf(0.5f, tanh_fast(0.5f * z), 0.5f); }
+__device__ __forceinline__ float silu_fast(float z) {
+  const float hz = 0.5f * z;
+  return fmaf(hz, tanh_fast(hz), hz);
+}
+__device__ __forceinline__ V8 half8(V8 a) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a.v[j] *= 0.5f;
+  return a;
+}
+// dz / da of SiLU(z) given hz = z / 2:  s + z * s * (1 - s)  with  s = (1 + t) / 2,  s (1 - s) = (1 - t^2) / 4,  t = tanh(hz)
+__device__ __forceinline__ float dsilu_half(float hz) {
+  const float t = tanh_fast(hz);
+  return fmaf(0.5f * hz, fmaf(-t, t, 1.f), fmaf(0.5f, t, 0.5f));
+}
 __device__ __forceinline__ V8 ldf8(const float* p) {
   const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
   V8 o;
@@ -161,7 +181,10 @@ __global__ void __launch_bounds__(kEwThreads) bn_act_fwd_kernel(const bf16* __re
   const unsigned cv = C >> 3;
   auto finish = [&](long pix, unsigned c, V8 v, const V8& sc, const V8& sh, const uint4* rraw) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v.v[j] = silu_fast(fmaf(v.v[j], sc.v[j], sh.v[j]));
+    for (int j = 0; j < 8; ++j) {  // sc / sh are HALF the BN scale / shift: hz = z / 2, SiLU(z) = hz * tanh(hz) + hz
+      const float hz = fmaf(v.v[j], sc.v[j], sh.v[j]);
+      v.v[j] = fmaf(hz, tanh_fast(hz), hz);
+    }
     if (rraw != nullptr) {
       const V8 r = cvt8(*rraw);
 #pragma unroll
@@ -182,7 +205,7 @@ __global__ void __launch_bounds__(kEwThreads) bn_act_fwd_kernel(const bf16* __re
     const unsigned T = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned c = (tid % cv) << 3;
     const long pstep = T / cv;
-    const V8 sc = ldf8(scale + c), sh = ldf8(shift + c);
+    const V8 sc = half8(ldf8(scale + c)), sh = half8(ldf8(shift + c));
     long pix = tid / cv;
     for (; pix + (kEwUnroll - 1) * pstep < npix; pix += kEwUnroll * pstep) {
       uint4 yr[kEwUnroll], rr[kEwUnroll];
@@ -209,7 +232,7 @@ __global__ void __launch_bounds__(kEwThreads) bn_act_fwd_kernel(const bf16* __re
       const uint4 yr = ldraw(y + pix * y_pitch + c);
       uint4 rr = make_uint4(0, 0, 0, 0);
       if (res != nullptr) rr = ldraw(res + pix * res_pitch + c);
-      finish(pix, c, cvt8(yr), ldf8(scale + c), ldf8(shift + c), res != nullptr ? &rr : nullptr);
+      finish(pix, c, cvt8(yr), half8(ldf8(scale + c)), half8(ldf8(shift + c)), res != nullptr ? &rr : nullptr);
     }
   }
 }
@@ -285,7 +308,7 @@ __device__ __forceinline__ float dsilu_f(float z) {
 // pass 1: per-channel sums of dz and dz*xhat, dz = da * silu'(y*scale+shift), xhat = (y-mean)*invstd.
 // block = (rows x cv) threads; every block owns a contiguous pixel range; partial[block][2][C].
 // mode 1: plain column sums of `da` (head bias gradient): partial[block][0][C] only.
-__global__ void __launch_bounds__(256, 3) bn_act_bwd_reduce_kernel(const bf16* __restrict__ da, long da_pitch, const bf16* __restrict__ y,
+__global__ void __launch_bounds__(256, 2) bn_act_bwd_reduce_kernel(const bf16* __restrict__ da, long da_pitch, const bf16* __restrict__ y,
                                          long y_pitch, long npix, int C, const float* __restrict__ scale,
                                          const float* __restrict__ shift, const float* __restrict__ mean,
                                          const float* __restrict__ invstd, float* __restrict__ partial, int rows_pb,
@@ -300,9 +323,12 @@ __global__ void __launch_bounds__(256, 3) bn_act_bwd_reduce_kernel(const bf16* _
   if (row < rows_pb) {
     const long per = (npix + gridDim.x - 1) / gridDim.x;
     const long p0 = (long)blockIdx.x * per, p1 = min(npix, p0 + per);
-    V8 sc, sh, mu, is;
+    V8 sc, sh, xa, xb;  // hz = y*sc + sh (half scale / shift), xhat = y*xa + xb
     if (mode == 0) {
-      sc = ldf8(scale + c); sh = ldf8(shift + c); mu = ldf8(mean + c); is = ldf8(invstd + c);
+      sc = half8(ldf8(scale + c)); sh = half8(ldf8(shift + c)); xa = ldf8(invstd + c);
+      const V8 mu = ldf8(mean + c);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xb.v[j] = -mu.v[j] * xa.v[j];
     }
     auto accum = [&](const uint4& graw, const uint4& yraw) {
       const V8 g = cvt8(graw);
@@ -310,9 +336,9 @@ __global__ void __launch_bounds__(256, 3) bn_act_bwd_reduce_kernel(const bf16* _
         const V8 yv = cvt8(yraw);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float dz = g.v[j] * dsilu_f(fmaf(yv.v[j], sc.v[j], sh.v[j]));
+          const float dz = g.v[j] * dsilu_half(fmaf(yv.v[j], sc.v[j], sh.v[j]));
           s1[j] += dz;
-          s2[j] = fmaf(dz, (yv.v[j] - mu.v[j]) * is.v[j], s2[j]);
+          s2[j] = fmaf(dz, fmaf(yv.v[j], xa.v[j], xb.v[j]), s2[j]);
         }
       } else {
 #pragma unroll
@@ -376,13 +402,22 @@ __global__ void __launch_bounds__(kEwThreads) bn_act_bwd_apply_kernel(const bf16
                                         const float* __restrict__ invstd, const float* __restrict__ coef,
                                         bf16* __restrict__ dy, long dy_pitch) {
   const unsigned cv = C >> 3;
+  // dy = scale * (dz - coef0 - xhat * coef1),  xhat = (y - mean) * invstd   ==>   dy = scale * dz + (y * m1 + m0)
   struct Par {
-    V8 sc, sh, mu, is, c0, c1;
+    V8 hsc, hsh, sc, m1, m0;
   };
   auto load_par = [&](unsigned c) {
     Par q;
-    q.sc = ldf8(scale + c); q.sh = ldf8(shift + c); q.mu = ldf8(mean + c); q.is = ldf8(invstd + c);
-    q.c0 = ldf8(coef + c); q.c1 = ldf8(coef + C + c);
+    q.sc = ldf8(scale + c);
+    q.hsc = half8(q.sc);
+    q.hsh = half8(ldf8(shift + c));
+    const V8 mu = ldf8(mean + c), is = ldf8(invstd + c), c0 = ldf8(coef + c), c1 = ldf8(coef + C + c);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float k1 = is.v[j] * c1.v[j];
+      q.m1.v[j] = -q.sc.v[j] * k1;
+      q.m0.v[j] = -q.sc.v[j] * (c0.v[j] - mu.v[j] * k1);
+    }
     return q;
   };
   auto finish = [&](long pix, unsigned c, const uint4& graw, const uint4& yraw, const Par& q) {
@@ -390,9 +425,8 @@ __global__ void __launch_bounds__(kEwThreads) bn_act_bwd_apply_kernel(const bf16
     V8 o;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float dz = g.v[j] * dsilu_f(fmaf(yv.v[j], q.sc.v[j], q.sh.v[j]));
-      const float xh = (yv.v[j] - q.mu.v[j]) * q.is.v[j];
-      o.v[j] = q.sc.v[j] * (dz - q.c0.v[j] - xh * q.c1.v[j]);
+      const float dz = g.v[j] * dsilu_half(fmaf(yv.v[j], q.hsc.v[j], q.hsh.v[j]));
+      o.v[j] = fmaf(q.sc.v[j], dz, fmaf(yv.v[j], q.m1.v[j], q.m0.v[j]));
     }
     st8(dy + pix * dy_pitch + c, o);
   };
@@ -655,7 +689,7 @@ int yb_add_into(const void* src, int64_t src_pitch, void* dst, int64_t dst_pitch
   return 0;
 }
 
-static constexpr int kReduceRows = 444;
+static constexpr int kReduceRows = 296;
 static int reduce_geometry(int C, long npix, int& threads, int& rows_pb, int& grid, size_t& smem) {
   const int cv = C / 8;
   YB_REQUIRE(C % 8 == 0 && cv <= 256, "bwd_reduce: C=%d unsupported", C);
@@ -664,7 +698,7 @@ static int reduce_geometry(int C, long npix, int& threads, int& rows_pb, int& gr
   threads = ((rows_pb * cv + 31) / 32) * 32;
   smem = (size_t)rows_pb * 2 * C * sizeof(float);
   const long want = (npix + (long)rows_pb * 16 - 1) / ((long)rows_pb * 16);  // >= 16 pixels per thread row
-  grid = (int)std::max<long>(1, std::min<long>(want, kReduceRows));  // one resident wave: 148 SMs x 3 CTAs
+  grid = (int)std::max<long>(1, std::min<long>(want, kReduceRows));  // one resident wave: 148 SMs x 2 CTAs
   return 0;
 }
 
