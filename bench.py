@@ -53,6 +53,24 @@ def peaks():
         return 1400.0, 6650.0, "fallback"
 
 
+def conv_traffic_per_launch():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the conv kernels, from the committed ncu launch summary
+    (profiles/launch_summary_*.json, written by tools/summarize_launches.py from an ncu capture of this same command)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "launch_summary_*.json")))
+    if not files:
+        return None
+    try:
+        with open(files[-1]) as f:
+            d = json.load(f)
+        ks = [k for k in d["kernels"] if "conv_igemm_kernel" in k["kernel"] or "conv_patch_kernel" in k["kernel"]]
+        n = sum(k["launches_per_step"] for k in ks)
+        b = sum(k["dram_read_GB_per_step"] + k["dram_write_GB_per_step"] for k in ks) * 1e9
+        return b / n if n else None
+    except Exception:
+        return None
+
+
 # ---------------------------------------------------------------------------------------------------- clocks sampler
 class Clocks:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -273,10 +291,11 @@ def run_ours(a):
         igemm_t = acc["fwd"][1] + acc["dgrad"][1]
         igemm_n = acc["fwd"][2] + acc["dgrad"][2]
         ach = igemm_f / igemm_t / 1e12
-        roof = {"bound": "tensor", "kernel": "conv_igemm_kernel (fwd + dgrad convolutions)", "achieved": ach,
-                "peak": peak_tf, "peak_source": peak_src + " bf16_tflops_sustained", "unit": "TFLOP/s", "frac": ach / peak_tf,
-                "traffic": None, "launches_per_step": igemm_n // nprof, "avg_launch_us": igemm_t / igemm_n * 1e6,
-                "ms_per_step": igemm_t / nprof * 1e3}
+        roof = {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM conv (conv_igemm_kernel + conv_patch_kernel: all fwd + dgrad launches)",
+                "achieved": ach, "peak": peak_tf, "peak_source": peak_src + " bf16_tflops_sustained", "unit": "TFLOP/s",
+                "frac": ach / peak_tf, "traffic": conv_traffic_per_launch(), "traffic_unit": "bytes/launch (dram read+write, ncu)",
+                "launches_per_step": igemm_n // nprof, "avg_launch_us": igemm_t / igemm_n * 1e6,
+                "flop_per_launch": igemm_f / igemm_n, "ms_per_step": igemm_t / nprof * 1e3}
         kern = {k: {"tflops": v[0] / v[1] / 1e12, "ms_per_step": v[1] / nprof * 1e3, "launches_per_step": v[2] // nprof}
                 for k, v in acc.items()}
         kern["whole_step_conv_tflops"] = value / world * TRAIN_GFLOP_PER_IMG * 1e9 / 1e12

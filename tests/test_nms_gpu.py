@@ -128,3 +128,21 @@ def test_nms_full_size_properties():
     # the first kept row is the global arg-max score with the lowest index
     best = bx[:, :, 1].max(dim=1).values
     assert torch.equal(rows[:, 0, 1], best)
+
+
+@gpu
+def test_decode_class_argmax_ties_and_saturation():
+    """class = argmax over sigmoid(logits), first maximum wins: duplicates, saturation to 1.0f (logits > ~17) and
+    all-equal rows must resolve exactly like torch.argmax(torch.sigmoid(.))."""
+    from yolov5m_b200.boxes import cells_to_bboxes
+    g = torch.Generator().manual_seed(5)
+    p = [torch.randn(2, 3, 8, 12, 85, generator=g) * 3 for _ in range(3)]
+    q = p[0]
+    q[0, 0, 0, 0, 5:] = 0.0                                   # all equal -> class 0
+    q[0, 0, 0, 1, 5:] = -30.0; q[0, 0, 0, 1, 5 + 17] = -2.0   # single winner far below saturation
+    q[0, 0, 0, 2, 5 + 40] = 25.0; q[0, 0, 0, 2, 5 + 7] = 19.0; q[0, 0, 0, 2, 5 + 63] = 30.0   # three saturated: first (7) wins
+    q[0, 0, 0, 3, 5 + 11] = 4.5; q[0, 0, 0, 3, 5 + 3] = 4.5   # exact duplicate maximum -> lower index
+    q[0, 0, 0, 4, 5:] = 40.0                                  # everything saturated
+    out = cells_to_bboxes([t.cuda() for t in p], model_ref.head_anchors().cuda(), [8, 16, 32], is_pred=True, to_list=False).cpu()
+    exp = torch.cat([torch.argmax(torch.sigmoid(t[..., 5:]), dim=-1).reshape(2, -1) for t in p], 1).float()
+    assert torch.equal(out[..., 0], exp)

@@ -50,14 +50,43 @@ __global__ void __launch_bounds__(256) decode_kernel(const float* __restrict__ p
       }
       continue;
     }
-    // class arg-max over sigmoid(logit): first maximum wins (torch.argmax), plot_utils.py:27
+    // class arg-max over sigmoid(logit): first maximum wins (torch.argmax), plot_utils.py:27.  sigmoid is monotonic, so
+    // only classes whose logit is within rounding reach of the largest one can hold the maximum sigmoid: find the max
+    // LOGIT first (no special-function work), then evaluate sigmoid only for those candidates (ties after rounding --
+    // close logits, or saturation to 1.0f above ~16.6 -- still resolve to the first index, bit-exactly).
+    float lv[3];
+    float lmax = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int k = lane + 32 * i;
+      lv[i] = k < nc ? ps[5 + k] : -INFINITY;
+      lmax = fmaxf(lmax, lv[i]);
+    }
+    for (int k = lane + 96; k < nc; k += 32) lmax = fmaxf(lmax, ps[5 + k]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+    const float cut = fminf(lmax, 16.0f) - 1e-3f * fmaxf(1.0f, fabsf(lmax));
     float bv = -1.f;
     int bi = 0x7fffffff;
-    for (int k = lane; k < nc; k += 32) {
-      const float s = sigmoid_t(ps[5 + k]);
-      if (s > bv) {
-        bv = s;
-        bi = k;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int k = lane + 32 * i;
+      if (k < nc && lv[i] >= cut) {
+        const float s = sigmoid_t(lv[i]);
+        if (s > bv) {
+          bv = s;
+          bi = k;
+        }
+      }
+    }
+    for (int k = lane + 96; k < nc; k += 32) {
+      const float l = ps[5 + k];
+      if (l >= cut) {
+        const float s = sigmoid_t(l);
+        if (s > bv) {
+          bv = s;
+          bi = k;
+        }
       }
     }
 #pragma unroll
@@ -70,10 +99,13 @@ __global__ void __launch_bounds__(256) decode_kernel(const float* __restrict__ p
       }
     }
     if (lane < 6) {
-      const long b = c / per_img, rem = c - b * per_img;
-      const int a = (int)(rem / ((long)H * W));
-      const long sp = rem - (long)a * H * W;
-      const int gy = (int)(sp / W), gx = (int)(sp - (long)gy * W);
+      // 32-bit index math (cells < 2^31 is checked on the host): 64-bit divisions cost more than the rest of the cell
+      const unsigned cu = (unsigned)c, hw = (unsigned)(H * W);
+      const unsigned bu = cu / (unsigned)per_img, remu = cu - bu * (unsigned)per_img;
+      const long b = bu, rem = remu;
+      const int a = (int)(remu / hw);
+      const unsigned sp = remu - (unsigned)a * hw;
+      const int gy = (int)(sp / (unsigned)W), gx = (int)(sp - (unsigned)gy * (unsigned)W);
       float v;
       if (lane == 0) {
         v = (float)bi;
@@ -353,6 +385,7 @@ int yb_decode_level(const float* p, int B, int na, int H, int W, int no, float s
   YB_REQUIRE(no >= 6 && na >= 1, "decode: no=%d na=%d", no, na);
   const long cells = (long)B * na * H * W;
   if (cells == 0) return 0;
+  YB_REQUIRE(cells < (1L << 31), "decode: %ld cells (limit 2^31)", cells);
   const int blocks = (int)std::max<long>(1, std::min<long>((cells + 7) / 8, (long)nms_sm_count() * 32));
   decode_kernel<<<blocks, 256, 0, ST(stream)>>>(p, cells, na, H, W, no, stride, anchors_px, is_pred, out, rows_per_image,
                                                 level_off);
