@@ -29,7 +29,8 @@ int yb_conv_max_partials(void);
 
 /* ---- Conv2d forward (model.py:16 CBL conv; model.py:162 head conv) ----------------
  * y[n,ho,wo,co] = epilogue( sum_{kh,kw,ci} x[n, ho*s+kh-p, wo*s+kw-p, ci] * w[co,(kh*ks+kw)*Cin+ci] )
- * ks in {1,3}, p = ks/2, s in {1,2}.  w_packed: bf16 [Cout][ks*ks*Cin].
+ * ks in {1,3}, p = ks/2, s in {1,2}; ks = 31 means a 3x1 kernel (three vertical taps, stride 1, w_packed [Cout][3*Cin]).
+ * w_packed: bf16 [Cout][ks*ks*Cin].
  * epilogue: v = acc; if scale: v = v*scale[co]+shift[co]; elif shift: v += shift[co];
  *           if act: v = SiLU(v); if addend: v += addend[n,ho,wo,co]; store.
  * out_kind 0: bf16 NHWC (y_pitch); 1: fp32 head layout (B,na,H,W,no) of model.py:173
@@ -126,7 +127,9 @@ int yb_maxpool5_fwd(const void* x, int64_t x_pitch, int N, int H, int W, int C, 
 int yb_maxpool5_bwd(const void* dy, int64_t dy_pitch, const uint8_t* argmax, int N, int H, int W, int C, void* dx,
                     int64_t dx_pitch, int accumulate, void* stream);
 /* x (N,3,H,W) NCHW, dtype 0 = float32 in [0,1], 1 = uint8 (divided by 255, training_utils.py:98)
- * -> out (N,H/2,W/2,16) bf16: space-to-depth so that the 6x6/s2 stem (model.py:184) becomes a 3x3/s1 conv */
+ * -> out (N,H/2,W/2,48) bf16: space-to-depth (12 -> 16 channels: (r*2+s)*3+c = x[c][2h+r][2w+s]) with the three horizontal
+ * taps gathered (channel kw*16+j = s2d pixel w+kw-1, zero outside), so that the 6x6/s2 stem (model.py:184) becomes a
+ * 3x1 convolution (ks code 31 of yb_conv_fwd_plan / yb_conv_wgrad_plan) with weights [Cout][3][48] = yb_repack_stem */
 int yb_prep_input(const void* x, int dtype, int N, int H, int W, void* out, void* stream);
 /* dense gradient of a head output (B,na,H,W,no) fp32 -> bf16 NHWC (B,H,W,Cpad), channel a*no+o (model.py:173 backward) */
 int yb_head_grad_pack(const float* g, int B, int na, int H, int W, int no, void* dy, int Cpad, void* stream);

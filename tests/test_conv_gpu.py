@@ -201,3 +201,21 @@ PATCH_DG = [
 @pytest.mark.parametrize("case", PATCH_DG)
 def test_conv_patch_dgrad(case, patch_mode):
     test_conv_dgrad(case)
+
+
+# ---- ks code 31: 3x1 kernel (three vertical taps, stride 1) -- the stem after horizontal tap gathering
+@pytest.mark.parametrize("N,H,W,Cin,Cout,patch", [(2, 32, 32, 48, 48, 0), (2, 32, 32, 48, 48, 2), (1, 24, 20, 48, 96, 0)])
+def test_conv_fwd_3x1(N, H, W, Cin, Cout, patch):
+    L = _lib.lib()
+    L.yb_set_conv_patch_mode(patch)
+    try:
+        g = torch.Generator().manual_seed(21)
+        x = torch.randn(N, Cin, H, W, generator=g).to(torch.bfloat16)
+        w = (torch.randn(Cout, Cin, 3, 1, generator=g) / (Cin * 3) ** 0.5).to(torch.bfloat16)
+        ref = F.conv2d(x.float(), w.float(), None, 1, (1, 0))
+        y, _, st = conv_fwd(x.permute(0, 2, 3, 1).contiguous().cuda(), pack_fwd(w.float()).cuda(), 31, 1, Cout, stats=True)
+        assert rel(y.float().cpu().permute(0, 3, 1, 2), ref) < TOL
+        m = ref.numel() // Cout
+        assert rel(st[1].cpu() / m, (ref * ref).mean((0, 2, 3))) < 1e-3
+    finally:
+        L.yb_set_conv_patch_mode(0)

@@ -165,14 +165,18 @@ def test_upsample_add_prep_pack():
         x = torch.rand(2, 3, 8, 12, generator=g)
         if dt == torch.uint8:
             x = (x * 255).to(torch.uint8)
-        out = torch.zeros(2, 4, 6, 16, device="cuda", dtype=torch.bfloat16)
+        out = torch.full((2, 4, 6, 48), 9.0, device="cuda", dtype=torch.bfloat16)
         _lib.check(L.yb_prep_input(_lib.ptr(x.cuda()), 0 if dt == torch.float32 else 1, 2, 8, 12, _lib.ptr(out), _lib.stream()))
         xf = x.float() / 255 if dt == torch.uint8 else x
-        want = torch.zeros(2, 4, 6, 16)
+        s2d = torch.zeros(2, 4, 6, 16)
         for r in range(2):
             for s_ in range(2):
                 for c in range(3):
-                    want[..., (r * 2 + s_) * 3 + c] = xf[:, c, r::2, s_::2]
+                    s2d[..., (r * 2 + s_) * 3 + c] = xf[:, c, r::2, s_::2]
+        want = torch.zeros(2, 4, 6, 48)            # channel kw*16+j = s2d[w + kw - 1][j], zero outside the image
+        want[..., 16:32] = s2d
+        want[:, :, 1:, 0:16] = s2d[:, :, :-1]
+        want[:, :, :-1, 32:48] = s2d[:, :, 1:]
         assert torch.equal(out.float().cpu(), want.to(torch.bfloat16).float())
     # dense head gradient repack
     gh = torch.randn(2, 3, 4, 6, 85, generator=g)

@@ -100,3 +100,21 @@ def test_conv_wgrad_patch(case, wpatch_mode):
 
 def test_wgrad_patch_index_map_and_pitch(wpatch_mode):
     test_wgrad_index_map_and_pitch()
+
+
+def test_conv_wgrad_3x1():
+    """ks code 31: 3x1 kernel (stem after horizontal tap gathering): dw [Cout][3][Cin]."""
+    N, H, W, Cin, Cout = 2, 32, 32, 48, 48
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(N, Cin, H, W, generator=g).to(torch.bfloat16)
+    dy = torch.randn(N, Cout, H, W, generator=g).to(torch.bfloat16)
+    ref = torch.nn.grad.conv2d_weight(x.float(), (Cout, Cin, 3, 1), dy.float(), 1, (1, 0))
+    L = _lib.lib()
+    xd = x.permute(0, 2, 3, 1).contiguous().cuda()
+    dyd = dy.permute(0, 2, 3, 1).contiguous().cuda()
+    ws = torch.empty(4 << 20, device="cuda", dtype=torch.float32)
+    dw = torch.zeros(Cout, 3, Cin, device="cuda", dtype=torch.float32)
+    _lib.check(L.yb_conv2d_wgrad(_lib.ptr(xd), N, H, W, Cin, _lib.c_i64(Cin), _lib.ptr(dyd), Cout, _lib.c_i64(Cout), 31, 1,
+                                 _lib.ptr(ws), _lib.c_i64(ws.numel()), 0, _lib.ptr(dw), Cout, None, 0, _lib.stream()))
+    torch.cuda.synchronize()
+    assert rel(dw.cpu().view(Cout, 3, 1, Cin).permute(0, 3, 1, 2), ref) < TOL

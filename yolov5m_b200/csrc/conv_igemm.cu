@@ -343,7 +343,10 @@ int conv_plan_fwd(ConvPlan& pl, const TView& in, const bf16* wp, int ks, int str
     pl.kind = 0;
   }
   ConvKParams& kp = pl.kp;
-  YB_REQUIRE((ks == 1 || ks == 3) && (stride == 1 || stride == 2), "conv fwd: ks=%d stride=%d unsupported", ks, stride);
+  // ks = 31: three vertical taps (a 3 x 1 kernel, stride 1) -- the stem after horizontal tap gathering (yb_prep_input)
+  YB_REQUIRE(((ks == 1 || ks == 3) && (stride == 1 || stride == 2)) || (ks == 31 && stride == 1),
+             "conv fwd: ks=%d stride=%d unsupported", ks, stride);
+  const int ksh = ks == 31 ? 3 : ks, ksw = ks == 31 ? 1 : ks;
   YB_REQUIRE(in.C % 16 == 0 && in.pitch % 8 == 0 && (ep.out_kind != OUT_BF16 || out.pitch % 8 == 0),
              "conv fwd: channel alignment");
   YB_REQUIRE(in.H % stride == 0 && in.W % stride == 0, "conv fwd: odd input for stride 2");
@@ -359,9 +362,9 @@ int conv_plan_fwd(ConvPlan& pl, const TView& in, const bf16* wp, int ks, int str
   if (stride == 1) {
     if (make_a_map(&kp.tmA[0], in, kp.KC, kp.PW, kp.PH, kp.PN, 0, 0, 1, 1)) return -1;
     for (int i = 1; i < 4; ++i) kp.tmA[i] = kp.tmA[0];
-    for (int kh = 0; kh < ks; ++kh)
-      for (int kw = 0; kw < ks; ++kw) {
-        kp.taps[nt] = ConvTap{0, (int8_t)(kw - pad), (int8_t)(kh - pad), 0, (int32_t)((kh * ks + kw) * in.C)};
+    for (int kh = 0; kh < ksh; ++kh)
+      for (int kw = 0; kw < ksw; ++kw) {
+        kp.taps[nt] = ConvTap{0, (int8_t)(kw - ksw / 2), (int8_t)(kh - ksh / 2), 0, (int32_t)((kh * ksw + kw) * in.C)};
         ++nt;
       }
   } else {
@@ -388,7 +391,7 @@ int conv_plan_fwd(ConvPlan& pl, const TView& in, const bf16* wp, int ks, int str
     kp.as_h = (int64_t)ep.addend_pitch * out.W;
     kp.as_w = ep.addend_pitch;
   }
-  return finish_plan(pl, wp, out.C, (long)ks * ks * in.C, out, ep);
+  return finish_plan(pl, wp, out.C, (long)ksh * ksw * in.C, out, ep);
 }
 
 int conv_plan_dgrad(ConvPlan& pl, const TView& dy, const bf16* wt, int ks, int stride, const TView& dx,

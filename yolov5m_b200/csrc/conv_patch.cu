@@ -413,8 +413,8 @@ static void set_out_strides(PatchKParams& kp, const TView& o, int step, const Co
 
 int conv_patch_plan_fwd(ConvPlan& pl, const TView& in, const bf16* wp, int ks, int stride, const TView& out,
                         const ConvEpilogue& ep) {
-  if ((ks != 3 && ks != 1) || (stride != 1 && stride != 2) || ep.out_kind != OUT_BF16) return 1;
-  if (ks == 1 && stride != 1) return 1;
+  if ((ks != 3 && ks != 1 && ks != 31) || (stride != 1 && stride != 2) || ep.out_kind != OUT_BF16) return 1;
+  if (ks != 3 && stride != 1) return 1;
   if (in.C % 8 || in.pitch % 8 || out.pitch % 8 || out.C % 16) return 1;
   if (in.H % stride || in.W % stride || out.H != in.H / stride || out.W != in.W / stride || out.N != in.N) return 1;
   if (!patch_eligible(out.W, out.H)) return 1;
@@ -424,10 +424,11 @@ int conv_patch_plan_fwd(ConvPlan& pl, const TView& in, const bf16* wp, int ks, i
   kp.H = out.H;
   kp.NB = out.N;
   kp.ngroups = 1;
-  if (finish_patch_plan(pl, wp, out.C, (long)ks * ks * in.C, in.C, out, ep, 0, 0)) return -1;
+  const int ntap_total = ks == 31 ? 3 : ks * ks;
+  if (finish_patch_plan(pl, wp, out.C, (long)ntap_total * in.C, in.C, out, ep, 0, 0)) return -1;
   const size_t stats_bytes = ep.stats ? (size_t)4 * 2 * out.C * sizeof(float) : 0;
   const int halo = ks == 1 ? 0 : (stride == 1 ? 2 : 1);
-  if (!choose_supertile(kp, out.W, out.H, out.N, 1, halo, halo, stats_bytes)) return 1;
+  if (!choose_supertile(kp, out.W, out.H, out.N, 1, ks == 31 ? 0 : halo, halo, stats_bytes)) return 1;
   const int SW = 8 * kp.TW, SH = 16 * kp.TH;
   int nt = 0, np = 0;
   if (ks == 1) {
@@ -442,6 +443,19 @@ int conv_patch_plan_fwd(ConvPlan& pl, const TView& in, const bf16* wp, int ks, i
     if (make_patch_map(&kp.tmA[0], in, SW, SH, 0, 0, 1, 1)) return -1;
     for (int i = 1; i < 4; ++i) kp.tmA[i] = kp.tmA[0];
     kp.taps[nt++] = PTap{0, 0};
+    pa.tap_end = nt;
+  } else if (ks == 31) {
+    // 3 x 1: vertical halo only; tap kh starts kh patch rows down
+    PPatch& pa = kp.patches[np++];
+    pa.map = 0;
+    pa.ox = 0;
+    pa.oy = -1;
+    pa.pitch = SW;
+    pa.bytes = (uint32_t)SW * (SH + 2) * 128u;
+    pa.tap_begin = 0;
+    if (make_patch_map(&kp.tmA[0], in, SW, SH + 2, 0, 0, 1, 1)) return -1;
+    for (int i = 1; i < 4; ++i) kp.tmA[i] = kp.tmA[0];
+    for (int kh = 0; kh < 3; ++kh) kp.taps[nt++] = PTap{kh * pa.pitch, kh * in.C};
     pa.tap_end = nt;
   } else if (stride == 1) {
     PPatch& pa = kp.patches[np++];

@@ -307,7 +307,7 @@ size_t wgrad_min_workspace_floats(int Cin, int Cout, int ks) {
   int n_tiles;
   const int bn = pick_block_n(Cout, n_tiles);
   const size_t cin_pad = (size_t)(Cin + kBoxC - 1) / kBoxC * kBoxC;
-  return (size_t)ks * ks * cin_pad * n_tiles * bn;
+  return (size_t)(ks == 31 ? 3 : ks * ks) * cin_pad * n_tiles * bn;
 }
 
 int wgrad_plan(WgradPlan& pl, const TView& x, const TView& dy, int ks, int stride, float* partial, size_t partial_floats,
@@ -319,14 +319,16 @@ int wgrad_plan(WgradPlan& pl, const TView& x, const TView& dy, int ks, int strid
     pl.kind = 0;
   }
   WgradKParams& kp = pl.kp;
-  YB_REQUIRE((ks == 1 || ks == 3) && (stride == 1 || stride == 2), "wgrad: ks=%d stride=%d unsupported", ks, stride);
+  YB_REQUIRE(((ks == 1 || ks == 3) && (stride == 1 || stride == 2)) || (ks == 31 && stride == 1),
+             "wgrad: ks=%d stride=%d unsupported", ks, stride);
+  const int ksh = ks == 31 ? 3 : ks, ksw = ks == 31 ? 1 : ks;
   YB_REQUIRE(x.C % 8 == 0 && dy.C % 8 == 0 && x.pitch % 8 == 0 && dy.pitch % 8 == 0, "wgrad: channel alignment");
   YB_REQUIRE(dy.H == x.H / stride && dy.W == x.W / stride && dy.N == x.N, "wgrad: geometry");
   YB_REQUIRE((reinterpret_cast<uintptr_t>(partial) & 31) == 0, "wgrad: workspace must be 32-byte aligned");
   YB_REQUIRE(x.H % stride == 0 && x.W % stride == 0, "wgrad: odd input for stride 2");
   kp.Cout = dy.C;
   kp.Cin = x.C;
-  kp.ntaps = ks * ks;
+  kp.ntaps = ksh * ksw;
   kp.cboxes = (x.C + kBoxC - 1) / kBoxC;
   kp.Cin_pad = kp.cboxes * kBoxC;
   kp.boxes_total = kp.ntaps * kp.cboxes;
@@ -382,9 +384,9 @@ int wgrad_plan(WgradPlan& pl, const TView& x, const TView& dy, int ks, int strid
   if (stride == 1) {
     if (make_map(&kp.tmX[0], x, kp.PW, kp.PH, kp.PN, 0, 0, 1, 1)) return -1;
     for (int i = 1; i < 4; ++i) kp.tmX[i] = kp.tmX[0];
-    for (int kh = 0; kh < ks; ++kh)
-      for (int kw = 0; kw < ks; ++kw) {
-        kp.taps[nt] = ConvTap{0, (int8_t)(kw - pad), (int8_t)(kh - pad), 0, (int32_t)((kh * ks + kw) * x.C)};
+    for (int kh = 0; kh < ksh; ++kh)
+      for (int kw = 0; kw < ksw; ++kw) {
+        kp.taps[nt] = ConvTap{0, (int8_t)(kw - ksw / 2), (int8_t)(kh - ksh / 2), 0, (int32_t)((kh * ksw + kw) * x.C)};
         ++nt;
       }
   } else {

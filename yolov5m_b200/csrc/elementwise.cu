@@ -553,7 +553,11 @@ __global__ void maxpool5_bwd_kernel(const bf16* __restrict__ dy, long dy_pitch, 
 }
 
 // ------------------------------------------------------------------------------------------------ input staging
-// x (N,3,H,W) float in [0,1] (or uint8, divided by 255) -> out (N,H/2,W/2,16) bf16 with channel (r*2+s)*3+c = x[c][2h+r][2w+s]
+// x (N,3,H,W) float in [0,1] (or uint8, divided by 255) -> out (N,H/2,W/2,48) bf16:
+//   space-to-depth: s2d[ho][wo][(r*2+s)*3+c] = x[c][2ho+r][2wo+s] (12 channels, padded to 16), then the three horizontal taps
+//   of the stem gathered:  out[ho][wo][kw*16 + j] = s2d[ho][wo+kw-1][j]  (zero outside the image).
+// The 6x6/s2 stem (model.py:184) = 3x3/s1 over s2d = THREE vertical taps over `out` with K = 48 per tap: a third of the
+// TMA boxes / MMA steps of the nine-tap form, and full-width pipeline stages instead of 32-byte rows.
 template <typename T>
 __global__ void prep_input_kernel(const T* __restrict__ x, int N, int H, int W, bf16* __restrict__ out) {
   const int Ho = H >> 1, Wo = W >> 1;
@@ -583,14 +587,30 @@ __global__ void prep_input_kernel(const T* __restrict__ x, int N, int H, int W, 
         v[(r * 2 + 0) * 3 + c] = a;
         v[(r * 2 + 1) * 3 + c] = b;
       }
-    V8 lo, hi;
+    V8 lo, hi, z;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       lo.v[j] = v[j];
       hi.v[j] = v[8 + j];
+      z.v[j] = 0.f;
     }
-    st8(out + i * 16, lo);
-    st8(out + i * 16 + 8, hi);
+    bf16* me = out + i * 48;
+    st8(me + 16, lo);  // centre tap of this pixel
+    st8(me + 24, hi);
+    if (wo + 1 < Wo) {  // left tap (kw = 0) of the right neighbour
+      st8(me + 48, lo);
+      st8(me + 56, hi);
+    } else {            // last column: its right tap is outside the image
+      st8(me + 32, z);
+      st8(me + 40, z);
+    }
+    if (wo > 0) {       // right tap (kw = 2) of the left neighbour
+      st8(me - 48 + 32, lo);
+      st8(me - 48 + 40, hi);
+    } else {            // first column: its left tap is outside the image
+      st8(me, z);
+      st8(me + 8, z);
+    }
   }
 }
 

@@ -239,7 +239,7 @@ class _Engine:
         w_ptr = net._wstem.data_ptr() if r.is_stem else net._wfwd.data_ptr() + 2 * r.w_off
         gam, bet = net._pflat.data_ptr() + 4 * r.g_off, net._pflat.data_ptr() + 4 * r.b_off
         rm, rv, nbt = r.rm.data_ptr(), r.rv.data_ptr(), r.nbt.data_ptr()
-        k, s = (3, 1) if r.is_stem else (r.k, r.stride)
+        k, s = (31, 1) if r.is_stem else (r.k, r.stride)  # stem: 3x1 over the tap-gathered staging (yb_prep_input)
         if not self.train:
             # eval: BN folded into the conv epilogue (running statistics), SiLU + residual in registers
             plan = _lib.checkp(L.yb_conv_fwd_plan(xin.ptr, xin.N, xin.H, xin.W, xin.C, xin.pitch, w_ptr, C, k, s, out.ptr,
@@ -335,7 +335,7 @@ class _Engine:
         bb, nk = net.backbone, net.neck
         c = net._first_out
         self.outs, self.head_dy = [], []
-        self.x16 = self.buf(B, H // 2, W // 2, 16, grad=False)
+        self.x16 = self.buf(B, H // 2, W // 2, 48, grad=False)  # stem staging: space-to-depth + gathered horizontal taps
         b0 = self.buf(B, H // 2, W // 2, c); self.cbl(bb[0], self.x16.v(), b0.v())
         b1 = self.buf(B, H // 4, W // 4, 2 * c); self.cbl(bb[1], b0.v(), b1.v())
         b2 = self.buf(B, H // 4, W // 4, 2 * c); self.c3(bb[2], b1.v(), b2.v())
@@ -438,7 +438,7 @@ class _Engine:
                 if not r.is_stem:
                     self.conv_flops["dgrad"] += flops
                 C, npix = r.cout, y.npix
-                k, s = (3, 1) if r.is_stem else (r.k, r.stride)
+                k, s = (31, 1) if r.is_stem else (r.k, r.stride)
                 self._flush_pending(out)
                 assert self._contrib_state(out), f"{r.name}: output gradient never produced"
                 if up is not None:
