@@ -47,11 +47,12 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const __grid_constant__ P
     mbar_init(mbar, 1);
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc(tmem_slot, 64);
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base2 = tmem_base;
   if (threadIdx.x == 0) {
     mbar_expect_tx(bar, 288 * 128 + 64 * 128);
     tma_load_2d(&p.tmA, bar, a_smem, 0, 0);
@@ -114,7 +115,30 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const __grid_constant__ P
     if (threadIdx.x == 0) p.cycles[v] = clock64() - t0;
     __syncthreads();
   }
-  if (warp == 0) tmem_dealloc(tmem_base, 64);
+  // ---- timing 2: accumulator placement.  N = 96 / 48, `nacc` accumulators `stride` columns apart, 4 MMAs (K = 64) per
+  //      accumulator visit, round robin -- the issue pattern of the multi-tile conv kernels
+  for (int v = 0; v < 8; ++v) {
+    const int N = v < 4 ? 96 : 48;
+    const int nacc = (v & 3) == 0 ? 1 : (v < 4 ? 2 : 4);
+    const int stride = (v & 3) == 1 ? N : ((v & 3) == 2 ? 128 : ((v & 3) == 3 ? 64 : 0));
+    long long t0 = 0;
+    if (threadIdx.x == 0) {
+      const uint32_t a0 = smem_u32(a_smem), b0 = smem_u32(b_smem);
+      const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+      t0 = clock64();
+      for (int i = 0; i < 128; ++i) {
+        const uint32_t d = tmem_base2 + (uint32_t)((i % nacc) * stride);
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(d, make_smem_desc(a0 + k * 32, 16, 1024, 2), make_smem_desc(b0 + k * 32, 16, 1024, 2), idesc, 1);
+      }
+      umma_commit(mbar);
+    }
+    mbar_wait(mbar, mph);
+    mph ^= 1;
+    if (threadIdx.x == 0) p.cycles[8 + v] = clock64() - t0;
+    __syncthreads();
+  }
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
 static float aval(int r, int c) { return (float)(((r * 7 + c * 3) % 23) - 11); }
@@ -146,7 +170,7 @@ int main() {
   }
   p.out = dO;
   long long* dC;
-  cudaMalloc(&dC, 8 * sizeof(long long));
+  cudaMalloc(&dC, 16 * sizeof(long long));
   p.cycles = dC;
   cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   probe_kernel<<<1, 128, 64 * 1024>>>(p);
@@ -179,10 +203,14 @@ int main() {
       }
       printf("\n");
     }
-  long long hC[8];
+  long long hC[16];
   cudaMemcpy(hC, dC, sizeof(hC), cudaMemcpyDeviceToHost);
   const int sbos[4] = {1024, 1280, 2048, 2304};
   for (int v = 0; v < 8; ++v)
     printf("timing: start row %d, SBO %4d : %.1f cycles per MMA (M=128 N=64 K=16; ideal 32)\n", v & 1, sbos[v >> 1], hC[v] / 512.0);
+  const char* an[8] = {"N=96 one accumulator", "N=96 two accumulators 96 columns apart", "N=96 two accumulators 128 apart",
+                       "N=96 two accumulators 64 apart (overlapping, timing only)", "N=48 one accumulator",
+                       "N=48 four accumulators 48 apart", "N=48 four accumulators 128 apart", "N=48 four accumulators 64 apart"};
+  for (int v = 0; v < 8; ++v) printf("timing2: %-58s : %.1f cycles per MMA\n", an[v], hC[8 + v] / 512.0);
   return 0;
 }

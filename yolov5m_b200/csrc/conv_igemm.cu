@@ -136,7 +136,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       uint32_t a_step = p.a_stage_bytes >> 4, b_step = p.b_stage_bytes >> 4;
       const TileDec td = load_tile_dec(p);
       int chunks = p.chunks, stages = p.stages;
-      keep_in_reg(a_step); keep_in_reg(b_step); keep_in_reg(chunks); keep_in_reg(stages);
+      int klast = (p.Ck - (p.chunks - 1) * p.KC + 15) / 16;
+      keep_in_reg(a_step); keep_in_reg(b_step); keep_in_reg(chunks); keep_in_reg(stages); keep_in_reg(klast);
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
@@ -150,11 +151,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + ab * 256;
         uint32_t acc = 0;
+        int chk = 0;
         for (int ks = 0; ks < nk; ++ks) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint64_t da = a_desc0 + (uint64_t)(s * a_step), db = b_desc0 + (uint64_t)(s * b_step);
-          if (kinner == 4) {
+          const bool last_chunk = ++chk == chunks;  // the zero-padded tail of the last channel chunk needs no MMAs
+          if (last_chunk) chk = 0;
+          if (last_chunk && klast != kinner) {
+            for (int k = 0; k < klast; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, k ? 1u : acc);
+          } else if (kinner == 4) {
             umma_bf16(d_tmem, da, db, idesc, acc);
             umma_bf16(d_tmem, da + 2, db + 2, idesc, 1u);
             umma_bf16(d_tmem, da + 4, db + 4, idesc, 1u);
@@ -353,6 +359,7 @@ int conv_plan_fwd(ConvPlan& pl, const TView& in, const bf16* wp, int ks, int str
   YB_REQUIRE(out.H == in.H / stride && out.W == in.W / stride && out.N == in.N, "conv fwd: geometry");
   kp.KC = pick_kc(in.C);
   kp.chunks = (in.C + kp.KC - 1) / kp.KC;
+  kp.Ck = in.C;
   kp.W = out.W;
   kp.H = out.H;
   kp.NB = out.N;
@@ -409,6 +416,7 @@ int conv_plan_dgrad(ConvPlan& pl, const TView& dy, const bf16* wt, int ks, int s
   YB_REQUIRE(dy.H == dx.H / stride && dy.W == dx.W / stride && dy.N == dx.N, "conv dgrad: geometry");
   kp.KC = pick_kc(dy.C);
   kp.chunks = (dy.C + kp.KC - 1) / kp.KC;
+  kp.Ck = dy.C;
   kp.NB = dx.N;
   const int pad = ks / 2;
   int nt = 0;

@@ -39,6 +39,7 @@ struct ConvKParams {
   ConvGroup groups[4];
   int32_t ngroups;
   int32_t chunks, KC;        // channel chunks per tap, channels per chunk (16/32/64)
+  int32_t Ck;                // true channels per tap: the last chunk issues only ceil((Ck - (chunks-1)*KC) / 16) MMAs
   int32_t PW, PH, PN;        // output-pixel patch of one 128-row tile
   int32_t tiles_w, tiles_h, tiles_n, tiles_c;
   int32_t W, H, NB;          // output pixel grid (per group)
@@ -79,6 +80,7 @@ struct PatchKParams {
   ConvGroup groups[4];  // tap_begin/tap_end index PATCHES here
   int32_t ngroups;
   int32_t chunks;            // 64-channel K chunks (the last one zero-padded by TMA OOB fill)
+  int32_t Ck;                // true channels per tap: the last chunk issues only ceil((Ck - 64*(chunks-1)) / 16) MMAs
   int32_t TH, TW;            // 128-pixel tiles (16 rows x 8 cols) per super-tile, vertically / horizontally
   int32_t tiles_w, tiles_h, tiles_c;  // super-tiles per image row / column, N tiles
   int32_t W, H, NB;          // output pixel grid (per group)

@@ -172,8 +172,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
       const uint32_t a_base16 = smem_u32(a_smem) >> 4;
       const STileDec td = load_stile_dec(p);
       int BN = p.BLOCK_N, chunks = p.chunks, nsa = p.sa, nsb = p.sb, TWl = p.TW;
+      int klast = (p.Ck - (p.chunks - 1) * 64 + 15) / 16;
       keep_in_reg(a_step); keep_in_reg(b_step); keep_in_reg(BN); keep_in_reg(chunks); keep_in_reg(nsa); keep_in_reg(nsb);
-      keep_in_reg(TWl);
+      keep_in_reg(TWl); keep_in_reg(klast);
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
       int it = 0;
@@ -199,6 +200,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
           for (int ch = 0; ch < chunks; ++ch) {
             mbar_wait(&afull[sa], pha);
             tc_fence_after();
+            const int nk = ch + 1 == chunks ? klast : 4;
             const uint64_t a_desc = a_hi | (uint64_t)(a_base16 + sa * a_step);
             for (int tp = pa.tap_begin; tp < pa.tap_end; ++tp) {
               const uint64_t a_tap = a_desc + (uint64_t)((uint32_t)s_taps[tp].row_off * 8u);
@@ -211,9 +213,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
                 const uint64_t da = a_tap + tile_off[tt];
                 const uint32_t d_tmem = d_base + (uint32_t)tt * BN;
                 umma_bf16(d_tmem, da, db, idesc, acc);
-                umma_bf16(d_tmem, da + 2, db + 2, idesc, 1u);
-                umma_bf16(d_tmem, da + 4, db + 4, idesc, 1u);
-                umma_bf16(d_tmem, da + 6, db + 6, idesc, 1u);
+                if (nk > 1) umma_bf16(d_tmem, da + 2, db + 2, idesc, 1u);  // nk < 4: zero-padded tail of the last chunk
+                if (nk > 2) umma_bf16(d_tmem, da + 4, db + 4, idesc, 1u);
+                if (nk > 3) umma_bf16(d_tmem, da + 6, db + 6, idesc, 1u);
               }
               acc = 1u;
               umma_commit(&bempty[sb]);
@@ -328,6 +330,7 @@ static int finish_patch_plan(ConvPlan& pl, const bf16* wmat, int wrows, long wco
   kp.BLOCK_N = pick_block_n(wrows);
   kp.tiles_c = (wrows + kp.BLOCK_N - 1) / kp.BLOCK_N;
   kp.chunks = (Kc + 63) / 64;
+  kp.Ck = Kc;
   {
     uint64_t dims[2] = {(uint64_t)wcols, (uint64_t)wrows};
     uint64_t strides[1] = {(uint64_t)wcols * 2};
