@@ -36,6 +36,33 @@ void note_launch();
     }                                         \
   } while (0)
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// Hot kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel of the stream may be
+// scheduled (and run its prologue: barrier init, TMEM allocation, descriptor prefetch) while this one drains.  Every such
+// kernel calls pdl_launch_dependents() first and pdl_wait() before it touches global memory; pdl_wait() returns only when
+// the preceding kernels have completed and their writes are visible, so the data dependences of plain stream order hold.
+// $YB_PDL=0 falls back to plain launches.
+bool pdl_enabled();
+#if defined(__CUDACC__)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // ---------------------------------------------------------------- small device utils
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -90,6 +90,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();  // PDL: let the next kernel of the stream start its prologue ...
+  pdl_wait();               // ... and do not touch global memory before the preceding kernels have completed
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -483,7 +485,7 @@ int conv_run(const ConvPlan& pl, cudaStream_t st) {
     YB_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  conv_igemm_kernel<<<pl.grid, kThreads, pl.smem, st>>>(pl.kp);
+  YB_CHECK_CUDA(launch_pdl(conv_igemm_kernel, dim3(pl.grid), dim3(kThreads), pl.smem, st, pl.kp));
   YB_LAUNCHED();
   return 0;
 }

@@ -104,6 +104,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();  // PDL: let the next kernel of the stream start its prologue ...
+  pdl_wait();               // ... and do not touch global memory before the preceding kernels have completed
 
   if (warp == 0) {
     // ------------------------------------------------------------------ patch producer
@@ -597,7 +599,7 @@ int conv_patch_run(const ConvPlan& pl, cudaStream_t st) {
     YB_CHECK_CUDA(cudaFuncSetAttribute(conv_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  conv_patch_kernel<<<pl.grid, kThreads, pl.smem, st>>>(pl.pp);
+  YB_CHECK_CUDA(launch_pdl(conv_patch_kernel, dim3(pl.grid), dim3(kThreads), pl.smem, st, pl.pp));
   YB_LAUNCHED();
   return 0;
 }

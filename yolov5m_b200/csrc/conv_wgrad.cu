@@ -77,6 +77,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();  // PDL: let the next kernel of the stream start its prologue ...
+  pdl_wait();               // ... and do not touch global memory before the preceding kernels have completed
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -225,6 +227,8 @@ __global__ void __launch_bounds__(1024) wgrad_reduce_kernel(const float* __restr
                                     int Cin_pad, int ldo, int out_rows, int SL, float* __restrict__ out,
                                     const int* __restrict__ map, int accumulate) {
   __shared__ float red[32][33];
+  pdl_launch_dependents();  // PDL: let the next kernel of the stream start its prologue ...
+  pdl_wait();               // ... and do not touch global memory before the preceding kernels have completed
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int KR = 32 / SL;
   const int kk = ty / SL, sl = ty - kk * SL;
@@ -450,7 +454,7 @@ int wgrad_run(const WgradPlan& pl, float* out, int out_rows, const int* map, int
   if (pl.kind == 1) {
     if (wgrad_patch_launch(pl, st)) return -2;
   } else {
-    conv_wgrad_kernel<<<pl.grid, kThreads, pl.smem, st>>>(pl.kp);
+    YB_CHECK_CUDA(launch_pdl(conv_wgrad_kernel, dim3(pl.grid), dim3(kThreads), pl.smem, st, pl.kp));
     YB_LAUNCHED();
   }
   const WgradKParams& kp = pl.kp;  // the patch planner fills the reduce-relevant fields of kp as well
@@ -459,8 +463,8 @@ int wgrad_run(const WgradPlan& pl, float* out, int out_rows, const int* map, int
   while (SL < 32 && SL * 2 <= kp.splits && (long)kp.ldo * out_rows * SL < 148L * 2048) SL *= 2;
   const int KR = 32 / SL;
   dim3 grid((kp.ldo + KR - 1) / KR, (out_rows + 31) / 32);
-  wgrad_reduce_kernel<<<grid, 1024, 0, st>>>(kp.partial, kp.splits, kp.Mpad, kp.Npad, kp.Cin, kp.Cin_pad, kp.ldo, out_rows,
-                                              SL, out, map, accumulate);
+  YB_CHECK_CUDA(launch_pdl(wgrad_reduce_kernel, dim3(grid), dim3(1024), 0, st, kp.partial, kp.splits, kp.Mpad, kp.Npad, kp.Cin, kp.Cin_pad, kp.ldo, out_rows,
+                                              SL, out, map, accumulate));
   YB_LAUNCHED();
   return 0;
 }

@@ -135,6 +135,8 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restri
                                    float momentum, float* running_mean, float* running_var, long long* nbt,
                                    float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
                                    float* __restrict__ invstd_out, int training) {
+  pdl_launch_dependents();  // PDL: let the next kernel of the stream start its prologue ...
+  pdl_wait();               // ... and do not touch global memory before the preceding kernels have completed
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   const bool cvalid = c < C;
   if (blockIdx.x == 0 && threadIdx.x == 0 && training && nbt != nullptr) *nbt += 1;
@@ -178,6 +180,8 @@ __global__ void __launch_bounds__(kEwThreads) bn_act_fwd_kernel(const bf16* __re
                                   const float* __restrict__ scale, const float* __restrict__ shift,
                                   const bf16* __restrict__ res, long res_pitch, bf16* __restrict__ out, long out_pitch,
                                   bf16* __restrict__ out_up, long up_pitch) {
+  pdl_launch_dependents();  // PDL: let the next kernel of the stream start its prologue ...
+  pdl_wait();               // ... and do not touch global memory before the preceding kernels have completed
   const unsigned cv = C >> 3;
   auto finish = [&](long pix, unsigned c, V8 v, const V8& sc, const V8& sh, const uint4* rraw) {
 #pragma unroll
@@ -313,6 +317,8 @@ __global__ void __launch_bounds__(256, 2) bn_act_bwd_reduce_kernel(const bf16* _
                                          const float* __restrict__ shift, const float* __restrict__ mean,
                                          const float* __restrict__ invstd, float* __restrict__ partial, int rows_pb,
                                          int mode) {
+  pdl_launch_dependents();  // PDL: let the next kernel of the stream start its prologue ...
+  pdl_wait();               // ... and do not touch global memory before the preceding kernels have completed
   extern __shared__ float sred[];  // [rows_pb][2][C]
   const int cv = C >> 3;
   const int tid = threadIdx.x;
@@ -381,6 +387,8 @@ __global__ void __launch_bounds__(256, 2) bn_act_bwd_reduce_kernel(const bf16* _
 __global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __restrict__ partial, int rows, int C, double count,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef,
                                        int accumulate) {
+  pdl_launch_dependents();  // PDL: let the next kernel of the stream start its prologue ...
+  pdl_wait();               // ... and do not touch global memory before the preceding kernels have completed
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   const bool cvalid = c < C;
   double s, q;
@@ -401,6 +409,8 @@ __global__ void __launch_bounds__(kEwThreads) bn_act_bwd_apply_kernel(const bf16
                                         const float* __restrict__ shift, const float* __restrict__ mean,
                                         const float* __restrict__ invstd, const float* __restrict__ coef,
                                         bf16* __restrict__ dy, long dy_pitch) {
+  pdl_launch_dependents();  // PDL: let the next kernel of the stream start its prologue ...
+  pdl_wait();               // ... and do not touch global memory before the preceding kernels have completed
   const unsigned cv = C >> 3;
   // dy = scale * (dz - coef0 - xhat * coef1),  xhat = (y - mean) * invstd   ==>   dy = scale * dz + (y * m1 + m0)
   struct Par {
@@ -654,10 +664,10 @@ int yb_bn_finalize(const float* stats, int rows, int C, double count, const floa
                    float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked, float* scale,
                    float* shift, float* mean, float* invstd, int training, void* stream) {
   YB_REQUIRE(training ? (stats != nullptr && rows > 0) : (running_mean && running_var), "bn_finalize: missing inputs");
-  bn_finalize_kernel<<<(C + 31) / 32, 1024, 0, ST(stream)>>>(stats, rows, C, count, gamma, beta, eps, momentum,
+  YB_CHECK_CUDA(launch_pdl(bn_finalize_kernel, dim3((C + 31) / 32), dim3(1024), 0, ST(stream), stats, rows, C, count, gamma, beta, eps, momentum,
                                                                running_mean, running_var,
                                                                reinterpret_cast<long long*>(num_batches_tracked), scale,
-                                                               shift, mean, invstd, training);
+                                                               shift, mean, invstd, training));
   LAUNCH_OK();
   return 0;
 }
@@ -671,11 +681,11 @@ int yb_bn_act_fwd(const void* y, int64_t y_pitch, int N, int H, int W, int C, co
   static const int occ_grid = ew_wave_grid(bn_act_fwd_kernel<true>, kEwThreads, 1L << 40);
   const int grid = std::min(occ_grid, ew_blocks(npix * (C / 8), kEwThreads, 64));
   if (kEwThreads % (C / 8) == 0)
-    bn_act_fwd_kernel<true><<<grid, kEwThreads, 0, ST(stream)>>>(CB16(y), y_pitch, H, W, C, npix, scale, shift, CB16(res),
-                                                                 res_pitch, B16(out), out_pitch, B16(out_up), up_pitch);
+    YB_CHECK_CUDA(launch_pdl(bn_act_fwd_kernel<true>, dim3(grid), dim3(kEwThreads), 0, ST(stream), CB16(y), y_pitch, H, W, C, npix, scale, shift, CB16(res),
+                                                                 res_pitch, B16(out), out_pitch, B16(out_up), up_pitch));
   else
-    bn_act_fwd_kernel<false><<<grid, kEwThreads, 0, ST(stream)>>>(CB16(y), y_pitch, H, W, C, npix, scale, shift, CB16(res),
-                                                                  res_pitch, B16(out), out_pitch, B16(out_up), up_pitch);
+    YB_CHECK_CUDA(launch_pdl(bn_act_fwd_kernel<false>, dim3(grid), dim3(kEwThreads), 0, ST(stream), CB16(y), y_pitch, H, W, C, npix, scale, shift, CB16(res),
+                                                                  res_pitch, B16(out), out_pitch, B16(out_up), up_pitch));
   LAUNCH_OK();
   return 0;
 }
@@ -736,8 +746,8 @@ int yb_bn_act_bwd_reduce(const void* da, int64_t da_pitch, const void* y, int64_
     YB_CHECK_CUDA(cudaFuncSetAttribute(bn_act_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr = true;
   }
-  bn_act_bwd_reduce_kernel<<<grid, threads, smem, ST(stream)>>>(CB16(da), da_pitch, CB16(y), y_pitch, npix, C, scale,
-                                                                shift, mean, invstd, partial, rows_pb, 0);
+  YB_CHECK_CUDA(launch_pdl(bn_act_bwd_reduce_kernel, dim3(grid), dim3(threads), smem, ST(stream), CB16(da), da_pitch, CB16(y), y_pitch, npix, C, scale,
+                                                                shift, mean, invstd, partial, rows_pb, 0));
   LAUNCH_OK();
   if (rows) *rows = grid;
   return 0;
@@ -752,8 +762,8 @@ int yb_colsum(const void* x, int64_t x_pitch, int64_t npix, int C, float* partia
     YB_CHECK_CUDA(cudaFuncSetAttribute(bn_act_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr = true;
   }
-  bn_act_bwd_reduce_kernel<<<grid, threads, smem, ST(stream)>>>(CB16(x), x_pitch, nullptr, 0, npix, C, nullptr, nullptr,
-                                                                nullptr, nullptr, partial, rows_pb, 1);
+  YB_CHECK_CUDA(launch_pdl(bn_act_bwd_reduce_kernel, dim3(grid), dim3(threads), smem, ST(stream), CB16(x), x_pitch, nullptr, 0, npix, C, nullptr, nullptr,
+                                                                nullptr, nullptr, partial, rows_pb, 1));
   LAUNCH_OK();
   if (rows) *rows = grid;
   return 0;
@@ -761,8 +771,8 @@ int yb_colsum(const void* x, int64_t x_pitch, int64_t npix, int C, float* partia
 
 int yb_bn_bwd_finalize(const float* partial, int rows, int C, double count, float* dgamma, float* dbeta, float* coef,
                        int accumulate, void* stream) {
-  bn_bwd_finalize_kernel<<<(C + 31) / 32, 1024, 0, ST(stream)>>>(partial, rows, C, count, dgamma, dbeta, coef,
-                                                                   accumulate);
+  YB_CHECK_CUDA(launch_pdl(bn_bwd_finalize_kernel, dim3((C + 31) / 32), dim3(1024), 0, ST(stream), partial, rows, C, count, dgamma, dbeta, coef,
+                                                                   accumulate));
   LAUNCH_OK();
   return 0;
 }
@@ -774,11 +784,11 @@ int yb_bn_act_bwd_apply(const void* da, int64_t da_pitch, const void* y, int64_t
   static const int occ_grid = ew_wave_grid(bn_act_bwd_apply_kernel<true>, kEwThreads, 1L << 40);
   const int grid = std::min(occ_grid, ew_blocks(npix * (C / 8), kEwThreads, 64));
   if (kEwThreads % (C / 8) == 0)
-    bn_act_bwd_apply_kernel<true><<<grid, kEwThreads, 0, ST(stream)>>>(CB16(da), da_pitch, CB16(y), y_pitch, npix, C, scale,
-                                                                       shift, mean, invstd, coef, B16(dy), dy_pitch);
+    YB_CHECK_CUDA(launch_pdl(bn_act_bwd_apply_kernel<true>, dim3(grid), dim3(kEwThreads), 0, ST(stream), CB16(da), da_pitch, CB16(y), y_pitch, npix, C, scale,
+                                                                       shift, mean, invstd, coef, B16(dy), dy_pitch));
   else
-    bn_act_bwd_apply_kernel<false><<<grid, kEwThreads, 0, ST(stream)>>>(CB16(da), da_pitch, CB16(y), y_pitch, npix, C, scale,
-                                                                        shift, mean, invstd, coef, B16(dy), dy_pitch);
+    YB_CHECK_CUDA(launch_pdl(bn_act_bwd_apply_kernel<false>, dim3(grid), dim3(kEwThreads), 0, ST(stream), CB16(da), da_pitch, CB16(y), y_pitch, npix, C, scale,
+                                                                        shift, mean, invstd, coef, B16(dy), dy_pitch));
   LAUNCH_OK();
   return 0;
 }
