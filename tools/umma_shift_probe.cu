@@ -138,6 +138,59 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const __grid_constant__ P
     if (threadIdx.x == 0) p.cycles[8 + v] = clock64() - t0;
     __syncthreads();
   }
+  // ---- timing 3: what slows the MMA stream down inside a real kernel?  N = 96 MMAs by thread 0 while warps 1..3
+  //      (a) idle, (b) stream tcgen05.ld from another TMEM column range, (c) hammer shared memory with 16-byte stores,
+  //      (d) (thread 32) keeps TMA loads of the A tile in flight into a scratch buffer
+  __shared__ volatile int s_stop;
+  for (int v = 0; v < 4; ++v) {
+    if (threadIdx.x == 0) s_stop = 0;
+    __syncthreads();
+    long long t0 = 0;
+    if (threadIdx.x == 0) {
+      const uint32_t a0 = smem_u32(a_smem), b0 = smem_u32(b_smem);
+      const uint32_t idesc = make_idesc_bf16(128, 96, 0, 0);
+      t0 = clock64();
+      for (int i = 0; i < 256; ++i)
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base2 + (i & 1) * 96, make_smem_desc(a0 + k * 32, 16, 1024, 2), make_smem_desc(b0 + k * 32, 16, 1024, 2), idesc, 1);
+      umma_commit(mbar);
+      mbar_wait(mbar, mph);
+      p.cycles[16 + v] = clock64() - t0;
+      s_stop = 1;
+    } else if (warp >= 1) {
+      uint32_t sink = 0;
+      if (v == 1) {
+        while (!s_stop) {
+          uint32_t vr[16];
+          tmem_ld16(tmem_base2 + ((uint32_t)(warp * 32) << 16) + 256 + (sink & 63), vr);
+          tmem_ld_wait();
+          sink += vr[0] & 1;
+        }
+      } else if (v == 2) {
+        uint4* scratch = reinterpret_cast<uint4*>(b_smem + 16 * 1024);  // 16 KB further down: unused shared memory
+        while (!s_stop) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) scratch[(threadIdx.x - 32) + 96 * u] = make_uint4(sink, u, 0, 0);
+          sink++;
+        }
+      } else if (v == 3 && threadIdx.x == 32) {
+        uint64_t* bar2 = bar + 8;
+        uint32_t ph2 = 0;
+        mbar_init(bar2, 1);
+        fence_mbar_init();
+        while (!s_stop) {
+          mbar_expect_tx(bar2, 144 * 128);
+          tma_load_2d(&p.tmA, bar2, b_smem + 16 * 1024, 0, 0);
+          mbar_wait(bar2, ph2);
+          ph2 ^= 1;
+        }
+      }
+      if (sink == 0xffffffffu) p.cycles[31] = sink;
+    }
+    if (threadIdx.x == 0) mph ^= 1;
+    __syncthreads();
+    mph = __shfl_sync(0xffffffffu, mph, 0);
+  }
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
@@ -170,10 +223,10 @@ int main() {
   }
   p.out = dO;
   long long* dC;
-  cudaMalloc(&dC, 16 * sizeof(long long));
+  cudaMalloc(&dC, 32 * sizeof(long long));
   p.cycles = dC;
-  cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-  probe_kernel<<<1, 128, 64 * 1024>>>(p);
+  cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  probe_kernel<<<1, 128, 100 * 1024>>>(p);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     printf("kernel failed: %s\n", cudaGetErrorString(e));
@@ -203,7 +256,7 @@ int main() {
       }
       printf("\n");
     }
-  long long hC[16];
+  long long hC[32];
   cudaMemcpy(hC, dC, sizeof(hC), cudaMemcpyDeviceToHost);
   const int sbos[4] = {1024, 1280, 2048, 2304};
   for (int v = 0; v < 8; ++v)
@@ -211,6 +264,8 @@ int main() {
   const char* an[8] = {"N=96 one accumulator", "N=96 two accumulators 96 columns apart", "N=96 two accumulators 128 apart",
                        "N=96 two accumulators 64 apart (overlapping, timing only)", "N=48 one accumulator",
                        "N=48 four accumulators 48 apart", "N=48 four accumulators 128 apart", "N=48 four accumulators 64 apart"};
+  const char* cn[4] = {"alone", "+ 3 warps streaming tcgen05.ld", "+ 3 warps storing to shared memory", "+ TMA loads kept in flight"};
+  for (int v = 0; v < 4; ++v) printf("timing3: N=96 MMA stream %-40s : %.1f cycles per MMA\n", cn[v], hC[16 + v] / 1024.0);
   for (int v = 0; v < 8; ++v) printf("timing2: %-58s : %.1f cycles per MMA\n", an[v], hC[8 + v] / 512.0);
   return 0;
 }
