@@ -11,7 +11,7 @@ import re
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libyolov5m_b200.so")
+_LIB_PATH = os.environ.get("YB_LIB") or os.path.join(_HERE, "libyolov5m_b200.so")  # YB_LIB: A/B another build of the same ABI
 _HEADER = os.path.join(_HERE, "..", "include", "yolov5m_b200.h")
 _lib = None
 

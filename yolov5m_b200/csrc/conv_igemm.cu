@@ -124,9 +124,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      // The issue loop is ONE thread: keep it to a few instructions per MMA (descriptor = constant high part + 14-bit
-      // start-address field in 16-byte units, advanced by integer adds) or small-N tiles become issue-bound.
+    // The WHOLE warp runs this loop with warp-uniform control flow and values, and one elected lane issues the MMAs:
+    // tcgen05.mma takes its descriptors from uniform registers, and in a single-lane (divergent) loop every MMA costs
+    // four R2UR moves plus an ELECT on the issuing thread's critical path (~100 cycles per MMA, more than a small-N MMA
+    // itself).  No asm-laundered values here: they would make the operands per-thread again.
+    {
+      const bool leader = elect_one();
       const uint32_t idesc = make_idesc_bf16(128, p.BLOCK_N, 0, 0);
       const uint32_t row_bytes = 2u * p.KC;
       const uint32_t lt = swizzle_layout_type(row_bytes);
@@ -135,18 +138,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       const uint64_t desc_hi = make_smem_desc(0, 16, sbo, lt);
       const uint64_t a_desc0 = desc_hi | (uint64_t)(smem_u32(a_smem) >> 4);
       const uint64_t b_desc0 = desc_hi | (uint64_t)(smem_u32(b_smem) >> 4);
-      uint32_t a_step = p.a_stage_bytes >> 4, b_step = p.b_stage_bytes >> 4;
-      const TileDec td = load_tile_dec(p);
-      int chunks = p.chunks, stages = p.stages;
-      int klast = (p.Ck - (p.chunks - 1) * p.KC + 15) / 16;
-      keep_in_reg(a_step); keep_in_reg(b_step); keep_in_reg(chunks); keep_in_reg(stages); keep_in_reg(klast);
+      const uint32_t a_step = p.a_stage_bytes >> 4, b_step = p.b_stage_bytes >> 4;
+      const TileDec td{p.fd_c, p.fd_w, p.fd_h, p.fd_n};
+      const int chunks = p.chunks, stages = p.stages;
+      const int klast = (p.Ck - (p.chunks - 1) * p.KC + 15) / 16;
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
         const TileCoord tc = decode_tile(td, t);
-        const ConvGroup grp = s_groups[tc.g];
-        const int nk = (grp.tap_end - grp.tap_begin) * chunks;
+        const int nk = (p.groups[tc.g].tap_end - p.groups[tc.g].tap_begin) * chunks;
         const int ab = it & 1;
         const uint32_t aph = (it >> 1) & 1;
         mbar_wait(&tempty_bar[ab], aph ^ 1);
@@ -160,24 +161,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
           const uint64_t da = a_desc0 + (uint64_t)(s * a_step), db = b_desc0 + (uint64_t)(s * b_step);
           const bool last_chunk = ++chk == chunks;  // the zero-padded tail of the last channel chunk needs no MMAs
           if (last_chunk) chk = 0;
-          if (last_chunk && klast != kinner) {
-            for (int k = 0; k < klast; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, k ? 1u : acc);
-          } else if (kinner == 4) {
+          const int nmma = last_chunk ? klast : kinner;
+          if (leader) {
             umma_bf16(d_tmem, da, db, idesc, acc);
-            umma_bf16(d_tmem, da + 2, db + 2, idesc, 1u);
-            umma_bf16(d_tmem, da + 4, db + 4, idesc, 1u);
-            umma_bf16(d_tmem, da + 6, db + 6, idesc, 1u);
-          } else {
-            for (int k = 0; k < kinner; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, k ? 1u : acc);
+            if (nmma > 1) umma_bf16(d_tmem, da + 2, db + 2, idesc, 1u);
+            if (nmma > 2) umma_bf16(d_tmem, da + 4, db + 4, idesc, 1u);
+            if (nmma > 3) umma_bf16(d_tmem, da + 6, db + 6, idesc, 1u);
+            umma_commit(&empty_bar[s]);
           }
+          __syncwarp();
           acc = 1u;
-          umma_commit(&empty_bar[s]);
           if (++s == stages) {
             s = 0;
             ph ^= 1;
           }
         }
-        umma_commit(&tfull_bar[ab]);
+        if (leader) umma_commit(&tfull_bar[ab]);
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {

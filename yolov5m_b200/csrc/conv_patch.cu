@@ -165,75 +165,79 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      // The issue loop is ONE thread: a handful of instructions per MMA (descriptor = constant high part + 14-bit
-      // start-address field in 16-byte units, advanced by integer adds), or small-N tiles become issue-bound.
+    // The WHOLE warp runs this loop with warp-uniform control flow and values; one elected lane issues the MMAs (see
+    // conv_igemm.cu: in a single-lane loop every tcgen05.mma costs four R2UR moves + an ELECT on the critical path).
+    {
+      const bool leader = elect_one();
       const uint32_t idesc = make_idesc_bf16(128, p.BLOCK_N, 0, 0);
       const uint64_t b_desc0 = make_smem_desc(smem_u32(b_smem), 16, 1024, 2);
-      uint32_t a_step = p.a_stage_bytes >> 4, b_step = p.b_stage_bytes >> 4;
+      const uint32_t a_step = p.a_stage_bytes >> 4, b_step = p.b_stage_bytes >> 4;
       const uint32_t a_base16 = smem_u32(a_smem) >> 4;
-      const STileDec td = load_stile_dec(p);
-      int BN = p.BLOCK_N, chunks = p.chunks, nsa = p.sa, nsb = p.sb, TWl = p.TW;
-      int klast = (p.Ck - (p.chunks - 1) * 64 + 15) / 16;
-      keep_in_reg(a_step); keep_in_reg(b_step); keep_in_reg(BN); keep_in_reg(chunks); keep_in_reg(nsa); keep_in_reg(nsb);
-      keep_in_reg(TWl); keep_in_reg(klast);
+      const STileDec td{p.fd_c, p.fd_w, p.fd_h, p.fd_n};
+      const int BN = p.BLOCK_N, chunks = p.chunks, nsa = p.sa, nsb = p.sb, TWl = p.TW;
+      const int klast = (p.Ck - (p.chunks - 1) * 64 + 15) / 16;
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
       int it = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
         const STile tc = decode_stile(td, t);
-        const ConvGroup grp = s_groups[tc.g];
+        const int pbeg = p.groups[tc.g].tap_begin, pend = p.groups[tc.g].tap_end;
         const int ab = it & 1;
         const uint32_t aph = (it >> 1) & 1;
         mbar_wait(&tempty_bar[ab], aph ^ 1);
         tc_fence_after();
         const uint32_t d_base = tmem_base + ab * 256;
         uint32_t acc = 0;
-        for (int pi = grp.tap_begin; pi < grp.tap_end; ++pi) {
-          const PPatch pa = s_patches[pi];
-          const uint64_t a_hi = make_smem_desc(0, 16, (uint32_t)pa.pitch * 128u, 2);
+        for (int pi = pbeg; pi < pend; ++pi) {
+          const int pitch = p.patches[pi].pitch, tbeg = p.patches[pi].tap_begin, tend = p.patches[pi].tap_end;
+          const uint64_t a_hi = make_smem_desc(0, 16, (uint32_t)pitch * 128u, 2);
           // tile (ty, tx) starts (16*ty*pitch + 8*tx) pixel rows (x 128 B = x 8 descriptor units) into the patch
           uint32_t tile_off[4];
 #pragma unroll
           for (int tt = 0; tt < 4; ++tt) {
             const int ty = tt / TWl, tx = tt - ty * TWl;
-            tile_off[tt] = (uint32_t)(ty * 16 * pa.pitch + tx * 8) * 8u;
+            tile_off[tt] = (uint32_t)(ty * 16 * pitch + tx * 8) * 8u;
           }
           for (int ch = 0; ch < chunks; ++ch) {
             mbar_wait(&afull[sa], pha);
             tc_fence_after();
             const int nk = ch + 1 == chunks ? klast : 4;
             const uint64_t a_desc = a_hi | (uint64_t)(a_base16 + sa * a_step);
-            for (int tp = pa.tap_begin; tp < pa.tap_end; ++tp) {
-              const uint64_t a_tap = a_desc + (uint64_t)((uint32_t)s_taps[tp].row_off * 8u);
+            for (int tp = tbeg; tp < tend; ++tp) {
+              const uint64_t a_tap = a_desc + (uint64_t)((uint32_t)p.taps[tp].row_off * 8u);
               mbar_wait(&bfull[sb], phb);
               tc_fence_after();
               const uint64_t db = b_desc0 + (uint64_t)(sb * b_step);
+              if (leader) {
 #pragma unroll
-              for (int tt = 0; tt < 4; ++tt) {
-                if (tt >= T) break;
-                const uint64_t da = a_tap + tile_off[tt];
-                const uint32_t d_tmem = d_base + (uint32_t)tt * BN;
-                umma_bf16(d_tmem, da, db, idesc, acc);
-                if (nk > 1) umma_bf16(d_tmem, da + 2, db + 2, idesc, 1u);  // nk < 4: zero-padded tail of the last chunk
-                if (nk > 2) umma_bf16(d_tmem, da + 4, db + 4, idesc, 1u);
-                if (nk > 3) umma_bf16(d_tmem, da + 6, db + 6, idesc, 1u);
+                for (int tt = 0; tt < 4; ++tt) {
+                  if (tt >= T) break;
+                  const uint64_t da = a_tap + tile_off[tt];
+                  const uint32_t d_tmem = d_base + (uint32_t)tt * BN;
+                  umma_bf16(d_tmem, da, db, idesc, acc);
+                  if (nk > 1) umma_bf16(d_tmem, da + 2, db + 2, idesc, 1u);  // nk < 4: zero-padded tail of the last chunk
+                  if (nk > 2) umma_bf16(d_tmem, da + 4, db + 4, idesc, 1u);
+                  if (nk > 3) umma_bf16(d_tmem, da + 6, db + 6, idesc, 1u);
+                }
+                umma_commit(&bempty[sb]);
               }
+              __syncwarp();
               acc = 1u;
-              umma_commit(&bempty[sb]);
               if (++sb == nsb) {
                 sb = 0;
                 phb ^= 1;
               }
             }
-            umma_commit(&aempty[sa]);
+            if (leader) umma_commit(&aempty[sa]);
+            __syncwarp();
             if (++sa == nsa) {
               sa = 0;
               pha ^= 1;
             }
           }
         }
-        umma_commit(&tfull_bar[ab]);
+        if (leader) umma_commit(&tfull_bar[ab]);
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {

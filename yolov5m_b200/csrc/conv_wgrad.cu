@@ -123,8 +123,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      // ONE thread issues: descriptors are advanced by integer adds on the 14-bit start-address field (16-byte units)
+    // whole warp, warp-uniform values, one elected lane issues (see conv_igemm.cu); descriptors advance by integer adds
+    {
+      const bool leader = elect_one();
       const uint32_t idesc = make_idesc_bf16(128, p.BLOCK_N, 1, 1);  // both operands MN-major
       const uint32_t lt = swizzle_layout_type(128);
       const int kinner = p.KP / 16;
@@ -147,24 +148,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
           tc_fence_after();
           const uint64_t a_desc = desc0 + (uint64_t)(s * stage_step);
           const uint64_t b_desc = a_desc + b_off;
-          for (int mt = 0; mt < mts; ++mt) {
-            const uint32_t d_tmem = tmem_base + mt * p.BLOCK_N;
-            uint64_t da = a_desc + (uint64_t)(mt * tile_step), db = b_desc;
-            umma_bf16(d_tmem, da, db, idesc, acc);
-            for (int k = 1; k < kinner; ++k) {
-              da += 128;  // 16 pixels x 128 B = 2048 B
-              db += 128;
-              umma_bf16(d_tmem, da, db, idesc, 1u);
+          if (leader) {
+            for (int mt = 0; mt < mts; ++mt) {
+              const uint32_t d_tmem = tmem_base + mt * p.BLOCK_N;
+              uint64_t da = a_desc + (uint64_t)(mt * tile_step), db = b_desc;
+              umma_bf16(d_tmem, da, db, idesc, acc);
+              for (int k = 1; k < kinner; ++k) {
+                da += 128;  // 16 pixels x 128 B = 2048 B
+                db += 128;
+                umma_bf16(d_tmem, da, db, idesc, 1u);
+              }
             }
+            umma_commit(&empty_bar[s]);
           }
+          __syncwarp();
           acc = 1u;
-          umma_commit(&empty_bar[s]);
           if (++s == p.stages) {
             s = 0;
             ph ^= 1;
           }
         }
-        umma_commit(tfull_bar);
+        if (leader) umma_commit(tfull_bar);
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {

@@ -103,8 +103,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_patch_kernel(const __g
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (one thread; integer-add descriptors)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer
+    // whole warp, warp-uniform values, one elected lane issues (see conv_igemm.cu); integer-add descriptors
+    {
+      const bool leader = elect_one();
       const uint32_t idesc = make_idesc_bf16(128, p.BLOCK_N, 1, 1);  // both operands MN-major
       const int ksteps = p.KP / 16;
       const uint32_t stage_step = p.stage_bytes >> 4;
@@ -136,26 +138,30 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_patch_kernel(const __g
           tc_fence_after();
           const uint32_t st16 = base16 + s * stage_step;
           const uint64_t b_desc = b_hi + (uint64_t)(st16 + b_off16);
+          if (leader) {
 #pragma unroll
-          for (int mt = 0; mt < kTilesPerChunk; ++mt) {
-            if (mt >= mts) break;
-            const uint32_t d_tmem = tmem_base + mt * p.BLOCK_N;
-            uint64_t da = a_tile[mt] + st16, db = b_desc;
-            umma_bf16(d_tmem, da, db, idesc, acc);
-            for (int k = 1; k < ksteps; ++k) {
-              da += p.a_step16;
-              db += 128;  // 16 pixels x 128 B
-              umma_bf16(d_tmem, da, db, idesc, 1u);
+            for (int mt = 0; mt < kTilesPerChunk; ++mt) {
+              if (mt >= mts) break;
+              const uint32_t d_tmem = tmem_base + mt * p.BLOCK_N;
+              uint64_t da = a_tile[mt] + st16, db = b_desc;
+              umma_bf16(d_tmem, da, db, idesc, acc);
+              for (int k = 1; k < ksteps; ++k) {
+                da += p.a_step16;
+                db += 128;  // 16 pixels x 128 B
+                umma_bf16(d_tmem, da, db, idesc, 1u);
+              }
             }
+            umma_commit(&empty_bar[s]);
           }
+          __syncwarp();
           acc = 1u;
-          umma_commit(&empty_bar[s]);
           if (++s == p.stages) {
             s = 0;
             ph ^= 1;
           }
         }
-        umma_commit(tfull_bar);
+        if (leader) umma_commit(tfull_bar);
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {
