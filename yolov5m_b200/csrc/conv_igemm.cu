@@ -95,25 +95,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      const TileDec td = load_tile_dec(p);
-      int PW = p.PW, PH = p.PH, PN = p.PN, BN = p.BLOCK_N, chunks = p.chunks, KC = p.KC, stages = p.stages;
-      uint32_t tx = p.a_tx_bytes + p.b_tx_bytes, a_sb = p.a_stage_bytes, b_sb = p.b_stage_bytes;
-      keep_in_reg(PW); keep_in_reg(PH); keep_in_reg(PN); keep_in_reg(BN); keep_in_reg(chunks); keep_in_reg(KC);
-      keep_in_reg(stages); keep_in_reg(tx); keep_in_reg(a_sb); keep_in_reg(b_sb);
+    // whole warp, warp-uniform values, one elected lane issues (TMA instructions take uniform-register operands too)
+    {
+      const bool leader = elect_one();
+      const TileDec td{p.fd_c, p.fd_w, p.fd_h, p.fd_n};
+      const int PW = p.PW, PH = p.PH, PN = p.PN, BN = p.BLOCK_N, chunks = p.chunks, KC = p.KC, stages = p.stages;
+      const uint32_t tx = p.a_tx_bytes + p.b_tx_bytes, a_sb = p.a_stage_bytes, b_sb = p.b_stage_bytes;
       int s = 0;
       uint32_t ph = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const TileCoord tc = decode_tile(td, t);
-        const ConvGroup grp = s_groups[tc.g];
+        const int tbeg = p.groups[tc.g].tap_begin, tend = p.groups[tc.g].tap_end;
         const int w0 = tc.wb * PW, h0 = tc.hb * PH, n0 = tc.nb * PN, c0 = tc.nt * BN;
-        for (int tp = grp.tap_begin; tp < grp.tap_end; ++tp) {
-          const ConvTap tap = s_taps[tp];
+        for (int tp = tbeg; tp < tend; ++tp) {
+          const int tmap = p.taps[tp].map, tdw = p.taps[tp].dw, tdh = p.taps[tp].dh, tkb = p.taps[tp].kbase;
           for (int ch = 0; ch < chunks; ++ch) {
             mbar_wait(&empty_bar[s], ph ^ 1);
-            mbar_expect_tx(&full_bar[s], tx);
-            tma_load_4d(&p.tmA[tap.map], &full_bar[s], a_smem + (size_t)s * a_sb, ch * KC, w0 + tap.dw, h0 + tap.dh, n0);
-            tma_load_2d(&p.tmB, &full_bar[s], b_smem + (size_t)s * b_sb, tap.kbase + ch * KC, c0);
+            if (leader) {
+              mbar_expect_tx(&full_bar[s], tx);
+              tma_load_4d(&p.tmA[tmap], &full_bar[s], a_smem + (size_t)s * a_sb, ch * KC, w0 + tdw, h0 + tdh, n0);
+              tma_load_2d(&p.tmB, &full_bar[s], b_smem + (size_t)s * b_sb, tkb + ch * KC, c0);
+            }
+            __syncwarp();
             if (++s == stages) {
               s = 0;
               ph ^= 1;

@@ -108,24 +108,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
   pdl_wait();               // ... and do not touch global memory before the preceding kernels have completed
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ patch producer
-    if (lane == 0) {
-      const STileDec td = load_stile_dec(p);
-      int SW = p.TW * 8, SH = p.TH * 16, chunks = p.chunks, nsa = p.sa;
-      uint32_t a_sb = p.a_stage_bytes;
-      keep_in_reg(SW); keep_in_reg(SH); keep_in_reg(chunks); keep_in_reg(nsa); keep_in_reg(a_sb);
+    // ------------------------------------------------------------------ patch producer (whole warp, elected lane issues)
+    {
+      const bool leader = elect_one();
+      const STileDec td{p.fd_c, p.fd_w, p.fd_h, p.fd_n};
+      const int SW = p.TW * 8, SH = p.TH * 16, chunks = p.chunks, nsa = p.sa;
+      const uint32_t a_sb = p.a_stage_bytes;
       int s = 0;
       uint32_t ph = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
         const STile tc = decode_stile(td, t);
-        const ConvGroup grp = s_groups[tc.g];
+        const int pbeg = p.groups[tc.g].tap_begin, pend = p.groups[tc.g].tap_end;
         const int w0 = tc.wb * SW, h0 = tc.hb * SH;
-        for (int pi = grp.tap_begin; pi < grp.tap_end; ++pi) {
-          const PPatch pa = s_patches[pi];
+        for (int pi = pbeg; pi < pend; ++pi) {
+          const int pmap = p.patches[pi].map, pox = p.patches[pi].ox, poy = p.patches[pi].oy;
+          const uint32_t pbytes = p.patches[pi].bytes;
           for (int ch = 0; ch < chunks; ++ch) {
             mbar_wait(&aempty[s], ph ^ 1);
-            mbar_expect_tx(&afull[s], pa.bytes);
-            tma_load_4d(&p.tmA[pa.map], &afull[s], a_smem + (size_t)s * a_sb, ch * 64, w0 + pa.ox, h0 + pa.oy, tc.n);
+            if (leader) {
+              mbar_expect_tx(&afull[s], pbytes);
+              tma_load_4d(&p.tmA[pmap], &afull[s], a_smem + (size_t)s * a_sb, ch * 64, w0 + pox, h0 + poy, tc.n);
+            }
+            __syncwarp();
             if (++s == nsa) {
               s = 0;
               ph ^= 1;
@@ -135,25 +139,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
       }
     }
   } else if (warp == 3) {
-    // ------------------------------------------------------------------ weight producer
-    if (lane == 0) {
-      const STileDec td = load_stile_dec(p);
-      int BN = p.BLOCK_N, chunks = p.chunks, nsb = p.sb;
-      uint32_t b_sb = p.b_stage_bytes, b_tx = p.b_tx_bytes;
-      keep_in_reg(BN); keep_in_reg(chunks); keep_in_reg(nsb); keep_in_reg(b_sb); keep_in_reg(b_tx);
+    // ------------------------------------------------------------------ weight producer (whole warp, elected lane issues)
+    {
+      const bool leader = elect_one();
+      const STileDec td{p.fd_c, p.fd_w, p.fd_h, p.fd_n};
+      const int BN = p.BLOCK_N, chunks = p.chunks, nsb = p.sb;
+      const uint32_t b_sb = p.b_stage_bytes, b_tx = p.b_tx_bytes;
       int s = 0;
       uint32_t ph = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
         const STile tc = decode_stile(td, t);
-        const ConvGroup grp = s_groups[tc.g];
+        const int pbeg = p.groups[tc.g].tap_begin, pend = p.groups[tc.g].tap_end;
         const int c0 = tc.nt * BN;
-        for (int pi = grp.tap_begin; pi < grp.tap_end; ++pi) {
-          const PPatch pa = s_patches[pi];
+        for (int pi = pbeg; pi < pend; ++pi) {
+          const int tbeg = p.patches[pi].tap_begin, tend = p.patches[pi].tap_end;
           for (int ch = 0; ch < chunks; ++ch) {
-            for (int tp = pa.tap_begin; tp < pa.tap_end; ++tp) {
+            for (int tp = tbeg; tp < tend; ++tp) {
               mbar_wait(&bempty[s], ph ^ 1);
-              mbar_expect_tx(&bfull[s], b_tx);
-              tma_load_2d(&p.tmB, &bfull[s], b_smem + (size_t)s * b_sb, s_taps[tp].kbase + ch * 64, c0);
+              if (leader) {
+                mbar_expect_tx(&bfull[s], b_tx);
+                tma_load_2d(&p.tmB, &bfull[s], b_smem + (size_t)s * b_sb, p.taps[tp].kbase + ch * 64, c0);
+              }
+              __syncwarp();
               if (++s == nsb) {
                 s = 0;
                 ph ^= 1;

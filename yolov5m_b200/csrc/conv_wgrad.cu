@@ -81,8 +81,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
   pdl_wait();               // ... and do not touch global memory before the preceding kernels have completed
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (whole warp, elected lane issues)
+    {
+      const bool leader = elect_one();
       int s = 0;
       uint32_t ph = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
@@ -98,22 +99,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
           fdivmod(m, p.fd_th, ni, hi);
           const int w0 = wi * p.PW, h0 = hi * p.PH, n0 = ni * p.PN;
           mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_expect_tx(&full_bar[s], tx);
-          uint8_t* as = stage_smem + (size_t)s * p.stage_bytes;
-          uint8_t* bs = as + (size_t)2 * p.MT * p.box_bytes;
-          for (int j = 0; j < p.nb; ++j)
-            tma_load_4d(&p.tmDY, &full_bar[s], bs + (size_t)j * p.box_bytes, it.nt * p.BLOCK_N + j * kBoxC, w0, h0, n0);
-          int tapi, cb;
-          fdivmod(box0, p.fd_cb, tapi, cb);
-          for (int b = box0; b < box1; ++b) {
-            const ConvTap tap = p.taps[tapi];
-            tma_load_4d(&p.tmX[tap.map], &full_bar[s], as + (size_t)(b - box0) * p.box_bytes, cb * kBoxC, w0 + tap.dw,
-                        h0 + tap.dh, n0);
-            if (++cb == p.cboxes) {
-              cb = 0;
-              ++tapi;
+          if (leader) {
+            mbar_expect_tx(&full_bar[s], tx);
+            uint8_t* as = stage_smem + (size_t)s * p.stage_bytes;
+            uint8_t* bs = as + (size_t)2 * p.MT * p.box_bytes;
+            for (int j = 0; j < p.nb; ++j)
+              tma_load_4d(&p.tmDY, &full_bar[s], bs + (size_t)j * p.box_bytes, it.nt * p.BLOCK_N + j * kBoxC, w0, h0, n0);
+            int tapi, cb;
+            fdivmod(box0, p.fd_cb, tapi, cb);
+            for (int b = box0; b < box1; ++b) {
+              tma_load_4d(&p.tmX[p.taps[tapi].map], &full_bar[s], as + (size_t)(b - box0) * p.box_bytes, cb * kBoxC,
+                          w0 + p.taps[tapi].dw, h0 + p.taps[tapi].dh, n0);
+              if (++cb == p.cboxes) {
+                cb = 0;
+                ++tapi;
+              }
             }
           }
+          __syncwarp();
           if (++s == p.stages) {
             s = 0;
             ph ^= 1;

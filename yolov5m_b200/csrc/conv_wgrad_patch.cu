@@ -74,8 +74,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_patch_kernel(const __g
   pdl_wait();               // ... and do not touch global memory before the preceding kernels have completed
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (whole warp, elected lane issues)
+    {
+      const bool leader = elect_one();
       int s = 0;
       uint32_t ph = 0;
       const uint32_t tx = p.patch_tx + (uint32_t)p.nb * p.box_bytes;  // patch_bytes is the 1024-aligned slot size
@@ -89,12 +90,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_patch_kernel(const __g
           fdivmod(m, p.fd_th, ni, hi);
           const int w0 = wi * p.PW, h0 = hi * p.PH;
           mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_expect_tx(&full_bar[s], tx);
-          uint8_t* as = stage_smem + (size_t)s * p.stage_bytes;
-          uint8_t* bs = as + p.patch_bytes;
-          tma_load_4d(&p.tmX, &full_bar[s], as, it.cb * 64, w0 - 1, h0 - 1, ni);
-          for (int j = 0; j < p.nb; ++j)
-            tma_load_4d(&p.tmDY, &full_bar[s], bs + (size_t)j * p.box_bytes, it.nt * p.BLOCK_N + j * 64, w0, h0, ni);
+          if (leader) {
+            mbar_expect_tx(&full_bar[s], tx);
+            uint8_t* as = stage_smem + (size_t)s * p.stage_bytes;
+            uint8_t* bs = as + p.patch_bytes;
+            tma_load_4d(&p.tmX, &full_bar[s], as, it.cb * 64, w0 - 1, h0 - 1, ni);
+            for (int j = 0; j < p.nb; ++j)
+              tma_load_4d(&p.tmDY, &full_bar[s], bs + (size_t)j * p.box_bytes, it.nt * p.BLOCK_N + j * 64, w0, h0, ni);
+          }
+          __syncwarp();
           if (++s == p.stages) {
             s = 0;
             ph ^= 1;
