@@ -131,6 +131,10 @@ int yb_maxpool5_bwd(const void* dy, int64_t dy_pitch, const uint8_t* argmax, int
  * taps gathered (channel kw*16+j = s2d pixel w+kw-1, zero outside), so that the 6x6/s2 stem (model.py:184) becomes a
  * 3x1 convolution (ks code 31 of yb_conv_fwd_plan / yb_conv_wgrad_plan) with weights [Cout][3][48] = yb_repack_stem */
 int yb_prep_input(const void* x, int dtype, int N, int H, int W, void* out, void* stream);
+/* same staging, but the (N,3,Hs,Ws) image is first resampled to (H,W) like the reference's multi_scale()
+ * (utils/training_utils.py:11-28: F.interpolate(img, size=(H,W), mode="bilinear", align_corners=False) of the float image);
+ * the resized float image is never materialised */
+int yb_prep_input_resized(const void* x, int dtype, int N, int Hs, int Ws, int H, int W, void* out, void* stream);
 /* dense gradient of a head output (B,na,H,W,no) fp32 -> bf16 NHWC (B,H,W,Cpad), channel a*no+o (model.py:173 backward) */
 int yb_head_grad_pack(const float* g, int B, int na, int H, int W, int no, void* dy, int Cpad, void* stream);
 

@@ -193,3 +193,36 @@ def test_upsample_add_prep_pack():
     out = torch.ones(255, device="cuda")
     _lib.check(L.yb_reduce_rows(_lib.ptr(part), rows.value, _lib.c_i64(512), 255, _lib.ptr(out), 1, _lib.stream()))
     assert torch.allclose(out.cpu(), 1 + x.float().sum(0)[:255].cpu(), atol=1e-3)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.uint8])
+@pytest.mark.parametrize("src,dst", [((48, 64), (32, 64)), ((40, 40), (64, 64)), ((64, 96), (32, 32)), ((33, 47), (64, 96))])
+def test_prep_input_resized_matches_interpolate(dt, src, dst):
+    """multi_scale (training_utils.py:11-28): bilinear, align_corners=False, of the float image, fused into the stem
+    staging.  Oracle: F.interpolate on the CPU, staged by the (already tested) plain yb_prep_input.  The two differ only
+    by fp32 summation order, i.e. by at most one bf16 rounding step of the staged value."""
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(src[0] * 131 + dst[1])
+    x = torch.rand(2, 3, *src, generator=g)
+    if dt == torch.uint8:
+        x = (x * 255).to(torch.uint8)
+    xf = x.float() / 255 if dt == torch.uint8 else x
+    want_img = F.interpolate(xf, size=dst, mode="bilinear", align_corners=False).contiguous()
+    H, W = dst
+    got = torch.empty(2, H // 2, W // 2, 48, device="cuda", dtype=torch.bfloat16)
+    want = torch.empty_like(got)
+    _lib.check(L.yb_prep_input_resized(_lib.ptr(x.cuda()), 0 if dt == torch.float32 else 1, 2, src[0], src[1], H, W,
+                                       _lib.ptr(got), _lib.stream()))
+    _lib.check(L.yb_prep_input(_lib.ptr(want_img.cuda()), 0, 2, H, W, _lib.ptr(want), _lib.stream()))
+    a, b = got.float().cpu(), want.float().cpu()
+    assert (a - b).abs().max().item() <= 2 ** -8          # values are in [0, 1]: one bf16 ulp at most
+    assert (a != b).float().mean().item() < 0.02           # and almost all are bit-identical
+    # identity resize == plain staging, bit for bit
+    same = torch.empty(2, src[0] // 2 * 2 // 2, src[1] // 2 * 2 // 2, 48, device="cuda", dtype=torch.bfloat16)
+    if src[0] % 2 == 0 and src[1] % 2 == 0:
+        ref = torch.empty_like(same)
+        _lib.check(L.yb_prep_input_resized(_lib.ptr(x.cuda()), 0 if dt == torch.float32 else 1, 2, src[0], src[1], src[0],
+                                           src[1], _lib.ptr(same), _lib.stream()))
+        _lib.check(L.yb_prep_input(_lib.ptr(x.cuda()), 0 if dt == torch.float32 else 1, 2, src[0], src[1], _lib.ptr(ref),
+                                   _lib.stream()))
+        assert torch.equal(same.cpu(), ref.cpu())

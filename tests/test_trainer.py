@@ -108,3 +108,23 @@ def test_train_step_runs_and_learns():
         b = m((x.float() / 255).cuda())
     for u, v in zip(a, b):
         assert torch.allclose(u, v, atol=1e-2, rtol=1e-2)
+
+
+def test_multi_scale_size_follows_reference_rule():
+    """utils/training_utils.py:11-28: longer side -> random multiple of 32 in [320, 640], shorter side scaled by the same
+    factor and rounded UP to a multiple of 32 (the reference passes a float to random.randrange, which Python >= 3.12
+    rejects; the draw is restated with the same integer bounds)."""
+    import math
+    import random
+    from yolov5m_b200.trainer import multi_scale_size
+    for (h, w) in [(640, 640), (480, 640), (640, 352), (1280, 1280)]:
+        r1, r2 = random.Random(7), random.Random(7)
+        seen = set()
+        for _ in range(300):
+            nh, nw = multi_scale_size(h, w, 640, 32, rng=r1)
+            sz = r2.randrange(320, 672) // 32 * 32
+            sf = sz / max(h, w)
+            assert (nh, nw) == (math.ceil(h * sf / 32) * 32, math.ceil(w * sf / 32) * 32)
+            assert nh % 32 == 0 and nw % 32 == 0 and max(nh, nw) == sz and 320 <= sz <= 640
+            seen.add(sz)
+        assert seen == set(range(320, 641, 32))

@@ -23,6 +23,7 @@
 #include "conv_wgrad.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace yb {
@@ -129,7 +130,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
     // whole warp, warp-uniform values, one elected lane issues (see conv_igemm.cu); descriptors advance by integer adds
     {
       const bool leader = elect_one();
-      const uint32_t idesc = make_idesc_bf16(128, p.BLOCK_N, 1, 1);  // both operands MN-major
       const uint32_t lt = swizzle_layout_type(128);
       const int kinner = p.KP / 16;
       const uint64_t desc0 = make_smem_desc(smem_u32(stage_smem), p.box_bytes, 1024, lt);
@@ -143,6 +143,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
         const int pt0 = (int)(((long)it.sp * p.ptiles) / p.splits);
         const int pt1 = (int)(((long)(it.sp + 1) * p.ptiles) / p.splits);
         const int mts = min(p.MT, p.m_tiles - it.mg * p.MT);
+        // MMA N = the real output channels of this N tile (rounded up to 16), not the 64-channel box multiple: the tail
+        // of the last dy box is OOB zero fill and never read (Cout = 96: N = 96 instead of 128, Cout = 48: 48 instead of 64)
+        const int n_mma = p.exact_n ? min(p.BLOCK_N, ((p.Cout + 15) & ~15) - it.nt * p.BLOCK_N) : p.BLOCK_N;
+        const uint32_t idesc = make_idesc_bf16(128, n_mma, 1, 1);  // both operands MN-major
         mbar_wait(tempty_bar, (iter & 1) ^ 1);
         tc_fence_after();
         uint32_t acc = 0;
@@ -346,13 +350,14 @@ int wgrad_plan(WgradPlan& pl, const TView& x, const TView& dy, int ks, int strid
   kp.boxes_total = kp.ntaps * kp.cboxes;
   kp.m_tiles = (kp.boxes_total + 1) / 2;
   kp.BLOCK_N = pick_block_n(dy.C, kp.n_tiles);
+  kp.exact_n = wgrad_exact_n();
   kp.nb = kp.BLOCK_N / kBoxC;
   kp.Mpad = kp.ntaps * kp.Cin_pad;
   kp.Npad = kp.n_tiles * kp.BLOCK_N;
   kp.ldo = kp.ntaps * x.C;
   // pixel patch (GEMM-K chunk) and the number of M tiles that share one dy stage: minimise the L2 -> shared-memory
   // bytes per MMA (nb + 2*MT boxes feed MT tiles) under >= 2 (preferably >= 3) pipeline stages of shared memory
-  const size_t budget = 227 * 1024 - 1024 - kBarRegion;
+  const size_t budget = wgrad_smem_budget();
   const int mt_max = std::max(1, std::min(512 / kp.BLOCK_N, kp.m_tiles));
   double best = -1;
   const double real_px = (double)dy.W * dy.H * dy.N;
@@ -442,6 +447,24 @@ int wgrad_plan(WgradPlan& pl, const TView& x, const TView& dy, int ks, int strid
 }
 
 static int g_sms = 0;
+int wgrad_exact_n() {
+  static const int v = [] {
+    const char* e = getenv("YB_WGRAD_EXACT_N");
+    return e != nullptr ? atoi(e) : 1;
+  }();
+  return v;
+}
+
+size_t wgrad_smem_budget() {
+  static const size_t budget = [] {
+    const char* e = getenv("YB_WGRAD_SMEM_KB");
+    int kb = e != nullptr ? atoi(e) : 227;
+    kb = std::min(227, std::max(128, kb));
+    return (size_t)kb * 1024 - 1024 - kBarRegion;
+  }();
+  return budget;
+}
+
 int wgrad_max_grid() {
   if (g_sms == 0) {
     int dev = 0;

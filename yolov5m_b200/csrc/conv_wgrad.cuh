@@ -16,6 +16,7 @@ struct WgradKParams {
   int32_t KP, PW, PH, PN;    // pixels per pipeline stage (GEMM-K chunk) and its patch shape
   int32_t tiles_w, tiles_h, tiles_n, ptiles;
   int32_t splits;
+  int32_t exact_n;           // 1: MMA N = real channels of the N tile (multiple of 16) instead of BLOCK_N
   FDiv fd_nt, fd_mg, fd_tw, fd_th, fd_cb;  // item / pixel-tile / box index decoding
   int32_t Cout, Cin, Cin_pad, ldo;  // ldo = ntaps * Cin = row length of dW
   int32_t Mpad, Npad;        // partial tile: [Mpad = ntaps*Cin_pad][Npad = n_tiles*BLOCK_N]
@@ -35,6 +36,7 @@ struct WPatchKParams {
   int32_t PW, PH, KP, pitch;
   int32_t a_step16, a_sbo;  // A start advance per K = 16 step (descriptor units) and byte stride between its two 8-pixel groups
   int32_t tiles_w, tiles_h, ptiles, splits;
+  int32_t exact_n;
   FDiv fd_nt, fd_mg, fd_cb, fd_tw, fd_th;
   int32_t Cout, Cin, Cin_pad, Mpad, Npad;
   int32_t stages;
@@ -54,6 +56,11 @@ int wgrad_patch_plan(WgradPlan& pl, const TView& x, const TView& dy, int ks, int
                      size_t partial_floats, int max_splits);
 int wgrad_patch_launch(const WgradPlan& pl, cudaStream_t st);
 int wgrad_max_grid();
+// Shared-memory budget of the operand ring of the weight-gradient kernels.  Default: the whole 227 KB.  YB_WGRAD_SMEM_KB
+// (128..227) shrinks it so that the CTAs of the HBM-bound BN/SiLU-backward passes (<= 17 KB each) fit on the same SM while
+// a weight-gradient kernel runs on the side stream (yolov5m_b200/model.py, _Engine._wgrad_async).
+size_t wgrad_smem_budget();
+int wgrad_exact_n();  // YB_WGRAD_EXACT_N (default 1)
 
 // x: conv input (N,H,W,Cin); dy: grad of the conv output (N,H/s,W/s,Cout).
 int wgrad_plan(WgradPlan& pl, const TView& x, const TView& dy, int ks, int stride, float* partial,

@@ -111,7 +111,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_patch_kernel(const __g
     // whole warp, warp-uniform values, one elected lane issues (see conv_igemm.cu); integer-add descriptors
     {
       const bool leader = elect_one();
-      const uint32_t idesc = make_idesc_bf16(128, p.BLOCK_N, 1, 1);  // both operands MN-major
       const int ksteps = p.KP / 16;
       const uint32_t stage_step = p.stage_bytes >> 4;
       const uint32_t base16 = smem_u32(stage_smem) >> 4;
@@ -126,6 +125,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_patch_kernel(const __g
         const int pt1 = (int)(((long)(it.sp + 1) * p.ptiles) / p.splits);
         const int tile0 = it.mg * p.MT;
         const int mts = min(p.MT, kTilesPerChunk - tile0);
+        // MMA N = real output channels of this N tile rounded up to 16 (see conv_wgrad.cu)
+        const int n_mma = p.exact_n ? min(p.BLOCK_N, ((p.Cout + 15) & ~15) - it.nt * p.BLOCK_N) : p.BLOCK_N;
+        const uint32_t idesc = make_idesc_bf16(128, n_mma, 1, 1);  // both operands MN-major
         // per tile: descriptor high part (LBO = distance between its two taps) + start of the first tap
         uint64_t a_tile[kTilesPerChunk];
 #pragma unroll
@@ -267,6 +269,7 @@ int wgrad_patch_plan(WgradPlan& pl, const TView& x, const TView& dy, int ks, int
     const int c64 = (dy.C + 63) / 64;
     kp.n_tiles = (c64 + 3) / 4;
     kp.BLOCK_N = (c64 + kp.n_tiles - 1) / kp.n_tiles * 64;
+    kp.exact_n = wgrad_exact_n();
   }
   kp.nb = kp.BLOCK_N / 64;
   kp.Mpad = 9 * kp.Cin_pad;
@@ -289,7 +292,7 @@ int wgrad_patch_plan(WgradPlan& pl, const TView& x, const TView& dy, int ks, int
     kp.a_step16 = 2 * kp.pitch * 8;
     kp.a_sbo = kp.pitch * 128;
   }
-  const size_t budget = 227 * 1024 - 1024 - kBarRegion;
+  const size_t budget = wgrad_smem_budget();
   kp.stages = (int)std::min<size_t>(kMaxStages, budget / kp.stage_bytes);
   if (kp.stages < 2) return 1;
   kp.MT = std::max(1, std::min(512 / kp.BLOCK_N, kTilesPerChunk));

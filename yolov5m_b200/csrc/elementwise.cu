@@ -568,8 +568,32 @@ __global__ void maxpool5_bwd_kernel(const bf16* __restrict__ dy, long dy_pitch, 
 //   of the stem gathered:  out[ho][wo][kw*16 + j] = s2d[ho][wo+kw-1][j]  (zero outside the image).
 // The 6x6/s2 stem (model.py:184) = 3x3/s1 over s2d = THREE vertical taps over `out` with K = 48 per tap: a third of the
 // TMA boxes / MMA steps of the nine-tap form, and full-width pipeline stages instead of 32-byte rows.
+// RESIZE: the image is first resampled from (Hs, Ws) to (H, W) exactly like the reference's multi_scale()
+// (utils/training_utils.py:11-28: nn.functional.interpolate(img, size, mode="bilinear", align_corners=False) on the
+// float image): src = max(scale * (dst + 0.5) - 0.5, 0), scale = in / out, neighbours (i, min(i + 1, in - 1)).
+struct Lerp {
+  int i0, i1;
+  float l0, l1;
+};
+__device__ __forceinline__ Lerp lerp_coord(int dst, float scale, int in) {
+  float src = scale * ((float)dst + 0.5f) - 0.5f;
+  src = src < 0.f ? 0.f : src;
+  Lerp r;
+  r.i0 = min((int)src, in - 1);
+  r.i1 = r.i0 + (r.i0 < in - 1 ? 1 : 0);
+  r.l1 = src - (float)r.i0;
+  r.l0 = 1.f - r.l1;
+  return r;
+}
 template <typename T>
-__global__ void prep_input_kernel(const T* __restrict__ x, int N, int H, int W, bf16* __restrict__ out) {
+__device__ __forceinline__ float px_value(const T* p) {
+  if constexpr (sizeof(T) == 1) return (float)(*p) / 255.f;
+  else return *p;
+}
+
+template <typename T, bool RESIZE>
+__global__ void prep_input_kernel(const T* __restrict__ x, int N, int H, int W, bf16* __restrict__ out, int Hs, int Ws,
+                                  float scale_h, float scale_w) {
   const int Ho = H >> 1, Wo = W >> 1;
   const long total = (long)N * Ho * Wo;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -580,23 +604,47 @@ __global__ void prep_input_kernel(const T* __restrict__ x, int N, int H, int W, 
     float v[16];
 #pragma unroll
     for (int j = 12; j < 16; ++j) v[j] = 0.f;
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
+    if constexpr (RESIZE) {
+      Lerp lx[2], ly[2];
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
-        const T* p = x + ((n * 3 + c) * H + 2 * ho + r) * (long)W + 2 * wo;
-        float a, b;
-        if constexpr (sizeof(T) == 1) {
-          a = (float)p[0] / 255.f;
-          b = (float)p[1] / 255.f;
-        } else {
-          const float2 f = *reinterpret_cast<const float2*>(p);
-          a = f.x;
-          b = f.y;
-        }
-        v[(r * 2 + 0) * 3 + c] = a;
-        v[(r * 2 + 1) * 3 + c] = b;
+        ly[r] = lerp_coord(2 * ho + r, scale_h, Hs);
+        lx[r] = lerp_coord(2 * wo + r, scale_w, Ws);
       }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const T* plane = x + (n * 3 + c) * (long)Hs * Ws;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const T* r0 = plane + (long)ly[r].i0 * Ws;
+          const T* r1 = plane + (long)ly[r].i1 * Ws;
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const float top = lx[q].l0 * px_value(r0 + lx[q].i0) + lx[q].l1 * px_value(r0 + lx[q].i1);
+            const float bot = lx[q].l0 * px_value(r1 + lx[q].i0) + lx[q].l1 * px_value(r1 + lx[q].i1);
+            v[(r * 2 + q) * 3 + c] = ly[r].l0 * top + ly[r].l1 * bot;
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const T* p = x + ((n * 3 + c) * H + 2 * ho + r) * (long)W + 2 * wo;
+          float a, b;
+          if constexpr (sizeof(T) == 1) {
+            a = (float)p[0] / 255.f;
+            b = (float)p[1] / 255.f;
+          } else {
+            const float2 f = *reinterpret_cast<const float2*>(p);
+            a = f.x;
+            b = f.y;
+          }
+          v[(r * 2 + 0) * 3 + c] = a;
+          v[(r * 2 + 1) * 3 + c] = b;
+        }
+    }
     V8 lo, hi, z;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -817,13 +865,29 @@ int yb_prep_input(const void* x, int dtype, int N, int H, int W, void* out, void
   YB_REQUIRE(H % 2 == 0 && W % 2 == 0, "prep_input: odd image size");
   const long total = (long)N * (H / 2) * (W / 2);
   if (dtype == 0)
-    prep_input_kernel<float><<<ew_blocks(total), 256, 0, ST(stream)>>>(reinterpret_cast<const float*>(x), N, H, W,
-                                                                        B16(out));
+    prep_input_kernel<float, false><<<ew_blocks(total), 256, 0, ST(stream)>>>(reinterpret_cast<const float*>(x), N, H, W,
+                                                                               B16(out), H, W, 1.f, 1.f);
   else if (dtype == 1)
-    prep_input_kernel<uint8_t><<<ew_blocks(total), 256, 0, ST(stream)>>>(reinterpret_cast<const uint8_t*>(x), N, H, W,
-                                                                          B16(out));
+    prep_input_kernel<uint8_t, false><<<ew_blocks(total), 256, 0, ST(stream)>>>(reinterpret_cast<const uint8_t*>(x), N, H,
+                                                                                 W, B16(out), H, W, 1.f, 1.f);
   else
     YB_REQUIRE(false, "prep_input: dtype %d (0 = float32, 1 = uint8)", dtype);
+  LAUNCH_OK();
+  return 0;
+}
+
+int yb_prep_input_resized(const void* x, int dtype, int N, int Hs, int Ws, int H, int W, void* out, void* stream) {
+  YB_REQUIRE(H % 2 == 0 && W % 2 == 0 && Hs > 0 && Ws > 0, "prep_input_resized: sizes");
+  const long total = (long)N * (H / 2) * (W / 2);
+  const float sh = (float)Hs / (float)H, sw = (float)Ws / (float)W;  // ATen area_pixel_compute_scale (align_corners=False)
+  if (dtype == 0)
+    prep_input_kernel<float, true><<<ew_blocks(total), 256, 0, ST(stream)>>>(reinterpret_cast<const float*>(x), N, H, W,
+                                                                              B16(out), Hs, Ws, sh, sw);
+  else if (dtype == 1)
+    prep_input_kernel<uint8_t, true><<<ew_blocks(total), 256, 0, ST(stream)>>>(reinterpret_cast<const uint8_t*>(x), N, H, W,
+                                                                                B16(out), Hs, Ws, sh, sw);
+  else
+    YB_REQUIRE(false, "prep_input_resized: dtype %d (0 = float32, 1 = uint8)", dtype);
   LAUNCH_OK();
   return 0;
 }

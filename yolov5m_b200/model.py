@@ -18,6 +18,7 @@ There is no CPU / PyTorch fallback: calling forward without the CUDA library or 
 """
 import ctypes
 import math
+import os
 
 import numpy as np
 import torch
@@ -191,6 +192,12 @@ class _Engine:
             self.wg_ws = torch.empty(32 << 20, device=self.dev, dtype=torch.float32)
             self.dy = None  # allocated after the forward build (max conv output size)
             self._dy_elems = 0
+            # YB_WGRAD_STREAM=1 (experiment, off by default): weight-gradient kernels on a second stream, meant to overlap
+            # the tensor-bound wgrad of layer L with the HBM-bound BN/SiLU backward of layer L-1.  Measured on B200
+            # (profiles/ab_wgrad_side_stream_r1.json): no gain -- the elementwise passes are launched as one full resident
+            # wave and hold the register file, so a 512-thread wgrad CTA cannot become co-resident until they drain.
+            self.side = torch.cuda.Stream(device=self.dev) if os.environ.get("YB_WGRAD_STREAM", "0") == "1" else None
+            self._bwd_events = []
         self._build()
 
     # -- timed launch wrappers (bench.py roofline: CUDA events around every tensor-core kernel launch when prof is a list)
@@ -213,6 +220,26 @@ class _Engine:
         _lib.check(self.L.yb_wgrad_plan_run(plan, *args, st))
         e1.record()
         self.prof.append(("wgrad", flops, e0, e1))
+
+    def _layer_events(self):
+        if self.side is None:
+            return None
+        evs = (torch.cuda.Event(), torch.cuda.Event())  # (dy ready + dgrad issued on the main stream, wgrad done on the side)
+        self._bwd_events.append(evs)
+        return evs
+
+    def _wgrad_async(self, evs, plan, st, flops, *args):
+        """Weight gradient of one layer.  With the side stream enabled it is ordered AFTER the layer's dgrad (so the dgrad
+        -- which the next layer's backward waits for -- gets the SMs first) and then runs concurrently with the HBM-bound
+        BN/SiLU-backward passes of the next layer; nothing on the main stream waits for it until its dy buffer is reused
+        (two layers later) or the step ends (run_backward)."""
+        if not self._side_on:
+            self._wgrad(plan, st, flops, *args)
+            return
+        evs[0].record(self._main)
+        self.side.wait_event(evs[0])
+        _lib.check(self.L.yb_wgrad_plan_run(plan, *args, self.side.cuda_stream))
+        evs[1].record(self.side)
 
     # -- allocation helpers
     def buf(self, N, H, W, C, grad=None):
@@ -361,8 +388,9 @@ class _Engine:
         for i, p in enumerate((P3, P4, P5)):
             self.head(i, p.v())
         if self.train:
-            self.dy = torch.empty(self._dy_elems, device=self.dev, dtype=torch.bfloat16)
-            self.nbytes += self._dy_elems * 2
+            ndy = 2 if self.side is not None else 1  # double-buffered when wgrad(L) overlaps the BN backward of L-1
+            self.dy = [torch.empty(self._dy_elems, device=self.dev, dtype=torch.bfloat16) for _ in range(ndy)]
+            self.nbytes += self._dy_elems * 2 * ndy
             self._build_backward()
 
     # -- backward construction (reverse tape); gradient fan-in is resolved statically
@@ -397,9 +425,9 @@ class _Engine:
 
     def _build_backward(self):
         net, L = self.net, self.L
-        dy_ptr = self.dy.data_ptr()
         redp, coefp = self.red_partial.data_ptr(), self.coef.data_ptr()
         ws, wsn = self.wg_ws.data_ptr(), self.wg_ws.numel()
+        nlayer, done_by_slot = 0, {}
         for rec in reversed(self.tape):
             kind = rec[0]
             if kind == "head":
@@ -418,11 +446,13 @@ class _Engine:
                 xin.buf.gw[xin.c0:xin.c0 + xin.C] = True
                 rows = ctypes.c_int(0)
 
-                def op(st, g, r=r, dyp=dyp, npix=npix, wplan=wplan, dplan=dplan, rows=rows, flops=flops):
+                evs = self._layer_events()
+
+                def op(st, g, r=r, dyp=dyp, npix=npix, wplan=wplan, dplan=dplan, rows=rows, flops=flops, evs=evs):
                     _lib.check(L.yb_colsum(dyp, HEAD_PAD, npix, HEAD_PAD, redp, ctypes.byref(rows), st))
                     _lib.check(L.yb_reduce_rows(redp, rows.value, 2 * HEAD_PAD, r.cout, g + 4 * r.bias_off, 0, st))
-                    self._wgrad(wplan, st, flops, g + 4 * r.w_off, r.cout, None, 0)
                     self._conv(dplan, st, flops, "dgrad")
+                    self._wgrad_async(evs, wplan, st, flops, g + 4 * r.w_off, r.cout, None, 0)
                 self.bwd_ops.append(op)
             elif kind == "pool":
                 _, src, dst, am = rec
@@ -439,6 +469,14 @@ class _Engine:
                     self.conv_flops["dgrad"] += flops
                 C, npix = r.cout, y.npix
                 k, s = (31, 1) if r.is_stem else (r.k, r.stride)
+                # dy scratch of this layer: alternates between two buffers when the weight gradients run on the side
+                # stream (wgrad of layer i reads dy[i % 2] while the BN backward of layer i+1 already writes the other one)
+                slot = nlayer % len(self.dy)
+                dy_ptr = self.dy[slot].data_ptr()
+                evs = self._layer_events()
+                dy_free = done_by_slot.get(slot)  # wgrad-done event of the previous user of this dy buffer
+                done_by_slot[slot] = evs[1] if evs is not None else None
+                nlayer += 1
                 self._flush_pending(out)
                 assert self._contrib_state(out), f"{r.name}: output gradient never produced"
                 if up is not None:
@@ -474,15 +512,17 @@ class _Engine:
                 count = float(npix)
 
                 def op(st, g, r=r, out=out, y=y, ptrs=ptrs, C=C, npix=npix, wplan=wplan, dplan=dplan, mapp=mapp, rows=rows,
-                       count=count, flops=flops):
+                       count=count, flops=flops, dy_ptr=dy_ptr, evs=evs, dy_free=dy_free):
                     _lib.check(L.yb_bn_act_bwd_reduce(out.gptr, out.pitch, y.ptr, C, npix, C, ptrs[1], ptrs[2], ptrs[3],
                                                       ptrs[4], redp, ctypes.byref(rows), st))
                     _lib.check(L.yb_bn_bwd_finalize(redp, rows.value, C, count, g + 4 * r.g_off, g + 4 * r.b_off, coefp, 0, st))
+                    if dy_free is not None and self._side_on:
+                        self._main.wait_event(dy_free)  # the wgrad that still reads this dy buffer (two layers back)
                     _lib.check(L.yb_bn_act_bwd_apply(out.gptr, out.pitch, y.ptr, C, npix, C, ptrs[1], ptrs[2], ptrs[3],
                                                      ptrs[4], coefp, dy_ptr, C, st))
-                    self._wgrad(wplan, st, flops, g + 4 * r.w_off, C, mapp, 0)
                     if dplan is not None:
                         self._conv(dplan, st, flops, "dgrad")
+                    self._wgrad_async(evs, wplan, st, flops, g + 4 * r.w_off, C, mapp, 0)
                 self.bwd_ops.append(op)
 
     # -- execution
@@ -490,7 +530,11 @@ class _Engine:
         L = self.L
         st = _lib.stream()
         dt = 0 if x.dtype == torch.float32 else 1
-        _lib.check(L.yb_prep_input(x.data_ptr(), dt, self.B, self.H, self.W, self.x16.t.data_ptr(), st))
+        Hs, Ws = x.shape[2], x.shape[3]
+        if (Hs, Ws) == (self.H, self.W):
+            _lib.check(L.yb_prep_input(x.data_ptr(), dt, self.B, self.H, self.W, self.x16.t.data_ptr(), st))
+        else:  # multi-scale training: bilinear resample fused into the stem staging (training_utils.py:11-28)
+            _lib.check(L.yb_prep_input_resized(x.data_ptr(), dt, self.B, Hs, Ws, self.H, self.W, self.x16.t.data_ptr(), st))
         for op in self.fwd_ops:
             op(st)
         return self.outs
@@ -498,8 +542,12 @@ class _Engine:
     def run_backward(self, gflat):
         st = _lib.stream()
         g = gflat.data_ptr()
+        self._main = torch.cuda.current_stream(self.dev)
+        self._side_on = self.side is not None and self.prof is None  # the per-kernel timing pass stays on one stream
         for op in self.bwd_ops:
             op(st, g)
+        if self._side_on:
+            self._main.wait_stream(self.side)  # every weight gradient is in the bucket before all-reduce / optimiser
 
     def __del__(self):
         try:
@@ -717,24 +765,35 @@ class YOLOV5m(nn.Module):
         return self._gflat[0]
 
     # -- forward -------------------------------------------------------------------------------------
+    # engines (buffers + launch plans) are cached per (batch, height, width, mode).  Multi-scale training visits up to 11
+    # square sizes (320..640 step 32): at bs=64 all of them together hold ~120 GB of activations, so the cache is bounded
+    # by bytes (YB_ENGINE_CACHE_GB, default 100 of the 180 GB), oldest first.
+    _ENGINE_CACHE_BYTES = int(float(os.environ.get("YB_ENGINE_CACHE_GB", "100")) * (1 << 30))
+
     def engine(self, B, H, W, train):
         key = (B, H, W, bool(train))
         e = self._engines.get(key)
         if e is None:
-            if len(self._engines) >= 4:  # multi-scale training visits many shapes: keep the cache bounded
-                self._engines.pop(next(iter(self._engines)))
             e = _Engine(self, B, H, W, train)
+            while self._engines and sum(v.nbytes for v in self._engines.values()) + e.nbytes > self._ENGINE_CACHE_BYTES:
+                self._engines.pop(next(iter(self._engines)))
             self._engines[key] = e
+        else:
+            self._engines[key] = self._engines.pop(key)  # most recently used last
         return e
 
-    def forward(self, x):
-        assert x.shape[2] % 32 == 0 and x.shape[3] % 32 == 0, "Width and Height aren't divisible by 32!"  # model.py:211
+    def forward(self, x, size=None):
+        """x: (B,3,H,W) float32 in [0,1] or uint8.  ``size=(h, w)`` (extension, both % 32 == 0): run the network on the
+        image bilinearly resampled to (h, w) -- the reference's multi_scale() (training_utils.py:11-28, :100) without
+        materialising the resized float image (the resample is fused into the stem's input staging)."""
+        H, W = (int(size[0]), int(size[1])) if size is not None else (x.shape[2], x.shape[3])
+        assert H % 32 == 0 and W % 32 == 0, "Width and Height aren't divisible by 32!"  # model.py:211
         if not (torch.is_tensor(x) and x.is_cuda and self._pflat.is_cuda):
             raise _lib.YBError("YOLOV5m (B200): model and input must be on a CUDA device (no CPU fallback)")
         if x.dtype not in (torch.float32, torch.uint8):
             x = x.float()
         x = x.contiguous()
-        B, _, H, W = x.shape
+        B = x.shape[0]
         self.refresh_packed()
         train = self.training
         eng = self.engine(B, H, W, train)

@@ -15,6 +15,9 @@ step function that mirrors the body of the reference's ``train_loop`` (reference
 One process per GPU; `torch.distributed` (NCCL) is only plumbing.  BatchNorm statistics stay local to each rank, like
 the reference's plain nn.BatchNorm2d (model.py:17).
 """
+import math
+import random
+
 import torch
 import torch.distributed as dist
 
@@ -107,13 +110,27 @@ class GradSync:
                 dist.all_reduce(g[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
 
 
-class TrainStep:
-    """One optimisation step = the body of the reference train_loop (training_utils.py:97-122) for one batch."""
+def multi_scale_size(h, w, target_shape=640, max_stride=32, rng=random):
+    """The output size the reference's multi_scale() draws (training_utils.py:11-28): a random side in
+    [target_shape / 2, target_shape + max_stride) rounded down to a multiple of max_stride for the longer image side,
+    the other side scaled by the same factor and rounded UP to a multiple of max_stride.  Returns (new_h, new_w)."""
+    sz = rng.randrange(int(target_shape * 0.5), int(target_shape + max_stride)) // max_stride * max_stride
+    sf = sz / max(h, w)
+    return tuple(math.ceil(i * sf / max_stride) * max_stride for i in (h, w))
 
-    def __init__(self, model, loss_fn, optimizer, max_norm=10.0, sync=None, loss_scale=1.0):
+
+class TrainStep:
+    """One optimisation step = the body of the reference train_loop (training_utils.py:97-122) for one batch.
+    ``multi_scale=True`` mirrors ``multi_scale_training`` (:100): every batch is resampled to a random size; all ranks
+    of a data-parallel job draw the same size (seeded ``random.Random``), so their step times stay aligned."""
+
+    def __init__(self, model, loss_fn, optimizer, max_norm=10.0, sync=None, loss_scale=1.0, multi_scale=False,
+                 target_shape=640, max_stride=32, seed=0):
         self.model, self.loss_fn, self.opt = model, loss_fn, optimizer
         self.max_norm, self.loss_scale = max_norm, loss_scale
         self.sync = sync if sync is not None else GradSync(model)
+        self.multi_scale, self.target_shape, self.max_stride = multi_scale, target_shape, max_stride
+        self._rng = random.Random(seed)
         model.expose_param_grads = False  # the fused optimiser reads the flat bucket
 
     def __call__(self, images, targets):
@@ -122,8 +139,11 @@ class TrainStep:
         dev = model.flat_params.device
         if not images.is_cuda:
             images = images.to(dev, non_blocking=True)
-        out = model(images)
-        loss = self.loss_fn(out, targets, pred_size=images.shape[2:4])
+        size = None
+        if self.multi_scale:
+            size = multi_scale_size(images.shape[2], images.shape[3], self.target_shape, self.max_stride, self._rng)
+        out = model(images, size=size)
+        loss = self.loss_fn(out, targets, pred_size=size if size is not None else images.shape[2:4])
         if self.loss_scale != 1.0:
             (loss * self.loss_scale).backward()
         else:
