@@ -200,10 +200,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
           const uint64_t a_hi = make_smem_desc(0, 16, (uint32_t)pitch * 128u, 2);
           // tile (ty, tx) starts (16*ty*pitch + 8*tx) pixel rows (x 128 B = x 8 descriptor units) into the patch
           uint32_t tile_off[4];
+          {
+            int ty = 0, tx = 0;  // (ty, tx) = (tt / TW, tt % TW) without the runtime division
 #pragma unroll
-          for (int tt = 0; tt < 4; ++tt) {
-            const int ty = tt / TWl, tx = tt - ty * TWl;
-            tile_off[tt] = (uint32_t)(ty * 16 * pitch + tx * 8) * 8u;
+            for (int tt = 0; tt < 4; ++tt) {
+              tile_off[tt] = (uint32_t)(ty * 16 * pitch + tx * 8) * 8u;
+              if (++tx == TWl) {
+                tx = 0;
+                ++ty;
+              }
+            }
           }
           for (int ch = 0; ch < chunks; ++ch) {
             mbar_wait(&afull[sa], pha);
@@ -271,16 +277,35 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
       const uint32_t aph = (it >> 1) & 1;
       mbar_wait(&tfull_bar[ab], aph);
       tc_fence_after();
-      for (int idx = eg; idx < T * nchunks; idx += kEpiGroups) {
-        const int tt = idx / nchunks, cc = idx - tt * nchunks;
+      // (tile tt, chunk cc) of the flat index idx = tt * nchunks + cc and (ty, tx) of tt advance incrementally: two
+      // runtime integer divisions per chunk were ~100 of the ~300 instructions of a chunk (ncu source page, r1)
+      int tt = 0, cc = eg, ty = 0, tx = 0;
+      while (cc >= nchunks) {
+        cc -= nchunks;
+        ++tt;
+        if (++tx == TWl) {
+          tx = 0;
+          ++ty;
+        }
+      }
+      for (; tt < T; ) {
         const int col0 = tc.nt * BN + cc * 16;
+        const int tt_c = tt, cc_c = cc, ty_c = ty, tx_c = tx;
+        cc += kEpiGroups;
+        while (cc >= nchunks) {
+          cc -= nchunks;
+          ++tt;
+          if (++tx == TWl) {
+            tx = 0;
+            ++ty;
+          }
+        }
         if (col0 >= ea.Cout) continue;
-        const int ty = tt / TWl, tx = tt - ty * TWl;
-        const int h = (tc.hb * THl + ty) * 16 + phh, w = (tc.wb * TWl + tx) * 8 + pw;
+        const int h = (tc.hb * THl + ty_c) * 16 + phh, w = (tc.wb * TWl + tx_c) * 8 + pw;
         const bool valid = h < ea.H && w < ea.W;
         const int64_t opix = o_base + h * os_h + w * os_w;
         const int64_t apix = a_base + h * as_h + w * as_w;
-        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 256 + tt * BN + cc * 16;
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 256 + tt_c * BN + cc_c * 16;
         conv_epilogue_chunk(ea, t_addr, col0, valid, tc.n, h, w, opix, apix, my_stats, lane);
       }
       tc_fence_before();

@@ -60,6 +60,7 @@ int wgrad_max_grid();
 // (128..227) shrinks it so that the CTAs of the HBM-bound BN/SiLU-backward passes (<= 17 KB each) fit on the same SM while
 // a weight-gradient kernel runs on the side stream (yolov5m_b200/model.py, _Engine._wgrad_async).
 size_t wgrad_smem_budget();
+int wgrad_waves();    // YB_WGRAD_WAVES: split-K work items per SM (waves of the persistent grid), default 1
 int wgrad_exact_n();  // YB_WGRAD_EXACT_N (default 1)
 
 // x: conv input (N,H,W,Cin); dy: grad of the conv output (N,H/s,W/s,Cout).

@@ -307,7 +307,7 @@ int wgrad_patch_plan(WgradPlan& pl, const TView& x, const TView& dy, int ks, int
   if (make_box_map(&kp.tmDY, dy, PW, PH) || make_box_map(&kp.tmX, x, PW + 2, PH + 2)) return -1;
   const int base_items = kp.cboxes * kp.m_groups * kp.n_tiles;
   const int sms = wgrad_max_grid();
-  int splits = std::max(1, (2 * sms) / base_items);
+  int splits = std::max(1, (wgrad_waves() * sms) / base_items);
   splits = std::min(splits, std::max(1, kp.ptiles / 8));
   if (max_splits > 0) splits = std::min(splits, max_splits);
   const size_t per_split = (size_t)kp.Mpad * kp.Npad;
