@@ -327,10 +327,20 @@ def run_ours(a):
 
 def main():
     a = parse()
-    if a.impl == "reference":
-        run_reference(a)
-    else:
-        run_ours(a)
+    # the contract is ONE JSON line on stdout: anything a library prints there (e.g. the "NCCL version ..." banner of
+    # ncclCommInit) is routed to stderr -- file descriptor 1 points at stderr while the bench runs, and the JSON line goes
+    # to a private duplicate of the real stdout
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
+    try:
+        if a.impl == "reference":
+            run_reference(a)
+        else:
+            run_ours(a)
+    finally:
+        real_stdout.flush()
 
 
 if __name__ == "__main__":
