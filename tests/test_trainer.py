@@ -89,6 +89,52 @@ def test_fused_clip_adam_matches_torch():
 
 
 @gpu
+def test_adam_state_dict_interoperates_with_torch_adam():
+    """checkpoint["optimizer"] wire format (reference train.py:140-143, utils/utils.py:74-82): the fused optimiser exports
+    the torch.optim.Adam state_dict, a stock torch Adam loads it and continues identically, and the other way round."""
+    from yolov5m_b200.model import YOLOV5m
+    from yolov5m_b200.trainer import Adam
+    m = YOLOV5m(first_out=48, nc=80, anchors=model_ref.ANCHORS, ch=(192, 384, 768)).cuda()
+    opt = Adam(m, lr=5e-4, weight_decay=5e-4)
+    assert opt.state_dict()["state"] == {} and len(opt.state_dict()["param_groups"][0]["params"]) == 243
+    gen = torch.Generator(device="cuda").manual_seed(3)
+
+    def fill():
+        m.flat_grads.copy_(torch.randn(m.flat_grads.numel(), device="cuda", generator=gen) * 0.01)
+    for _ in range(2):
+        fill(); opt.step()
+    sd = opt.state_dict()
+    assert set(sd["state"]) == set(range(243)) and float(sd["state"][0]["step"]) == 2.0
+    p0 = next(m.parameters())
+    assert sd["state"][0]["exp_avg"].shape == p0.shape and sd["state"][0]["exp_avg"].is_contiguous()
+    # fused -> torch
+    ref_p = [p.detach().clone().requires_grad_(True) for p in m.parameters()]
+    ref_opt = torch.optim.Adam(ref_p, lr=1e-3, weight_decay=0.0)   # hyper-parameters come from the loaded dict
+    ref_opt.load_state_dict(sd)
+    assert ref_opt.param_groups[0]["lr"] == 5e-4 and ref_opt.param_groups[0]["weight_decay"] == 5e-4
+    fill()
+    for rp, gv in zip(ref_p, m._grad_views(m.flat_grads)):
+        rp.grad = gv.contiguous().clone()
+    ref_opt.step(); opt.step()
+    for p, rp in zip(m.parameters(), ref_p):
+        assert torch.allclose(p.detach(), rp.detach(), atol=2e-6, rtol=1e-5)
+    # torch -> fused (a fresh fused optimiser resumes from the torch optimiser's state)
+    m2 = YOLOV5m(first_out=48, nc=80, anchors=model_ref.ANCHORS, ch=(192, 384, 768)).cuda()
+    m2.load_state_dict(m.state_dict())
+    opt2 = Adam(m2, lr=1.0, weight_decay=0.0)
+    opt2.load_state_dict(ref_opt.state_dict())
+    assert opt2.step_count == 3 and opt2.lr == 5e-4 and opt2.weight_decay == 5e-4
+    fill()
+    m2.flat_grads.copy_(m.flat_grads)
+    opt.step(); opt2.step()
+    for p2, p1 in zip(m2.parameters(), m.parameters()):  # (the alignment padding of the flat buffers is not state)
+        assert torch.allclose(p2.detach(), p1.detach(), atol=2e-6, rtol=1e-5)
+    # the flat format of earlier versions still loads
+    opt2.load_state_dict({"step": 5, "exp_avg": opt.m, "exp_avg_sq": opt.v})
+    assert opt2.step_count == 5 and torch.equal(opt2.m, opt.m)
+
+
+@gpu
 def test_train_step_runs_and_learns():
     """TrainStep = train_loop body: loss decreases over a few steps on a fixed batch; uint8 and float inputs agree."""
     import yolov5m_b200 as yb

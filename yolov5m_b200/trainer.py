@@ -70,12 +70,56 @@ class Adam:
         model._packed_sig = model._param_signature()  # the bf16 operands are current
 
     def state_dict(self):
-        return {"step": self.step_count, "exp_avg": self.m, "exp_avg_sq": self.v, "lr": self.lr, "betas": self.betas,
-                "eps": self.eps, "weight_decay": self.weight_decay}
+        """The ``torch.optim.Adam.state_dict()`` wire format (what the reference stores under checkpoint["optimizer"],
+        train.py:140-143, and reloads with utils/utils.py:74-82): per-parameter ``step / exp_avg / exp_avg_sq`` in
+        ``model.parameters()`` order plus one param group.  The moment tensors are copies in the parameters' logical
+        (NCHW) layout, so the dict loads into a stock ``torch.optim.Adam`` of the reference model and vice versa."""
+        model = self.model
+        n = len(model._poffs)
+        state = {}
+        if self.step_count > 0:
+            ms, vs = model._grad_views(self.m), model._grad_views(self.v)
+            for i in range(n):
+                state[i] = {"step": torch.tensor(float(self.step_count)), "exp_avg": ms[i].contiguous().clone(),
+                            "exp_avg_sq": vs[i].contiguous().clone()}
+        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.weight_decay,
+                 "amsgrad": False, "maximize": False, "foreach": None, "capturable": False, "differentiable": False,
+                 "fused": None, "params": list(range(n))}
+        return {"state": state, "param_groups": [group]}
 
     def load_state_dict(self, sd):
-        self.step_count = int(sd["step"])
-        self.m.copy_(sd["exp_avg"]); self.v.copy_(sd["exp_avg_sq"])
+        """Accepts the torch.optim.Adam format above (e.g. the "optimizer" entry of a reference checkpoint) or the flat
+        format of earlier versions of this class ({"step", "exp_avg", "exp_avg_sq"} over the flat buffer)."""
+        if "param_groups" not in sd:  # flat format
+            self.step_count = int(sd["step"])
+            self.m.copy_(sd["exp_avg"]); self.v.copy_(sd["exp_avg_sq"])
+            self._step_dev.fill_(self.step_count)
+            return
+        model = self.model
+        n = len(model._poffs)
+        groups = sd["param_groups"]
+        if len(groups) != 1 or len(groups[0]["params"]) != n:
+            raise ValueError(f"yolov5m_b200.Adam: expected one param group with {n} parameters "
+                             f"(got {len(groups)} groups / {sum(len(g['params']) for g in groups)} parameters)")
+        g = groups[0]
+        if g.get("amsgrad") or g.get("maximize"):
+            raise ValueError("yolov5m_b200.Adam: amsgrad / maximize are not supported")
+        self.lr, self.betas, self.eps = float(g["lr"]), tuple(g["betas"]), float(g["eps"])
+        self.weight_decay = float(g["weight_decay"])
+        state = sd["state"]
+        self.m.zero_(); self.v.zero_()
+        steps = set()
+        if state:
+            ms, vs = model._grad_views(self.m), model._grad_views(self.v)
+            for i, pid in enumerate(g["params"]):
+                st = state.get(pid, state.get(str(pid)))
+                if st is None:
+                    continue
+                ms[i].copy_(st["exp_avg"]); vs[i].copy_(st["exp_avg_sq"])
+                steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise ValueError(f"yolov5m_b200.Adam: parameters carry different step counts {sorted(steps)}; the fused step keeps one")
+        self.step_count = steps.pop() if steps else 0
         self._step_dev.fill_(self.step_count)
 
 
