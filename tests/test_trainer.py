@@ -89,6 +89,28 @@ def test_fused_clip_adam_matches_torch():
 
 
 @gpu
+def test_dgrad_operand_repack_layout():
+    """yb_repack_dgrad: every non-stem conv's bf16 dgrad operand is [Cin][tap][Cout_pad] of the fp32 master weight
+    (zero in the padded output channels), bit for bit."""
+    from yolov5m_b200.model import YOLOV5m
+    m = YOLOV5m(first_out=48, nc=80, anchors=model_ref.ANCHORS, ch=(192, 384, 768)).cuda()
+    m.refresh_packed(force=True)
+    torch.cuda.synchronize()
+    checked = 0
+    for r in m._recs:
+        if r.is_stem:
+            continue
+        w = r.conv.weight.detach()                                   # logical (Cout, Cin, k, k)
+        co, ci, kh, kw = w.shape
+        want = torch.zeros(ci, kh * kw, r.cout_pad, device="cuda", dtype=torch.bfloat16)
+        want[:, :, :co] = w.permute(1, 2, 3, 0).reshape(ci, kh * kw, co).to(torch.bfloat16)
+        got = m._wdg[r.wt_off:r.wt_off + want.numel()].view_as(want)
+        assert torch.equal(got, want), r.name
+        checked += 1
+    assert checked == 81
+
+
+@gpu
 def test_adam_state_dict_interoperates_with_torch_adam():
     """checkpoint["optimizer"] wire format (reference train.py:140-143, utils/utils.py:74-82): the fused optimiser exports
     the torch.optim.Adam state_dict, a stock torch Adam loads it and continues identically, and the other way round."""

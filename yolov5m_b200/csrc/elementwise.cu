@@ -58,6 +58,20 @@ __device__ __forceinline__ void st8(bf16* p, const V8& a) {
   for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(a.v[2 * j], a.v[2 * j + 1]);
   *reinterpret_cast<uint4*>(p) = r;
 }
+// 16 channels (32 bytes, 32-byte aligned) in ONE store: a full L2 sector
+__device__ __forceinline__ void st16(bf16* p, const V8& a, const V8& b) {
+  uint4 r0, r1;
+  __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&r0);
+  __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&r1);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    h0[j] = __floats2bfloat162_rn(a.v[2 * j], a.v[2 * j + 1]);
+    h1[j] = __floats2bfloat162_rn(b.v[2 * j], b.v[2 * j + 1]);
+  }
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(r0.x), "r"(r0.y), "r"(r0.z),
+               "r"(r0.w), "r"(r1.x), "r"(r1.y), "r"(r1.z), "r"(r1.w)
+               : "memory");
+}
 __device__ __forceinline__ V8 cvt8(const uint4& r) {
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
   V8 o;
@@ -489,28 +503,34 @@ __global__ void maxpool5_fwd_kernel(const bf16* __restrict__ x, long x_pitch, in
     const long t = pix / W;
     const int h = (int)(t % H);
     const long n = t / H;
+    // fully unrolled, branch-free window: every tap loads from a clamped (always valid) address, so the 25 loads are
+    // independent and in flight together; a tap outside the image is masked out of the comparison.  `arg` starts at the
+    // first in-image tap, which is what "first max wins" yields when every value is -inf.
     float best[8];
     int arg[8];
+    const int arg0 = max(0, 2 - h) * 5 + max(0, 2 - w);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       best[j] = -INFINITY;
-      arg[j] = 0;
+      arg[j] = arg0;
     }
-    bool first = true;
+#pragma unroll
     for (int kh = 0; kh < 5; ++kh) {
       const int ih = h + kh - 2;
-      if (ih < 0 || ih >= H) continue;
+      const bool okh = ih >= 0 && ih < H;
+      const int ihc = min(max(ih, 0), H - 1);
+#pragma unroll
       for (int kw = 0; kw < 5; ++kw) {
         const int iw = w + kw - 2;
-        if (iw < 0 || iw >= W) continue;
-        const V8 v = ld8(x + ((n * H + ih) * W + iw) * x_pitch + c);
+        const bool ok = okh && iw >= 0 && iw < W;
+        const int iwc = min(max(iw, 0), W - 1);
+        const V8 v = ld8(x + ((n * H + ihc) * W + iwc) * x_pitch + c);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          if (first || v.v[j] > best[j] || v.v[j] != v.v[j]) {  // first max wins; NaN propagates (ATen max_pool2d)
+          if (ok && (v.v[j] > best[j] || v.v[j] != v.v[j])) {  // first max wins; NaN propagates (ATen max_pool2d)
             best[j] = v.v[j];
             arg[j] = kh * 5 + kw;
           }
-        first = false;
       }
     }
     V8 o;
@@ -541,20 +561,24 @@ __global__ void maxpool5_bwd_kernel(const bf16* __restrict__ dy, long dy_pitch, 
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    for (int kh = 0; kh < 5; ++kh) {
+#pragma unroll
+    for (int kh = 0; kh < 5; ++kh) {  // unrolled and branch-free like the forward pass (clamped addresses, masked taps)
       const int oh = h - kh + 2;
-      if (oh < 0 || oh >= H) continue;
+      const bool okh = oh >= 0 && oh < H;
+      const int ohc = min(max(oh, 0), H - 1);
+#pragma unroll
       for (int kw = 0; kw < 5; ++kw) {
         const int ow = w - kw + 2;
-        if (ow < 0 || ow >= W) continue;
-        const long op = (n * H + oh) * W + ow;
+        const bool ok = okh && ow >= 0 && ow < W;
+        const int owc = min(max(ow, 0), W - 1);
+        const long op = (n * H + ohc) * W + owc;
         const uint2 pk = *reinterpret_cast<const uint2*>(argmax + op * C + c);
         const V8 g = ld8(dy + op * dy_pitch + c);
         const unsigned k = kh * 5 + kw;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const unsigned a = ((j < 4 ? pk.x : pk.y) >> (8 * (j & 3))) & 0xffu;
-          if (a == k) acc[j] += g.v[j];
+          if (ok && a == k) acc[j] += g.v[j];
         }
       }
     }
@@ -662,23 +686,14 @@ __global__ void prep_input_kernel(const T* __restrict__ x, int N, int H, int W, 
       hi.v[j] = v[8 + j];
       z.v[j] = 0.f;
     }
+    // every tap slot is 16 channels = 32 bytes = one L2 sector, 32-byte aligned: one st.global.v8 per slot (two 16-byte
+    // stores would be two half-sector writes)
     bf16* me = out + i * 48;
-    st8(me + 16, lo);  // centre tap of this pixel
-    st8(me + 24, hi);
-    if (wo + 1 < Wo) {  // left tap (kw = 0) of the right neighbour
-      st8(me + 48, lo);
-      st8(me + 56, hi);
-    } else {            // last column: its right tap is outside the image
-      st8(me + 32, z);
-      st8(me + 40, z);
-    }
-    if (wo > 0) {       // right tap (kw = 2) of the left neighbour
-      st8(me - 48 + 32, lo);
-      st8(me - 48 + 40, hi);
-    } else {            // first column: its left tap is outside the image
-      st8(me, z);
-      st8(me + 8, z);
-    }
+    st16(me + 16, lo, hi);  // centre tap of this pixel
+    if (wo + 1 < Wo) st16(me + 48, lo, hi);  // left tap (kw = 0) of the right neighbour
+    else st16(me + 32, z, z);                // last column: its right tap is outside the image
+    if (wo > 0) st16(me - 48 + 32, lo, hi);  // right tap (kw = 2) of the left neighbour
+    else st16(me, z, z);                     // first column: its left tap is outside the image
   }
 }
 

@@ -333,10 +333,27 @@ __global__ void __launch_bounds__(256) loss_bwd_kernel(const __grid_constant__ L
     float v8[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v8[j] = 0.f;
-    for (int a = 0; a < P.na; ++a) {
+    // the per-anchor loads (chain head, objectness logit) of all anchors are issued up front: the pass is bound by
+    // the latency of these dependent loads, not by bandwidth
+    constexpr int kMaxNa = 4;
+    int heads[kMaxNa];
+    float xs[kMaxNa];
+#pragma unroll
+    for (int a = 0; a < kMaxNa; ++a) {
+      heads[a] = 0;
+      xs[a] = 0.f;
+      if (a < P.na) {
+        const long cell = (b * P.na + a) * hw + sp;
+        heads[a] = L.cell_head[cell];
+        xs[a] = L.p[cell * P.no + 4];
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < kMaxNa; ++a) {
+      if (a >= P.na) break;
       const long cell = (b * P.na + a) * hw + sp;
-      const int head = L.cell_head[cell];
-      const float x = L.p[cell * P.no + 4];
+      const int head = heads[a];
+      const float x = xs[a];
       float tobj = 0.f;
       // fp32 row of this anchor: lane owns o = lane, lane+32, lane+64
       float f0 = 0.f, f1 = 0.f, f2 = 0.f;
@@ -527,6 +544,7 @@ int yb_loss_bwd(const yb_loss_level* levels, int nl, int B, int na, int no, int6
   for (int i = 0; i < nl; ++i)
     YB_REQUIRE(levels[i].grad_bf16 == nullptr || (cpad % 8 == 0 && cpad >= na * no && cpad <= 256),
                "loss_bwd: cpad=%d must be a multiple of 8 in [na*no, 256]", cpad);
+  YB_REQUIRE(na <= 4, "loss_bwd: na=%d > 4 anchors per level", na);
   long pix = 0;
   for (int i = 0; i < nl; ++i) pix += (long)B * levels[i].H * levels[i].W;
   const int blocks = (int)std::max<long>(1, std::min<long>((pix + 7) / 8, (long)sm_count() * 16));

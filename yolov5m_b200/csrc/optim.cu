@@ -26,24 +26,59 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict
 
 // table[l] = {src_off, dst_off, Cout, taps, Cin, Cout_pad, dst_cum_begin, dst_cum_end}
 // dst[dst_off + (ci*taps + tap)*Cout_pad + co] = co < Cout ? src[src_off + (co*taps + tap)*Cin + ci] : 0
-__global__ void repack_dgrad_kernel(const float* __restrict__ src, bf16* __restrict__ dst,
-                                    const long long* __restrict__ table, int nlayers, long total) {
-  const long stride = (long)gridDim.x * blockDim.x;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    int lo = 0, hi = nlayers - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (i >= table[mid * 8 + 7]) lo = mid + 1; else hi = mid;
+// A per-(layer, tap) [Cout x Cin] -> [Cin x Cout_pad] transpose in 32 x 32 tiles through shared memory: 128-byte coalesced
+// fp32 reads along ci, 64-byte coalesced bf16 writes along co.  (The first version decoded every element on its own -- a
+// binary search over the layer table, two 64-bit divisions and a 4-byte gather whose neighbours sit taps*Cin*4 bytes apart:
+// 0.29 ms per step for 21 M weights.)  Persistent blocks walk the tile list; the layer of a tile is found by advancing a
+// cursor, since tile ids are ordered by layer.
+__device__ __forceinline__ long repack_layer_tiles(const long long* t) {
+  const long cout_pad = t[5], taps = t[3], cin = t[4];
+  return taps * ((cout_pad + 31) / 32) * ((cin + 31) / 32);
+}
+__global__ void __launch_bounds__(256) repack_dgrad_kernel(const float* __restrict__ src, bf16* __restrict__ dst,
+                                                           const long long* __restrict__ table, int nlayers) {
+  __shared__ float tile[32][33];
+  __shared__ long s_info[2];  // layer of the current tile, tile index inside that layer
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 warps: warp w handles tile rows w, w + 8, w + 16, w + 24
+  int layer = 0;        // cursor (thread 0 only)
+  long layer_begin = 0;  // first tile id of `layer`
+  for (long t = blockIdx.x;; t += gridDim.x) {
+    if (threadIdx.x == 0) {
+      while (layer < nlayers) {
+        const long n = repack_layer_tiles(table + layer * 8);
+        if (t < layer_begin + n) break;
+        layer_begin += n;
+        ++layer;
+      }
+      s_info[0] = layer;
+      s_info[1] = t - layer_begin;
     }
-    const long long* t = table + lo * 8;
-    const long e = i - t[6];
-    const int cop = (int)t[5], taps = (int)t[3], cin = (int)t[4], cout = (int)t[2];
-    const int co = (int)(e % cop);
-    const long r = e / cop;
-    const int tap = (int)(r % taps);
-    const int ci = (int)(r / taps);
-    const float v = co < cout ? src[t[0] + ((long)co * taps + tap) * cin + ci] : 0.f;
-    dst[t[1] + e] = __float2bfloat16(v);
+    __syncthreads();
+    const int l = (int)s_info[0];
+    long rem = s_info[1];
+    if (l >= nlayers) break;  // uniform: past the last tile
+    const long long* e = table + l * 8;
+    const int cout = (int)e[2], taps = (int)e[3], cin = (int)e[4], cop = (int)e[5];
+    const int tiles_ci = (cin + 31) / 32, tiles_co = (cop + 31) / 32;
+    const int tci = (int)(rem % tiles_ci);
+    rem /= tiles_ci;
+    const int tco = (int)(rem % tiles_co);
+    const int tap = (int)(rem / tiles_co);
+    const int co0 = tco * 32, ci0 = tci * 32;
+    const float* sp = src + e[0];
+    bf16* dp = dst + e[1];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int co = co0 + ty + 8 * k, ci = ci0 + tx;
+      tile[ty + 8 * k][tx] = (co < cout && ci < cin) ? sp[((long)co * taps + tap) * cin + ci] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int ci = ci0 + ty + 8 * k, co = co0 + tx;
+      if (ci < cin && co < cop) dp[((long)ci * taps + tap) * cop + co] = __float2bfloat16(tile[tx][ty + 8 * k]);
+    }
+    // the next iteration's first __syncthreads orders these tile reads before the next tile's writes
   }
 }
 
@@ -152,8 +187,9 @@ int yb_cast_bf16(const float* src, void* dst, int64_t n, void* stream) {
 }
 
 int yb_repack_dgrad(const float* src, void* dst, const int64_t* table, int nlayers, int64_t total, void* stream) {
-  repack_dgrad_kernel<<<blocks_for(total), 256, 0, ST(stream)>>>(src, reinterpret_cast<bf16*>(dst),
-                                                                 reinterpret_cast<const long long*>(table), nlayers, total);
+  (void)total;
+  repack_dgrad_kernel<<<148 * 8, 256, 0, ST(stream)>>>(src, reinterpret_cast<bf16*>(dst),
+                                                       reinterpret_cast<const long long*>(table), nlayers);
   YB_LAUNCHED();
   return 0;
 }
