@@ -90,4 +90,6 @@ def ptr(t):
 
 
 def stream():
+    if not torch.cuda.is_available():
+        raise YBError("yolov5m_b200: a CUDA device is required (there is no CPU / PyTorch fallback for the hot path)")
     return torch.cuda.current_stream().cuda_stream
