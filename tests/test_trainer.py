@@ -196,3 +196,31 @@ def test_multi_scale_size_follows_reference_rule():
             assert nh % 32 == 0 and nw % 32 == 0 and max(nh, nw) == sz and 320 <= sz <= 640
             seen.add(sz)
         assert seen == set(range(320, 641, 32))
+
+
+def test_chunk_ready_after_schedule():
+    """Overlapped all-reduce: a bucket chunk is released right after the last backward op that writes into it."""
+    from yolov5m_b200.trainer import chunk_ready_after
+    writes = {0: [(90, 10)], 1: [(50, 40)], 2: [], 3: [(0, 50)], 4: [(60, 0)]}
+    assert chunk_ready_after(writes, [0, 25, 50, 75, 100]) == {1: [2, 3], 3: [0, 1]}
+    # a chunk nobody writes (alignment padding only) is released with the first op
+    assert chunk_ready_after({5: [(0, 10)], 7: [(10, 10)]}, [0, 10, 20, 30]) == {5: [0, 2], 7: [1]}
+
+
+@gpu
+def test_engine_grad_chunk_schedule_covers_the_bucket():
+    import yolov5m_b200 as yb
+    from yolov5m_b200.trainer import GradSync
+    m = yb.YOLOV5m(first_out=48, nc=80, anchors=yb.ANCHORS, ch=(192, 384, 768)).cuda().train()
+    eng = m.engine(2, 64, 64, True)
+    # every parameter slice is written by exactly one backward op
+    got = sorted(sl for w in eng.bwd_writes.values() for sl in w)
+    want = sorted((o, n) for o, n in m._poffs)
+    assert got == want
+    b = GradSync(m, chunks=4)._bounds(m.flat_params.numel())
+    sched = eng.grad_chunk_schedule(b)
+    order = [c for i in sorted(sched) for c in sched[i]]
+    assert sorted(order) == [0, 1, 2, 3]
+    first = {c: i for i in sched for c in sched[i]}
+    assert first[3] < first[0], "the tail of the bucket (head / neck gradients) must be complete long before its head"
+    assert max(first.values()) <= len(eng.bwd_ops) - 1

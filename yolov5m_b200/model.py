@@ -173,6 +173,8 @@ class _Engine:
         self.dev = net._pflat.device
         self.L = _lib.lib()
         self.fwd_ops, self.bwd_ops, self.tape = [], [], []
+        self.bwd_writes = {}      # backward op index -> [(offset, length)] slices of the flat gradient bucket it writes
+        self.on_grad_chunks = None  # (schedule {op index: [chunk]}, callback(chunk, gflat)) set by trainer.GradSync
         self.prof = None
         self.conv_flops = {"fwd": 0.0, "dgrad": 0.0, "wgrad": 0.0}  # algorithmic FLOPs of the reference convs per step
         self.plans = []
@@ -393,6 +395,19 @@ class _Engine:
             self.nbytes += self._dy_elems * 2 * ndy
             self._build_backward()
 
+    def _add_bwd_op(self, op, writes):
+        """backward op that writes the parameter-gradient slices `writes` = [(offset, length), ...] of the flat bucket"""
+        self.bwd_writes[len(self.bwd_ops)] = writes
+        self.bwd_ops.append(op)
+
+    def grad_chunk_schedule(self, bounds):
+        """For the all-reduce chunks [bounds[c], bounds[c+1]) of the flat gradient bucket: {backward op index: [chunks that
+        are complete once that op has been issued]} -- a chunk is complete after the LAST op (in execution order) that
+        writes a slice intersecting it.  (Data-parallel overlap: yolov5m_b200.trainer.GradSync reduces a chunk while the
+        rest of the backward pass still runs.)"""
+        from .trainer import chunk_ready_after
+        return chunk_ready_after(self.bwd_writes, bounds)
+
     # -- backward construction (reverse tape); gradient fan-in is resolved statically
     def _contrib_state(self, view):
         w = view.buf.gw[view.c0:view.c0 + view.C]
@@ -453,7 +468,7 @@ class _Engine:
                     _lib.check(L.yb_reduce_rows(redp, rows.value, 2 * HEAD_PAD, r.cout, g + 4 * r.bias_off, 0, st))
                     self._conv(dplan, st, flops, "dgrad")
                     self._wgrad_async(evs, wplan, st, flops, g + 4 * r.w_off, r.cout, None, 0)
-                self.bwd_ops.append(op)
+                self._add_bwd_op(op, [(r.bias_off, r.cout), (r.w_off, r.cout * r.cin)])
             elif kind == "pool":
                 _, src, dst, am = rec
                 self._flush_pending(dst)
@@ -523,7 +538,7 @@ class _Engine:
                     if dplan is not None:
                         self._conv(dplan, st, flops, "dgrad")
                     self._wgrad_async(evs, wplan, st, flops, g + 4 * r.w_off, C, mapp, 0)
-                self.bwd_ops.append(op)
+                self._add_bwd_op(op, [(r.g_off, C), (r.b_off, C), (r.w_off, r.conv.weight.numel())])
 
     # -- execution
     def run_forward(self, x):
@@ -544,8 +559,12 @@ class _Engine:
         g = gflat.data_ptr()
         self._main = torch.cuda.current_stream(self.dev)
         self._side_on = self.side is not None and self.prof is None  # the per-kernel timing pass stays on one stream
-        for op in self.bwd_ops:
+        hook = self.on_grad_chunks if not self._side_on and self.prof is None else None
+        for i, op in enumerate(self.bwd_ops):
             op(st, g)
+            if hook is not None and i in hook[0]:
+                for c in hook[0][i]:
+                    hook[1](c, gflat)  # this chunk of the bucket is final: its all-reduce overlaps the remaining ops
         if self._side_on:
             self._main.wait_stream(self.side)  # every weight gradient is in the bucket before all-reduce / optimiser
 

@@ -16,6 +16,7 @@ One process per GPU; `torch.distributed` (NCCL) is only plumbing.  BatchNorm sta
 the reference's plain nn.BatchNorm2d (model.py:17).
 """
 import math
+import os
 import random
 
 import torch
@@ -123,6 +124,25 @@ class Adam:
         self._step_dev.fill_(self.step_count)
 
 
+def chunk_ready_after(writes, bounds):
+    """writes: {op index: [(offset, length), ...]} -- the bucket slices each backward op writes, ops executed in index
+    order; bounds: ascending chunk boundaries.  Returns {op index: [chunk, ...]}: chunk c = [bounds[c], bounds[c+1]) is
+    complete right after the last op that writes into it (chunks nobody writes are ready after the first op)."""
+    nchunks = len(bounds) - 1
+    last = [min(writes) if writes else 0] * nchunks
+    for i, sl in writes.items():
+        for off, n in sl:
+            if n <= 0:
+                continue
+            for c in range(nchunks):
+                if off < bounds[c + 1] and off + n > bounds[c]:
+                    last[c] = max(last[c], i)
+    out = {}
+    for c, i in enumerate(last):
+        out.setdefault(i, []).append(c)
+    return out
+
+
 class GradSync:
     """Data-parallel gradient exchange: one all-reduce (sum) of the flat fp32 gradient bucket per step, split into a few
     large chunks so the collective is not latency-bound.  The 1/world_size average is folded into the
@@ -132,6 +152,7 @@ class GradSync:
         self.model, self.group = model, group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.chunks = max(1, chunks)
+        self._comm, self._b, self._ready, self._next = None, None, set(), -1
 
     def broadcast_parameters(self, src=0):
         if self.world > 1:
@@ -141,17 +162,58 @@ class GradSync:
             if self.model.flat_params.is_cuda:
                 self.model.refresh_packed(force=True)
 
+    def _bounds(self, n):
+        per = (n + self.chunks - 1) // self.chunks
+        return [min(n, c * per) for c in range(self.chunks + 1)]
+
     def all_reduce(self, grads=None):
         if self.world == 1:
             return
         g = self.model.flat_grads if grads is None else grads
-        n = g.numel()
-        per = (n + self.chunks - 1) // self.chunks
+        b = self._bounds(g.numel())
         # gradients are produced head-first (end of the bucket first): reduce from the tail
         for c in reversed(range(self.chunks)):
-            lo, hi = c * per, min(n, (c + 1) * per)
-            if hi > lo:
-                dist.all_reduce(g[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+            if b[c + 1] > b[c]:
+                dist.all_reduce(g[b[c]:b[c + 1]], op=dist.ReduceOp.SUM, group=self.group)
+
+    # -- overlapped form (YB_OVERLAP_AR=1; off by default): a chunk is reduced on a communication stream as soon as the
+    #    backward pass has issued the last kernel that writes into it, while the remaining layers' backward still runs.
+    #    Measured on 2 x B200 (profiles/ab_overlap_allreduce_r1.json): identical loss, 28.49 vs 28.45 ms/step -- the
+    #    collective of the 85 MB bucket costs ~0.5 ms after the backward pass and is not cheaper under it (the NCCL CTAs
+    #    wait for SMs behind the persistent conv CTAs), so the simple post-backward form stays the default.
+    def attach(self, engine):
+        """install the chunk-ready hook on a training engine (idempotent); returns False when overlap is off"""
+        if self.world == 1 or os.environ.get("YB_OVERLAP_AR", "0") != "1" or not self.model.flat_params.is_cuda:
+            engine.on_grad_chunks = None
+            return False
+        if engine.on_grad_chunks is None or engine.on_grad_chunks[1] != self._chunk_ready:
+            self._b = self._bounds(self.model.flat_params.numel())
+            engine.on_grad_chunks = (engine.grad_chunk_schedule(self._b), self._chunk_ready)
+        if self._comm is None:
+            self._comm = torch.cuda.Stream()
+        self._ready, self._next = set(), self.chunks - 1
+        return True
+
+    def _chunk_ready(self, c, gflat):
+        """Chunks are handed to NCCL strictly from the last one down (every rank must issue the same sequence of
+        collectives, whatever order its backward pass completes them in): chunk c goes out once it and all later chunks
+        are complete."""
+        self._ready.add(c)
+        main = torch.cuda.current_stream()
+        while self._next >= 0 and self._next in self._ready:
+            k = self._next
+            self._next -= 1
+            if self._b[k + 1] > self._b[k]:
+                self._comm.wait_stream(main)  # everything issued so far, i.e. all writers of chunks >= k
+                with torch.cuda.stream(self._comm):
+                    dist.all_reduce(gflat[self._b[k]:self._b[k + 1]], op=dist.ReduceOp.SUM, group=self.group)
+
+    def finish(self, gflat):
+        """after backward: reduce whatever the hook did not see and make the main stream wait for the collectives"""
+        for c in range(self.chunks - 1, -1, -1):
+            if c not in self._ready:
+                self._chunk_ready(c, gflat)
+        torch.cuda.current_stream().wait_stream(self._comm)
 
 
 def multi_scale_size(h, w, target_shape=640, max_stride=32, rng=random):
@@ -188,11 +250,15 @@ class TrainStep:
             size = multi_scale_size(images.shape[2], images.shape[3], self.target_shape, self.max_stride, self._rng)
         out = model(images, size=size)
         loss = self.loss_fn(out, targets, pred_size=size if size is not None else images.shape[2:4])
+        overlapped = self.sync.world > 1 and self.sync.attach(out[0]._yb_engine)
         if self.loss_scale != 1.0:
             (loss * self.loss_scale).backward()
         else:
             loss.backward()
-        self.sync.all_reduce()
+        if overlapped:
+            self.sync.finish(model.flat_grads)  # chunks were all-reduced while the backward pass ran
+        else:
+            self.sync.all_reduce()
         self.opt.step(grad_scale=1.0 / (self.loss_scale * self.sync.world), max_norm=self.max_norm)
         self.opt.zero_grad(set_to_none=True)
         return loss
