@@ -249,11 +249,11 @@ def run_ours(a):
             tot = 0.0
             for i in range(n):
                 k = i % nbuf
-                if i + 1 < n:
-                    prefetch(i + 1)
                 torch.cuda.current_stream().wait_event(ready[k])
                 ls = step(stage_i[k], stage_t[k])
                 consumed[k].record()
+                if i + 1 < n:
+                    prefetch(i + 1)  # queued after this step's launches: the copy runs under step i, off its critical path
                 tot += float(ls.item())  # device -> host read of the step's result, every step
             return tot
 
