@@ -135,8 +135,9 @@ int yb_prep_input(const void* x, int dtype, int N, int H, int W, void* out, void
  * (utils/training_utils.py:11-28: F.interpolate(img, size=(H,W), mode="bilinear", align_corners=False) of the float image);
  * the resized float image is never materialised */
 int yb_prep_input_resized(const void* x, int dtype, int N, int Hs, int Ws, int H, int W, void* out, void* stream);
-/* dense gradient of a head output (B,na,H,W,no) fp32 -> bf16 NHWC (B,H,W,Cpad), channel a*no+o (model.py:173 backward) */
-int yb_head_grad_pack(const float* g, int B, int na, int H, int W, int no, void* dy, int Cpad, void* stream);
+/* dense gradient of a head output (B,na,H,W,no) fp32 -> bf16 NHWC (B,H,W,Cpad), channel a*no+o (model.py:173 backward);
+ * accumulate = 1 adds to what dy already holds (a second gradient contribution to the same head output) */
+int yb_head_grad_pack(const float* g, int B, int na, int H, int W, int no, void* dy, int Cpad, int accumulate, void* stream);
 
 /* ---- parameter packing + optimiser tail on the flat fp32 master / gradient buffers ------------------------------
  * The master weights stay in the reference's state_dict tensors (fp32, conv weights channels-last = [Cout][kh*kw][Cin]),
@@ -154,7 +155,11 @@ int yb_repack_dgrad(const float* src, void* dst, const int64_t* table, int nlaye
 int yb_repack_stem(const float* w6, void* w3, int Cout, void* stream);
 int yb_grad_norm(const float* g, int64_t n, float grad_scale, float* partial, int partial_len, float* norm_out,
                  void* stream);
-int yb_counter_inc(int64_t* counter, void* stream);
+/* counter += 1 unless norm (optional, device) is inf / NaN: a step with non-finite gradients is skipped like
+ * GradScaler.step (training_utils.py:119); yb_adam_step given the same norm leaves p / m / v / w_bf16 untouched then */
+int yb_counter_inc(int64_t* counter, const float* norm, void* stream);
+/* dst += src over a flat fp32 bucket: gradient accumulation over micro-batches (training_utils.py:88-90,:116) */
+int yb_accumulate_f32(float* dst, const float* src, int64_t n, void* stream);
 int yb_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                  float weight_decay, int64_t step, const int64_t* step_dev, float grad_scale, float max_norm,
                  const float* norm, void* w_bf16, void* stream);

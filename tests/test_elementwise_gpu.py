@@ -181,7 +181,7 @@ def test_upsample_add_prep_pack():
     # dense head gradient repack
     gh = torch.randn(2, 3, 4, 6, 85, generator=g)
     dy = torch.ones(2, 4, 6, 256, device="cuda", dtype=torch.bfloat16)
-    _lib.check(L.yb_head_grad_pack(_lib.ptr(gh.cuda()), 2, 3, 4, 6, 85, _lib.ptr(dy), 256, _lib.stream()))
+    _lib.check(L.yb_head_grad_pack(_lib.ptr(gh.cuda()), 2, 3, 4, 6, 85, _lib.ptr(dy), 256, 0, _lib.stream()))
     want = torch.zeros(2, 4, 6, 256)
     want[..., :255] = gh.permute(0, 2, 3, 1, 4).reshape(2, 4, 6, 255)
     assert torch.equal(dy.float().cpu(), want.to(torch.bfloat16).float())

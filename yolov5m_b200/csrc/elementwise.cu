@@ -699,7 +699,7 @@ __global__ void prep_input_kernel(const T* __restrict__ x, int N, int H, int W, 
 
 // g (B,na,H,W,no) fp32 -> dy (B,H,W,Cpad) bf16, channel a*no+o; channels >= na*no are zero
 __global__ void head_grad_pack_kernel(const float* __restrict__ g, int na, long hw, int no, bf16* __restrict__ dy, int Cpad,
-                                      long total) {
+                                      long total, int accumulate) {
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int c = (int)(i % Cpad);
     const long t = i / Cpad;
@@ -709,6 +709,7 @@ __global__ void head_grad_pack_kernel(const float* __restrict__ g, int na, long 
       const int a = c / no, o = c - a * no;
       v = g[((b * na + a) * hw + pix) * no + o];
     }
+    if (accumulate) v += __bfloat162float(dy[i]);
     dy[i] = __float2bfloat16(v);
   }
 }
@@ -917,10 +918,10 @@ int yb_prep_input_resized(const void* x, int dtype, int N, int Hs, int Ws, int H
   return 0;
 }
 
-int yb_head_grad_pack(const float* g, int B, int na, int H, int W, int no, void* dy, int Cpad, void* stream) {
+int yb_head_grad_pack(const float* g, int B, int na, int H, int W, int no, void* dy, int Cpad, int accumulate, void* stream) {
   YB_REQUIRE(Cpad >= na * no, "head_grad_pack: Cpad");
   const long total = (long)B * H * W * Cpad;
-  head_grad_pack_kernel<<<ew_blocks(total), 256, 0, ST(stream)>>>(g, na, (long)H * W, no, B16(dy), Cpad, total);
+  head_grad_pack_kernel<<<ew_blocks(total), 256, 0, ST(stream)>>>(g, na, (long)H * W, no, B16(dy), Cpad, total, accumulate);
   LAUNCH_OK();
   return 0;
 }

@@ -123,7 +123,24 @@ __global__ void sqnorm_partial_kernel(const float* __restrict__ g, long n, float
 }
 
 // norm_out[0] = grad_scale * sqrt(sum partial)  (the norm of the UNSCALED, averaged gradient)
-__global__ void counter_inc_kernel(long long* c) { c[0] += 1; }
+// the optimiser's step counter advances only when the gradient norm is finite: a step with inf / NaN gradients is skipped
+// entirely, like GradScaler.step (utils/training_utils.py:119)
+__global__ void counter_inc_kernel(long long* c, const float* norm) {
+  if (norm == nullptr || isfinite(norm[0])) c[0] += 1;
+}
+
+// dst += src over the flat fp32 gradient bucket (gradient accumulation over micro-batches, training_utils.py:88-90,116)
+__global__ void accumulate_f32_kernel(float* __restrict__ dst, const float* __restrict__ src, long n) {
+  const long n4 = n >> 2;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 a = reinterpret_cast<float4*>(dst)[i];
+    const float4 b = reinterpret_cast<const float4*>(src)[i];
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    reinterpret_cast<float4*>(dst)[i] = a;
+  }
+  for (long i = (n4 << 2) + (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] += src[i];
+}
 
 __global__ void sqnorm_final_kernel(const float* __restrict__ partial, int n, float grad_scale, float* __restrict__ norm_out) {
   double s = 0.0;
@@ -143,6 +160,9 @@ __global__ void adam_step_kernel(float* __restrict__ p, const float* __restrict_
     bc1 = 1.f - (float)pow((double)b1, t);
     bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, t));
   }
+  // inf / NaN gradients (norm is computed from sum g^2, so any non-finite element makes it non-finite): skip the whole
+  // update -- parameters, moments and bf16 operands stay as they are (GradScaler.step semantics, training_utils.py:119)
+  if (norm != nullptr && !isfinite(norm[0])) return;
   float clip = 1.f;
   if (max_norm > 0.f && norm != nullptr) clip = fminf(1.f, max_norm / (norm[0] + 1e-6f));
   const float gs = grad_scale * clip;
@@ -211,8 +231,14 @@ int yb_grad_norm(const float* g, int64_t n, float grad_scale, float* partial, in
   return 0;
 }
 
-int yb_counter_inc(int64_t* counter, void* stream) {
-  counter_inc_kernel<<<1, 1, 0, ST(stream)>>>(reinterpret_cast<long long*>(counter));
+int yb_counter_inc(int64_t* counter, const float* norm, void* stream) {
+  counter_inc_kernel<<<1, 1, 0, ST(stream)>>>(reinterpret_cast<long long*>(counter), norm);
+  YB_LAUNCHED();
+  return 0;
+}
+
+int yb_accumulate_f32(float* dst, const float* src, int64_t n, void* stream) {
+  accumulate_f32_kernel<<<blocks_for(n / 4 + 1), 256, 0, ST(stream)>>>(dst, src, n);
   YB_LAUNCHED();
   return 0;
 }

@@ -56,6 +56,23 @@ class _Workspace:
             lv.cell_head, lv.obj_partial = self.cell_head[i].data_ptr(), self.obj_partial[i].data_ptr()
 
 
+class _Lease:
+    """Marks a workspace busy for as long as a backward pass can still need it.  Held by the autograd node (ctx): released by
+    backward, or -- when the graph is dropped without a backward (validation loss, logging) -- by the node's destruction, so
+    forward-only evaluations never strand a workspace in the pool."""
+
+    def __init__(self, ws):
+        self.ws = ws
+        ws.busy = True
+
+    def release(self):
+        if self.ws is not None:
+            self.ws.busy = False
+            self.ws = None
+
+    __del__ = release
+
+
 class _LossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, owner, targets, *p):
@@ -63,8 +80,9 @@ class _LossFn(torch.autograd.Function):
         ctx.owner, ctx.ws, ctx.fast = owner, ws, fast
         ctx.shapes = [tuple(t.shape) for t in p]
         ctx.p = p  # the logits are re-read by the backward kernel (objectness sigmoid)
-        ws.busy = True
-        owner.last_parts = ws.out4[1:4]
+        # only a differentiable evaluation keeps the workspace (under no_grad / detached inputs nothing can call backward)
+        ctx.lease = _Lease(ws) if any(ctx.needs_input_grad[2:]) else None
+        owner.last_parts = ws.out4[1:4].clone()
         return ws.out4[0:1].clone()
 
     @staticmethod
@@ -74,6 +92,8 @@ class _LossFn(torch.autograd.Function):
         gout = gout.to(torch.float32).contiguous()
         grads = []
         eng = ctx.fast
+        if eng is not None and eng.head_ready:
+            eng = None  # a second loss on the same outputs: hand autograd a dense gradient, _NetFn.backward adds it in
         for i, pi in enumerate(ctx.p):
             lv = ws.levels[i]
             lv.p = pi.data_ptr()
@@ -90,7 +110,8 @@ class _LossFn(torch.autograd.Function):
                                  owner.lambda_obj, owner.lambda_class, gout.data_ptr(), cpad, st))
         if eng is not None:
             eng.head_ready = True
-        ws.busy = False
+        if ctx.lease is not None:
+            ctx.lease.release()
         return (None, None) + tuple(grads)
 
 
@@ -184,7 +205,8 @@ class ComputeLoss:
             if t2 is not t and hasattr(t, "_yb_engine"):
                 t2._yb_engine = None
             pc.append(t2)
-        loss = _LossFn.apply(self, targets, *pc)
+        with torch.cuda.device(dev):  # launches go to the predictions' device, whatever the current device is
+            loss = _LossFn.apply(self, targets, *pc)
         if self.save_logs and batch_idx is not None and batch_idx % 100 == 0:  # ultralytics_loss.py:108-116
             lbox, lobj, lcls = (float(v) for v in self.last_parts.tolist())
             with open(os.path.join("train_eval_metrics", self.filename, "loss.csv"), "a") as f:
@@ -195,8 +217,9 @@ class ComputeLoss:
         """ultralytics_loss.py:122-311 -> (tcls, tbox, indices, anchors), each a list over levels."""
         dev, targets = self._prep(p, targets)
         shapes = [tuple(t.shape) for t in p]
-        ws = self._workspace(shapes, targets.shape[0], dev, need_free=True)
-        self._build(ws, p, targets, dev)
+        with torch.cuda.device(dev):
+            ws = self._workspace(shapes, targets.shape[0], dev, need_free=True)
+            self._build(ws, p, targets, dev)
         counts = ws.counts.tolist()
         tcls, tbox, indices, anch = [], [], [], []
         for i, n in enumerate(counts):

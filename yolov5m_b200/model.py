@@ -592,16 +592,30 @@ class _NetFn(torch.autograd.Function):
         net, eng = ctx.net, ctx.eng
         L = _lib.lib()
         st = _lib.stream()
-        if not eng.head_ready:  # generic path: dense fp32 gradients from an arbitrary loss
-            for i, go in enumerate(gouts):
-                dyh = eng.head_dy[i]
-                if go is None:
+        # fast path (eng.head_ready): ComputeLoss.backward already wrote dL/dp into eng.head_dy and returned stride-0 zero
+        # sentinels.  Anything else that reaches an output (an auxiliary term, a second loss on the same outputs) arrives
+        # here as a dense gradient -- possibly summed with a sentinel by autograd -- and is ADDED to head_dy.
+        fast = eng.head_ready
+        for i, go in enumerate(gouts):
+            dyh = eng.head_dy[i]
+            sentinel = go is not None and go.numel() > 1 and all(s == 0 for s in go.stride())
+            if go is None or sentinel:
+                if not fast:
                     dyh.zero_()
-                    continue
-                go = go.contiguous().float()
-                B, na, H, W, no = go.shape
-                _lib.check(L.yb_head_grad_pack(go.data_ptr(), B, na, H, W, no, dyh.data_ptr(), HEAD_PAD, st))
+                continue
+            go = go.contiguous().float()
+            B, na, H, W, no = go.shape
+            _lib.check(L.yb_head_grad_pack(go.data_ptr(), B, na, H, W, no, dyh.data_ptr(), HEAD_PAD, 1 if fast else 0, st))
         eng.head_ready = False
+        if net._accumulate_grads and not net.expose_param_grads:
+            # gradient accumulation on the fused-optimiser path (trainer.TrainStep(accumulate=k)): this micro-batch's
+            # gradients go to the second flat bucket and are added into the first
+            if net._gflat[1] is None:
+                net._gflat[1] = torch.zeros_like(net._pflat)
+            gflat = net._gflat[1]
+            eng.run_backward(gflat)
+            _lib.check(L.yb_accumulate_f32(net.flat_grads.data_ptr(), gflat.data_ptr(), gflat.numel(), st))
+            return (None, None, None) + (None,) * len(net._poffs)
         gflat = net._grad_target()
         eng.run_backward(gflat)
         if not net.expose_param_grads:  # fused optimiser path: the flat bucket is consumed directly (trainer.py)
@@ -637,6 +651,7 @@ class YOLOV5m(nn.Module):
         # True: backward publishes p.grad views of the flat gradient bucket (stock torch optimisers work);
         # False: gradients stay only in `flat_grads` (yolov5m_b200.trainer.Adam reads the bucket) -- saves 243 view objects
         self.expose_param_grads = True
+        self._accumulate_grads = False  # set by trainer.TrainStep around the backward of an accumulated micro-batch
         self._flatten()
 
     # -- flat parameter storage -----------------------------------------------------------------
@@ -811,17 +826,21 @@ class YOLOV5m(nn.Module):
             raise _lib.YBError("YOLOV5m (B200): model and input must be on a CUDA device (no CPU fallback)")
         if x.dtype not in (torch.float32, torch.uint8):
             x = x.float()
+        if x.device != self._pflat.device:
+            raise _lib.YBError(f"YOLOV5m (B200): input on {x.device} but the model lives on {self._pflat.device}")
         x = x.contiguous()
         B = x.shape[0]
-        self.refresh_packed()
-        train = self.training
-        eng = self.engine(B, H, W, train)
-        if train and torch.is_grad_enabled():
-            outs = _NetFn.apply(self, eng, x, *self.parameters())
-            outs = list(outs)
-            for o in outs:
-                o._yb_engine = eng
-            return outs
-        with torch.no_grad():
-            outs = eng.run_forward(x)
-        return [o.clone() for o in outs] if not train else list(outs)
+        # every launch goes to the current stream of the MODEL's device, whatever the process's current device is
+        with torch.cuda.device(self._pflat.device):
+            self.refresh_packed()
+            train = self.training
+            eng = self.engine(B, H, W, train)
+            if train and torch.is_grad_enabled():
+                outs = _NetFn.apply(self, eng, x, *self.parameters())
+                outs = list(outs)
+                for o in outs:
+                    o._yb_engine = eng
+                return outs
+            with torch.no_grad():
+                outs = eng.run_forward(x)
+            return [o.clone() for o in outs] if not train else list(outs)

@@ -49,26 +49,40 @@ class Adam:
         else:
             self.model.flat_grads.zero_()
 
-    def step(self, grad_scale=1.0, max_norm=0.0, grads=None, device_step=False):
+    def step(self, grad_scale=1.0, max_norm=0.0, grads=None, device_step=True):
         """grad_scale multiplies the stored gradient (1/loss_scale, 1/world_size); max_norm > 0 clips the global norm of
-        the scaled gradient like torch.nn.utils.clip_grad_norm_ (training_utils.py:118)."""
+        the scaled gradient like torch.nn.utils.clip_grad_norm_ (training_utils.py:118).  A step whose gradient norm is
+        inf / NaN is skipped on the device (parameters, moments, step counter untouched) like GradScaler.step
+        (training_utils.py:119); ``device_step=False`` keeps the host-side counter only (no skipping bookkeeping)."""
+        model = self.model
+        with torch.cuda.device(model.flat_params.device):
+            self._step(grad_scale, max_norm, grads, device_step)
+
+    def _step(self, grad_scale, max_norm, grads, device_step):
         model = self.model
         L, st = _lib.lib(), _lib.stream()
         g = model.flat_grads if grads is None else grads
         p = model.flat_params
         n = p.numel()
-        if max_norm > 0:
-            _lib.check(L.yb_grad_norm(g.data_ptr(), n, grad_scale, self._partial.data_ptr(), self._partial.numel(),
-                                      self.grad_norm.data_ptr(), st))
+        # the norm is always computed: it doubles as the finite check of the whole bucket
+        _lib.check(L.yb_grad_norm(g.data_ptr(), n, grad_scale, self._partial.data_ptr(), self._partial.numel(),
+                                  self.grad_norm.data_ptr(), st))
         self.step_count += 1
         if device_step:
-            _lib.check(L.yb_counter_inc(self._step_dev.data_ptr(), st))
+            _lib.check(L.yb_counter_inc(self._step_dev.data_ptr(), self.grad_norm.data_ptr(), st))
         _lib.check(L.yb_adam_step(p.data_ptr(), g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), n, self.lr, self.betas[0],
                                   self.betas[1], self.eps, self.weight_decay, self.step_count,
                                   self._step_dev.data_ptr() if device_step else None, grad_scale, max_norm,
-                                  self.grad_norm.data_ptr() if max_norm > 0 else None, model._wfwd.data_ptr(), st))
+                                  self.grad_norm.data_ptr(), model._wfwd.data_ptr(), st))
+        self._device_steps = device_step
         model._repack_derived(st)                     # dgrad-layout / stem operands from the updated masters
         model._packed_sig = model._param_signature()  # the bf16 operands are current
+
+    def steps_taken(self):
+        """optimiser steps actually applied (skipped non-finite steps excluded); synchronises when the device counter is live"""
+        if getattr(self, "_device_steps", False):
+            self.step_count = int(self._step_dev.item())
+        return self.step_count
 
     def state_dict(self):
         """The ``torch.optim.Adam.state_dict()`` wire format (what the reference stores under checkpoint["optimizer"],
@@ -78,6 +92,7 @@ class Adam:
         model = self.model
         n = len(model._poffs)
         state = {}
+        self.steps_taken()
         if self.step_count > 0:
             ms, vs = model._grad_views(self.m), model._grad_views(self.v)
             for i in range(n):
@@ -231,8 +246,12 @@ class TrainStep:
     of a data-parallel job draw the same size (seeded ``random.Random``), so their step times stay aligned."""
 
     def __init__(self, model, loss_fn, optimizer, max_norm=10.0, sync=None, loss_scale=1.0, multi_scale=False,
-                 target_shape=640, max_stride=32, seed=0):
+                 target_shape=640, max_stride=32, seed=0, accumulate=1):
+        """``accumulate`` = micro-batches per optimiser step: the reference accumulates gradients over
+        ``max(round(64 / batch_size), 1)`` batches (training_utils.py:88-90,:116); pass that value (see
+        :func:`nominal_accumulate`) for bs < 64.  ``flush()`` steps on a partial window (the reference's ``idx == nb-1``)."""
         self.model, self.loss_fn, self.opt = model, loss_fn, optimizer
+        self.accumulate, self._micro = max(1, int(accumulate)), 0
         self.max_norm, self.loss_scale = max_norm, loss_scale
         self.sync = sync if sync is not None else GradSync(model)
         self.multi_scale, self.target_shape, self.max_stride = multi_scale, target_shape, max_stride
@@ -250,15 +269,41 @@ class TrainStep:
             size = multi_scale_size(images.shape[2], images.shape[3], self.target_shape, self.max_stride, self._rng)
         out = model(images, size=size)
         loss = self.loss_fn(out, targets, pred_size=size if size is not None else images.shape[2:4])
-        overlapped = self.sync.world > 1 and self.sync.attach(out[0]._yb_engine)
-        if self.loss_scale != 1.0:
-            (loss * self.loss_scale).backward()
-        else:
-            loss.backward()
+        last = self._micro + 1 >= self.accumulate
+        # micro-batches after the first of a window are accumulated: their backward writes the second flat bucket, which is
+        # then added into the first (model._NetFn.backward); the all-reduce overlap only applies to single-batch windows
+        model._accumulate_grads = self._micro > 0
+        overlapped = self.accumulate == 1 and self.sync.world > 1 and self.sync.attach(out[0]._yb_engine)
+        if self.accumulate > 1:
+            out[0]._yb_engine.on_grad_chunks = None
+        try:
+            if self.loss_scale != 1.0:
+                (loss * self.loss_scale).backward()
+            else:
+                loss.backward()
+        finally:
+            model._accumulate_grads = False
+        self._micro += 1
+        if last:
+            self._apply(overlapped)
+        return loss
+
+    def _apply(self, overlapped=False):
+        model = self.model
         if overlapped:
             self.sync.finish(model.flat_grads)  # chunks were all-reduced while the backward pass ran
         else:
             self.sync.all_reduce()
         self.opt.step(grad_scale=1.0 / (self.loss_scale * self.sync.world), max_norm=self.max_norm)
         self.opt.zero_grad(set_to_none=True)
-        return loss
+        self._micro = 0
+
+    def flush(self):
+        """optimiser step on a partially filled accumulation window (end of an epoch, training_utils.py:116 `idx == nb-1`)"""
+        if self._micro > 0:
+            self._apply(False)
+
+
+def nominal_accumulate(batch_size, nbs=64):
+    """micro-batches per optimiser step of the reference train_loop (training_utils.py:88-90)"""
+    return max(round(nbs / batch_size), 1)
