@@ -34,7 +34,8 @@ int yb_conv_max_partials(void);
  * epilogue: v = acc; if scale: v = v*scale[co]+shift[co]; elif shift: v += shift[co];
  *           if act: v = SiLU(v); if addend: v += addend[n,ho,wo,co]; store.
  * out_kind 0: bf16 NHWC (y_pitch); 1: fp32 head layout (B,na,H,W,no) of model.py:173
- *          (Cout = na*no, need not be a multiple of 16); 2: fp32 NHWC.
+ *          (Cout = na*no, need not be a multiple of 16); 2: fp32 NHWC; 3 / 4: like 2 / 1 but out += value
+ *          (fp32 accumulate: the parity mode sums several bf16-split passes of one convolution, see yb_p32_* below).
  * stats (optional): fp32 [yb_conv_max_partials()][2][Cout]; row r receives CTA r's sum and
  * sum of squares of the raw accumulator per out channel (training-mode BatchNorm2d batch
  * statistics, model.py:17); *stats_rows = rows written. */
@@ -46,10 +47,10 @@ int yb_conv2d_fwd(const void* x, int N, int H, int W, int Cin, int64_t x_pitch, 
 /* ---- Conv2d data gradient (autograd of model.py:16 / :162) ---------------------------
  * dx[n,h,w,ci] = sum_{kh,kw,co} dy[n,(h+p-kh)/s,(w+p-kw)/s,co] * wt[ci,(kh*ks+kw)*Cout+co]
  * (terms with non-integral or out-of-range dy coordinates vanish).  wt_packed: bf16
- * [Cin][ks*ks*Cout].  H, W are the INPUT (dx) spatial dims.  Same epilogue options. */
+ * [Cin][ks*ks*Cout].  H, W are the INPUT (dx) spatial dims.  out_kind 0 (bf16), 2 (fp32) or 3 (fp32 accumulate). */
 int yb_conv2d_dgrad(const void* dy, int N, int H, int W, int Cout, int64_t dy_pitch, const void* wt_packed, int Cin,
                     int ks, int stride, void* dx, int64_t dx_pitch, const void* addend, int64_t addend_pitch,
-                    void* stream);
+                    int out_kind, void* stream);
 
 
 /* ---- cached launch plans (TMA descriptors are encoded once per tensor geometry) ------------------------------
@@ -61,7 +62,8 @@ void* yb_conv_fwd_plan(const void* x, int N, int H, int W, int Cin, int64_t x_pi
                        const float* shift, int act, const void* addend, int64_t addend_pitch, float* stats,
                        int* stats_rows, int head_na, int head_no);
 void* yb_conv_dgrad_plan(const void* dy, int N, int H, int W, int Cout, int64_t dy_pitch, const void* wt_packed, int Cin,
-                         int ks, int stride, void* dx, int64_t dx_pitch, const void* addend, int64_t addend_pitch);
+                         int ks, int stride, void* dx, int64_t dx_pitch, const void* addend, int64_t addend_pitch,
+                         int out_kind);
 int yb_plan_run(void* plan, void* stream);
 /* Kernel selection for 3x3 convolutions planned AFTER the call (tuning / test knob; default 0, or $YB_CONV_PATCH):
  * 0 = heuristic, 1 = halo-patch kernel (conv_patch.cu) wherever legal, 2 = same plus multi-tile super-tiles on small
@@ -139,6 +141,39 @@ int yb_prep_input_resized(const void* x, int dtype, int N, int Hs, int Ws, int H
  * accumulate = 1 adds to what dy already holds (a second gradient contribution to the same head output) */
 int yb_head_grad_pack(const float* g, int B, int na, int H, int W, int no, void* dy, int Cpad, int accumulate, void* stream);
 
+/* ---- fp32 parity mode (BASELINE.json configs[1]: "fp32 vs reference", 1e-3) --------------------------
+ * Activations and gradients stay fp32; a convolution is six passes of the SAME tcgen05 kernels above over the 3-way bf16
+ * split of both operands (x = x0+x1+x2, 24 mantissa bits), accumulating into one fp32 tensor (out_kind 2 then 3; wgrad
+ * accumulate = 1).  "planes" = three bf16 tensors of the fp32 tensor's geometry, plane_stride elements apart.  The
+ * element-wise operators of model.py:17,23,50,103,225 and their backward run as plain fp32 kernels (exact SiLU, double
+ * accumulation of the BatchNorm sums).  partial / rows feed yb_bn_finalize, yb_bn_bwd_finalize and yb_reduce_rows. */
+int yb_p32_split_flat(const void* src, int dtype, int64_t n, float* o0, float* o1, float* o2, void* stream);
+int yb_p32_planes(const float* src, int64_t src_pitch, int64_t npix, int C, void* planes, int64_t pl_pitch,
+                  int64_t plane_stride, void* stream);
+int yb_p32_bn_stats(const float* y, int64_t y_pitch, int64_t npix, int C, float* partial, int max_rows, int* rows,
+                    void* stream);
+int yb_p32_bn_act_fwd(const float* y, int64_t y_pitch, int N, int H, int W, int C, const float* scale, const float* shift,
+                      const float* res, int64_t res_pitch, float* out, void* out_planes, int64_t out_pitch,
+                      int64_t out_plane_stride, float* up, void* up_planes, int64_t up_pitch, int64_t up_plane_stride,
+                      void* stream);
+int yb_p32_bn_act_bwd_reduce(const float* da, int64_t da_pitch, const float* y, int64_t y_pitch, int64_t npix, int C,
+                             const float* scale, const float* shift, const float* mean, const float* invstd,
+                             float* partial, int max_rows, int* rows, void* stream);
+int yb_p32_bn_act_bwd_apply(const float* da, int64_t da_pitch, const float* y, int64_t y_pitch, int64_t npix, int C,
+                            const float* scale, const float* shift, const float* mean, const float* invstd,
+                            const float* coef, float* dy, void* dy_planes, int64_t dy_pitch, int64_t dy_plane_stride,
+                            void* stream);
+int yb_p32_maxpool5_fwd(const float* x, int64_t x_pitch, int N, int H, int W, int C, float* y, void* y_planes,
+                        int64_t y_pitch, int64_t y_plane_stride, uint8_t* argmax, void* stream);
+int yb_p32_maxpool5_bwd(const float* dy, int64_t dy_pitch, const uint8_t* argmax, int N, int H, int W, int C, float* dx,
+                        int64_t dx_pitch, int accumulate, void* stream);
+int yb_p32_upsample2x_bwd(const float* dup, int64_t dup_pitch, int N, int H, int W, int C, float* dsrc, int64_t dsrc_pitch,
+                          int accumulate, void* stream);
+int yb_p32_add_into(const float* src, int64_t src_pitch, float* dst, int64_t dst_pitch, int64_t npix, int C, int accumulate,
+                    void* stream);
+int yb_p32_head_grad_pack(const float* g, int B, int na, int H, int W, int no, float* dy, void* dy_planes, int Cpad,
+                          int64_t plane_stride, int accumulate, void* stream);
+
 /* ---- parameter packing + optimiser tail on the flat fp32 master / gradient buffers ------------------------------
  * The master weights stay in the reference's state_dict tensors (fp32, conv weights channels-last = [Cout][kh*kw][Cin]),
  * laid out back to back in one flat buffer; the tcgen05 operands are bf16 copies:
@@ -194,12 +229,28 @@ int yb_box_iou(const float* boxes_preds, const float* boxes_labels, int64_t n, i
  * (offset-major, then anchor, then target -- the order boolean-mask indexing produces) and counts[nl]. */
 int yb_build_targets(const float* targets, int nt, const float* anchors, const yb_loss_level* levels, int nl, int na,
                      float anchor_t, int64_t cap, int* counts, void* stream);
-/* ComputeLoss.__call__ (ultralytics_loss.py:60-120): out4 = [(lbox+lobj+lcls)*B, lbox, lobj, lcls] (weighted parts). */
+/* ComputeLoss.__call__ (ultralytics_loss.py:60-120): out4 = [(lbox+lobj+lcls)*B, lbox, lobj, lcls] (weighted parts).
+ * counts[nl] = row slots to scan per level.  Rows with image index < 0 are unused slots; rows with tcls < 0 are "ignore"
+ * rows (objectness target -1, no box / class term: YOLO_LOSS, loss.py:190).  nobj (optional, device [nl]) = number of
+ * object rows = denominator of the box / class means (NULL: counts).  nan_on_empty = 1 reproduces the NaN the reference's
+ * YOLO_LOSS returns for a level without objects (mean of an empty tensor, loss.py:211). */
 int yb_loss_fwd(const yb_loss_level* levels, int nl, int B, int na, int no, int64_t cap, const int* counts,
-                float lam_box, float lam_obj, float lam_cls, float* out4, void* stream);
+                const int* nobj, int nan_on_empty, float lam_box, float lam_obj, float lam_cls, float* out4, void* stream);
 /* its backward: gout = device scalar dLoss (NULL = 1).  Needs the scratch yb_loss_fwd left in the levels. */
 int yb_loss_bwd(const yb_loss_level* levels, int nl, int B, int na, int no, int64_t cap, const int* counts,
-                float lam_box, float lam_obj, float lam_cls, const float* gout, int cpad, void* stream);
+                const int* nobj, float lam_box, float lam_obj, float lam_cls, const float* gout, int cpad, void* stream);
+/* YOLO_LOSS.build_targets (loss.py:101-192), the matcher train.py uses without --ultralytics_loss: sequential per image.
+ * labels: device float64 [nt][5] = class, x, y, w, h (normalised; np.loadtxt rows); offsets: device int32 [B+1].
+ * anchor_table: device fp32 [T][9][2], row k = the reference's anchor tensor after k in-place divisions by 640
+ * (utils/bboxes_utils.py:18), times the level stride; the label row r (0-based in this batch) uses table row
+ * min(decay_base + (r+1)*decay_stride, T-1), or row 1 when decay_stride = 0 (anchors normalised once = the bug fixed).
+ * Writes the row lists of the three levels (3 slots per label row; unused slots get image index -1), counts[3] = 3*nt,
+ * nobj[3]; state: int8 scratch of sum_l B*3*H*W bytes; dense (optional): the reference's dense target tensors, level after
+ * level, each (B,3,H,W,6) fp32 = [x_cell, y_cell, w_cell, h_cell, objectness (1 / -1 / 0), class]. */
+int yb_yolo_build_targets(const double* labels, const int* offsets, int B, int nt, const float* anchor_table, int T,
+                          int64_t decay_base, int decay_stride, const float* head_anchors, const yb_loss_level* levels,
+                          int nl, int na, float ignore_thr, int64_t cap, int8_t* state, float* dense, int* counts,
+                          int* nobj, void* stream);
 
 /* ---- cells_to_bboxes(is_pred=True) (utils/plot_utils.py:10-40) and non_max_suppression (utils/bboxes_utils.py:175-209)
  * yb_decode_level: p (B,na,H,W,no) logits of one level -> rows [cls, sigmoid(obj), cx, cy, w, h] (pixels) written at

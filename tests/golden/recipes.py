@@ -76,3 +76,23 @@ def nms_boxes(seed, b, n, mode="realistic", size=640.0):
         cxy = torch.rand(b, n, 2, generator=g) * size
         wh = torch.exp(torch.randn(b, n, 2, generator=g) * 0.8 + 4)
     return torch.cat([cls, score, cxy, wh], -1)
+
+
+def yolo_labels(seed, b, max_boxes=6):
+    """per-image label arrays for the reference's default loss (loss.py:64): tuple of (n_i, 5) float64
+    [class, x, y, w, h] like Training_Dataset.collate_fn yields (np.loadtxt rows); some images have no boxes,
+    some boxes repeat a cell (exercises the `anchor_taken` / ignore rules)."""
+    import numpy as np
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for i in range(b):
+        n = int(torch.randint(0, max_boxes + 1, (1,), generator=g))
+        cls = torch.randint(0, 80, (n, 1), generator=g).double()
+        xy = torch.rand(n, 2, generator=g, dtype=torch.float64) * 0.98 + 0.01
+        wh = torch.exp(torch.randn(n, 2, generator=g, dtype=torch.float64) * 0.9 - 2.2).clamp(0.01, 0.95)
+        lab = torch.cat([cls, xy, wh], 1).numpy().astype(np.float64)
+        if n >= 2 and i % 2 == 0:
+            lab[1, 1:3] = lab[0, 1:3]        # same centre as box 0: same cells on every level
+            lab[1, 3:5] = lab[0, 3:5] * 1.05  # near-identical shape: same anchor ranking
+        out.append(lab)
+    return tuple(out)

@@ -147,7 +147,7 @@ def test_conv_dgrad(case):
         ref = ref + add_c.float()
     _lib.check(L.yb_conv2d_dgrad(_lib.ptr(dyd), N, H, W, Cout, _lib.c_i64(Cout), _lib.ptr(pack_dgrad(w.float()).cuda()),
                                  Cin, ks, s, _lib.ptr(dx), _lib.c_i64(Cin), _lib.ptr(add), _lib.c_i64(Cin),
-                                 _lib.stream()))
+                                 0, _lib.stream()))
     torch.cuda.synchronize()
     assert rel(dx.float().cpu().permute(0, 3, 1, 2), ref) < TOL
 

@@ -1,5 +1,7 @@
 """Pin the oracle (oracle/) against golden vectors produced by the real reference
 (tests/golden/make_golden.py).  CPU only."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -114,3 +116,34 @@ def test_nms_keep_sets(golden, tag):
     assert [len(o) for o in outs] == list(g[f"{tag}_counts"])
     rows = np.concatenate(outs, 0) if outs else np.zeros((0, 6), np.float32)
     assert np.array_equal(rows.astype(np.float32), g[f"{tag}_rows"])  # bit-exact rows == bit-exact keep set
+
+
+# ---- the reference's default loss YOLO_LOSS (loss.py), SURVEY.md 8(f) rank 3 -------------------------------------------
+YOLO_SEQ = [("c0", 2, 128, 128, 31), ("c1", 4, 160, 96, 32), ("c2", 3, 64, 64, 33), ("c3", 4, 128, 160, 34)]
+
+
+def test_yolo_loss_oracle_matches_reference_sequence():
+    """the oracle reproduces a SEQUENCE of reference calls (the anchors decay by /640 per box, bboxes_utils.py:18):
+    losses to 1e-6, gradients to 1e-5, single-image target tensors bit for bit"""
+    import numpy as np
+    import recipes
+    from oracle import model_ref
+    from oracle.yolo_loss_ref import YoloLossRef
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "yolo_loss.npz"))
+    o = YoloLossRef(model_ref.head_anchors())
+    for tag, b, h, w, seed in YOLO_SEQ:
+        p = [t.requires_grad_(True) for t in recipes.head_outputs(40 + seed, b, h, w)]
+        loss, _ = o(p, recipes.yolo_labels(seed, b))
+        loss.backward()
+        assert abs(float(loss.detach()) - float(g[tag + "_loss"][0])) <= 1e-6 * abs(float(g[tag + "_loss"][0])), tag
+        for i in range(3):
+            assert abs(float(p[i].grad.norm()) - float(g[f"{tag}_gnorm{i}"])) <= 1e-5 * float(g[f"{tag}_gnorm{i}"])
+    for k, lab in enumerate(recipes.yolo_labels(35, 3)):
+        tg = o.build_targets([(12, 16), (6, 8), (3, 4)], lab)
+        for i in range(3):
+            assert np.array_equal(tg[i], g[f"bt{k}_l{i}"]), (k, i)
+    f = YoloLossRef(model_ref.head_anchors())
+    for k, lab in enumerate(recipes.yolo_labels(36, 4, max_boxes=5)):
+        tg = f.build_targets([(32, 32), (16, 16), (8, 8)], lab)
+        for i in range(3):
+            assert np.array_equal(tg[i], g[f"fresh{k}_l{i}"]), (k, i)

@@ -76,7 +76,7 @@ def main():
             L.yb_plan_destroy(p)
         if "dgrad" in a.only and cin != 16:
             p = _lib.checkp(L.yb_conv_dgrad_plan(y.data_ptr(), B, hin, hin, cout, cout, wt.data_ptr(), cin, k, s,
-                                                 x.data_ptr(), cin, None, 0))
+                                                 x.data_ptr(), cin, None, 0, 0))
             t = time_it(lambda: L.yb_plan_run(p, st), a.iters)
             r["dgrad_us"] = t * 1e6; r["dgrad_tf"] = flops / t / 1e12; tot["dgrad"] += t * cnt
             L.yb_plan_destroy(p)

@@ -46,10 +46,11 @@ int yb_conv2d_fwd(const void* x, int N, int H, int W, int Cin, int64_t x_pitch, 
 
 int yb_conv2d_dgrad(const void* dy, int N, int H, int W, int Cout, int64_t dy_pitch, const void* wt_packed, int Cin,
                     int ks, int stride, void* dx, int64_t dx_pitch, const void* addend, int64_t addend_pitch,
-                    void* stream) {
+                    int out_kind, void* stream) {
   TView g{const_cast<void*>(dy), N, H / stride, W / stride, Cout, (long)dy_pitch};
   TView o{dx, N, H, W, Cin, (long)dx_pitch};
   ConvEpilogue ep;
+  ep.out_kind = out_kind;
   ep.addend = reinterpret_cast<const bf16*>(addend);
   ep.addend_pitch = (long)addend_pitch;
   ConvPlan pl;
@@ -92,10 +93,12 @@ void* yb_conv_fwd_plan(const void* x, int N, int H, int W, int Cin, int64_t x_pi
 }
 
 void* yb_conv_dgrad_plan(const void* dy, int N, int H, int W, int Cout, int64_t dy_pitch, const void* wt_packed, int Cin,
-                         int ks, int stride, void* dx, int64_t dx_pitch, const void* addend, int64_t addend_pitch) {
+                         int ks, int stride, void* dx, int64_t dx_pitch, const void* addend, int64_t addend_pitch,
+                         int out_kind) {
   TView g{const_cast<void*>(dy), N, H / stride, W / stride, Cout, (long)dy_pitch};
   TView o{dx, N, H, W, Cin, (long)dx_pitch};
   ConvEpilogue ep;
+  ep.out_kind = out_kind;
   ep.addend = reinterpret_cast<const bf16*>(addend);
   ep.addend_pitch = (long)addend_pitch;
   YbPlan* pl = new YbPlan();

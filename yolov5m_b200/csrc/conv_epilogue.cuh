@@ -154,11 +154,18 @@ __device__ __forceinline__ void conv_epilogue_chunk(const EpiArgs& p, uint32_t t
           reinterpret_cast<uint4*>(op)[0] = o0;
           reinterpret_cast<uint4*>(op)[1] = o1;
         }
-      } else if (p.out_kind == OUT_F32) {
+      } else if (p.out_kind == OUT_F32 || p.out_kind == OUT_F32_ACC) {
         float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + opix + col0);
+        if (p.out_kind == OUT_F32_ACC) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 o = op[j];
+            v[4 * j] += o.x; v[4 * j + 1] += o.y; v[4 * j + 2] += o.z; v[4 * j + 3] += o.w;
+          }
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-      } else {  // OUT_HEAD_F32
+      } else {  // OUT_HEAD_F32 / OUT_HEAD_F32_ACC
         float* ob = reinterpret_cast<float*>(p.out);
         const int64_t hw = (int64_t)p.H * p.W;
         const int64_t pix = (int64_t)h * p.W + w;
@@ -167,7 +174,8 @@ __device__ __forceinline__ void conv_epilogue_chunk(const EpiArgs& p, uint32_t t
           const int col = col0 + j;
           if (col < p.Cout) {
             const int a = col / p.head_no, o = col - a * p.head_no;
-            ob[(((int64_t)n * p.head_na + a) * hw + pix) * p.head_no + o] = v[j];
+            float* dst = ob + (((int64_t)n * p.head_na + a) * hw + pix) * p.head_no + o;
+            *dst = p.out_kind == OUT_HEAD_F32_ACC ? *dst + v[j] : v[j];
           }
         }
       }

@@ -328,7 +328,8 @@ static int finish_plan(ConvPlan& pl, const bf16* wmat, int wrows, long wcols, co
   kp.stats = ep.stats;
   kp.head_na = ep.head_na;
   kp.head_no = ep.head_no;
-  YB_REQUIRE(ep.out_kind == OUT_HEAD_F32 || wrows % 16 == 0, "conv: Cout=%d must be a multiple of 16", wrows);
+  YB_REQUIRE(ep.out_kind == OUT_HEAD_F32 || ep.out_kind == OUT_HEAD_F32_ACC || wrows % 16 == 0,
+             "conv: Cout=%d must be a multiple of 16", wrows);
   YB_REQUIRE(ep.scale == nullptr || ep.shift != nullptr, "conv: scale without shift");
   const size_t stats_bytes = ep.stats ? (size_t)4 * 2 * wrows * sizeof(float) : 0;
   const size_t budget = 227 * 1024 - 1024 /*align slack*/ - kBarRegion - stats_bytes;

@@ -30,7 +30,9 @@ struct ConvGroup {
   int64_t add_off;  // same for the addend tensor
 };
 
-enum { OUT_BF16 = 0, OUT_HEAD_F32 = 1, OUT_F32 = 2 };
+// OUT_F32_ACC / OUT_HEAD_F32_ACC: out += value (fp32 read-modify-write) -- the parity mode runs one convolution as several
+// bf16-split passes of the same kernel that accumulate into one fp32 tensor (model.py parity engine, csrc/parity.cu)
+enum { OUT_BF16 = 0, OUT_HEAD_F32 = 1, OUT_F32 = 2, OUT_F32_ACC = 3, OUT_HEAD_F32_ACC = 4 };
 
 struct ConvKParams {
   CUtensorMap tmA[4];

@@ -454,7 +454,8 @@ static void set_out_strides(PatchKParams& kp, const TView& o, int step, const Co
 
 int conv_patch_plan_fwd(ConvPlan& pl, const TView& in, const bf16* wp, int ks, int stride, const TView& out,
                         const ConvEpilogue& ep) {
-  if ((ks != 3 && ks != 1 && ks != 31) || (stride != 1 && stride != 2) || ep.out_kind != OUT_BF16) return 1;
+  const bool nhwc_out = ep.out_kind == OUT_BF16 || ep.out_kind == OUT_F32 || ep.out_kind == OUT_F32_ACC;
+  if ((ks != 3 && ks != 1 && ks != 31) || (stride != 1 && stride != 2) || !nhwc_out) return 1;
   if (ks != 3 && stride != 1) return 1;
   if (in.C % 8 || in.pitch % 8 || out.pitch % 8 || out.C % 16) return 1;
   if (in.H % stride || in.W % stride || out.H != in.H / stride || out.W != in.W / stride || out.N != in.N) return 1;
@@ -547,7 +548,8 @@ int conv_patch_plan_fwd(ConvPlan& pl, const TView& in, const bf16* wp, int ks, i
 
 int conv_patch_plan_dgrad(ConvPlan& pl, const TView& dy, const bf16* wt, int ks, int stride, const TView& dx,
                           const ConvEpilogue& ep) {
-  if ((ks != 3 && ks != 1) || (stride != 1 && stride != 2) || ep.out_kind != OUT_BF16) return 1;
+  const bool nhwc_out = ep.out_kind == OUT_BF16 || ep.out_kind == OUT_F32 || ep.out_kind == OUT_F32_ACC;
+  if ((ks != 3 && ks != 1) || (stride != 1 && stride != 2) || !nhwc_out) return 1;
   if (ks == 1 && stride != 1) return 1;
   if (dy.C % 8 || dy.pitch % 8 || dx.pitch % 8 || dx.C % 16) return 1;
   if (dx.H % stride || dx.W % stride || dy.H != dx.H / stride || dy.W != dx.W / stride || dy.N != dx.N) return 1;

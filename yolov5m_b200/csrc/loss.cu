@@ -31,6 +31,10 @@ struct LossKParams {
   int nl, B, na, no, nc;
   long cap;
   const int* counts;
+  const int* nobj;   // optional: object rows per level (denominator of the box / class means) when the row lists also hold
+                     // "ignore" rows or unused slots (YOLO_LOSS, yolo_loss.cu); NULL -> counts
+  int nan_empty;     // 1: a level without object rows yields NaN box / class terms like the reference's mean() of an empty
+                     // tensor (loss.py:211,232); 0: ComputeLoss semantics (the level contributes nothing, ultralytics_loss.py:76)
   float lam_box, lam_obj, lam_cls;
   const float* gout;
   int cpad;
@@ -154,10 +158,28 @@ __global__ void __launch_bounds__(256) loss_rows_kernel(const __grid_constant__ 
     if (k >= P.counts[lvl]) continue;
     const yb_loss_level& L = P.lv[lvl];
     const long b = L.idx[k], a = L.idx[P.cap + k], gj = L.idx[2 * P.cap + k], gi = L.idx[3 * P.cap + k];
-    if (b < 0 || b >= P.B) continue;  // the reference would raise an IndexError; never write out of bounds
+    if (b < 0 || b >= P.B) {  // unused slot (YOLO_LOSS) or an image index the reference would raise IndexError on
+      if (lane == 0) {
+        L.row_val[k] = 0.f;
+        L.row_val[P.cap + k] = 0.f;
+        L.row_val[2 * P.cap + k] = 0.f;
+      }
+      continue;
+    }
     const long cell = ((b * P.na + a) * L.H + gj) * L.W + gi;
     const float* ps = L.p + cell * P.no;
     float* rg = L.row_grad + k * P.no;
+    if (L.tcls[k] < 0) {
+      // "ignore" row of YOLO_LOSS (loss.py:190): objectness target -1, no box / class term
+      for (int c = lane; c < P.no; c += 32) rg[c] = 0.f;
+      if (lane == 0) {
+        L.row_val[k] = -1.f;
+        L.row_val[P.cap + k] = 0.f;
+        L.row_val[2 * P.cap + k] = 0.f;
+        L.row_prev[k] = atomicExch(&L.cell_head[cell], (int)k + 1);
+      }
+      continue;
+    }
     // ---- class BCE (ultralytics_loss.py:93-95)
     float csum = 0.f;
     if (P.nc > 1) {
@@ -282,13 +304,17 @@ __global__ void __launch_bounds__(256) loss_finalize_kernel(const __grid_constan
   double lbox = 0.0, lobj = 0.0, lcls = 0.0;
   for (int lvl = 0; lvl < P.nl; ++lvl) {
     const yb_loss_level& L = P.lv[lvl];
-    const int n = P.counts[lvl];
-    const double sb = block_sum_ordered(L.row_val + P.cap, n, sh);
-    const double sc = block_sum_ordered(L.row_val + 2 * P.cap, n, sh);
+    const int nrows = P.counts[lvl];
+    const int n = P.nobj != nullptr ? P.nobj[lvl] : nrows;
+    const double sb = block_sum_ordered(L.row_val + P.cap, nrows, sh);
+    const double sc = block_sum_ordered(L.row_val + 2 * P.cap, nrows, sh);
     const double so = block_sum_ordered(L.obj_partial, P.obj_rows, sh);
     if (n > 0) {
       lbox += sb / n;                                   // (1 - iou).mean(), :85
       if (P.nc > 1) lcls += sc / ((double)n * P.nc);    // BCEcls mean over n*nc, :95
+    } else if (P.nan_empty) {
+      lbox += nan("");
+      lcls += nan("");
     }
     lobj += so / ((double)P.B * P.na * L.H * L.W) * (double)L.balance;  // :101-102
   }
@@ -325,7 +351,7 @@ __global__ void __launch_bounds__(256) loss_bwd_kernel(const __grid_constant__ L
     const long pix = wi - lvl_begin[lvl];
     const long hw = (long)L.H * L.W;
     const long b = pix / hw, sp = pix - b * hw;
-    const int n = P.counts[lvl];
+    const int n = P.nobj != nullptr ? P.nobj[lvl] : P.counts[lvl];
     const float cbox = n > 0 ? g * P.lam_box / (float)n : 0.f;
     const float ccls = (n > 0 && P.nc > 1) ? g * P.lam_cls / ((float)n * (float)P.nc) : 0.f;
     const float cobj = g * P.lam_obj * L.balance / (float)((long)P.B * P.na * hw);
@@ -508,9 +534,11 @@ int yb_build_targets(const float* targets, int nt, const float* anchors, const y
 }
 
 int yb_loss_fwd(const yb_loss_level* levels, int nl, int B, int na, int no, int64_t cap, const int* counts,
-                float lam_box, float lam_obj, float lam_cls, float* out4, void* stream) {
+                const int* nobj, int nan_on_empty, float lam_box, float lam_obj, float lam_cls, float* out4, void* stream) {
   LossKParams P;
   if (fill_params(P, levels, nl, B, na, no, cap, counts)) return -1;
+  P.nobj = nobj;
+  P.nan_empty = nan_on_empty;
   P.lam_box = lam_box;
   P.lam_obj = lam_obj;
   P.lam_cls = lam_cls;
@@ -533,9 +561,10 @@ int yb_loss_fwd(const yb_loss_level* levels, int nl, int B, int na, int no, int6
 }
 
 int yb_loss_bwd(const yb_loss_level* levels, int nl, int B, int na, int no, int64_t cap, const int* counts,
-                float lam_box, float lam_obj, float lam_cls, const float* gout, int cpad, void* stream) {
+                const int* nobj, float lam_box, float lam_obj, float lam_cls, const float* gout, int cpad, void* stream) {
   LossKParams P;
   if (fill_params(P, levels, nl, B, na, no, cap, counts)) return -1;
+  P.nobj = nobj;
   P.lam_box = lam_box;
   P.lam_obj = lam_obj;
   P.lam_cls = lam_cls;

@@ -106,7 +106,7 @@ class _LossFn(torch.autograd.Function):
                 grads.append(g)
         B, na, _, _, no = ctx.shapes[0]
         cpad = eng.head_dy[0].shape[-1] if eng is not None else 0
-        _lib.check(L.yb_loss_bwd(ws.levels, len(ctx.p), B, na, no, ws.cap, ws.counts.data_ptr(), owner.lambda_box,
+        _lib.check(L.yb_loss_bwd(ws.levels, len(ctx.p), B, na, no, ws.cap, ws.counts.data_ptr(), owner._nobj_ptr(ws), owner.lambda_box,
                                  owner.lambda_obj, owner.lambda_class, gout.data_ptr(), cpad, st))
         if eng is not None:
             eng.head_ready = True
@@ -117,6 +117,11 @@ class _LossFn(torch.autograd.Function):
 
 class ComputeLoss:
     sort_obj_iou = False
+    nan_on_empty = False   # ComputeLoss: a level without targets contributes nothing (ultralytics_loss.py:76)
+    rows_per_target = None  # row capacity per target row: 5 * na (ultralytics_loss.py:248), set in _workspace
+
+    def _nobj_ptr(self, ws):
+        return None  # every row is an object row: the means divide by counts
 
     def __init__(self, model, save_logs=False, filename=None, resume=False, image_size=IMAGE_SIZE):
         device = next(model.parameters()).device
@@ -186,12 +191,13 @@ class ComputeLoss:
         self._build(ws, p, targets, dev)
         L, st = _lib.lib(), _lib.stream()
         B, na, _, _, no = shapes[0]
-        _lib.check(L.yb_loss_fwd(ws.levels, self.nl, B, na, no, ws.cap, ws.counts.data_ptr(), self.lambda_box, self.lambda_obj,
+        _lib.check(L.yb_loss_fwd(ws.levels, self.nl, B, na, no, ws.cap, ws.counts.data_ptr(), self._nobj_ptr(ws),
+                                 1 if self.nan_on_empty else 0, self.lambda_box, self.lambda_obj,
                                  self.lambda_class, ws.out4.data_ptr(), st))
         # fast path: p are the live head tensors of a YOLOV5m engine -> backward writes its bf16 gradient operand
         eng = getattr(p[0], "_yb_engine", None)
         if eng is not None:
-            ok = eng.train and all(getattr(t, "_yb_engine", None) is eng and t.data_ptr() == o.data_ptr()
+            ok = eng.train and not eng.parity and all(getattr(t, "_yb_engine", None) is eng and t.data_ptr() == o.data_ptr()
                                    for t, o in zip(p, eng.outs))
             eng = eng if ok else None
         return ws, eng

@@ -124,13 +124,21 @@ class HEADS(nn.Module):  # reference model.py:143-175
 
 
 # ------------------------------------------------------------------------------------------------ engine pieces
-class _Buf:
-    """NHWC bf16 allocation (+ same-shaped gradient when training)."""
+PARITY_PASSES = ((0, 0), (0, 1), (1, 0), (1, 1), (0, 2), (2, 0))  # (activation plane, weight plane) per conv pass
 
-    def __init__(self, N, H, W, C, grad, dev):
+
+class _Buf:
+    """NHWC bf16 allocation (+ same-shaped gradient when training).  Parity mode (csrc/parity.cu): the tensor and its
+    gradient are fp32 and `pl` holds the three bf16 planes of the 3-way split that the tcgen05 convs read."""
+
+    def __init__(self, N, H, W, C, grad, dev, parity=False, planes=True):
         self.N, self.H, self.W, self.C = N, H, W, C
-        self.t = torch.empty(N, H, W, C, device=dev, dtype=torch.bfloat16)
-        self.g = torch.empty(N, H, W, C, device=dev, dtype=torch.bfloat16) if grad else None
+        dt = torch.float32 if parity else torch.bfloat16
+        self.esz = 4 if parity else 2
+        self.t = torch.empty(N, H, W, C, device=dev, dtype=dt)
+        self.g = torch.empty(N, H, W, C, device=dev, dtype=dt) if grad else None
+        self.pl = torch.empty(3, N, H, W, C, device=dev, dtype=torch.bfloat16) if (parity and planes) else None
+        self.plane_stride = N * H * W * C
         self.gw = np.zeros(C, bool)  # (backward-list construction) which gradient channels already hold a value
         self.pending = []            # identity gradient contributions (c0, C, src_view) not yet materialised
 
@@ -146,11 +154,19 @@ class _View:
 
     @property
     def ptr(self):
-        return self.buf.t.data_ptr() + 2 * self.c0
+        return self.buf.t.data_ptr() + self.buf.esz * self.c0
 
     @property
     def gptr(self):
-        return self.buf.g.data_ptr() + 2 * self.c0
+        return self.buf.g.data_ptr() + self.buf.esz * self.c0
+
+    def plptr(self, k=0):
+        """parity mode: bf16 plane k of the 3-way split of this view"""
+        return self.buf.pl.data_ptr() + 2 * (k * self.buf.plane_stride + self.c0)
+
+    @property
+    def plane_stride(self):
+        return self.buf.plane_stride
 
     def tensor(self):
         return self.buf.t[..., self.c0:self.c0 + self.C]
@@ -168,8 +184,8 @@ class _LayerRec:
 class _Engine:
     """Static launch plan for one (batch, height, width, mode): buffers, TMA plans, forward / backward op lists."""
 
-    def __init__(self, net, B, H, W, train):
-        self.net, self.B, self.H, self.W, self.train = net, B, H, W, train
+    def __init__(self, net, B, H, W, train, parity=False):
+        self.net, self.B, self.H, self.W, self.train, self.parity = net, B, H, W, train, parity
         self.dev = net._pflat.device
         self.L = _lib.lib()
         self.fwd_ops, self.bwd_ops, self.tape = [], [], []
@@ -198,7 +214,8 @@ class _Engine:
             # the tensor-bound wgrad of layer L with the HBM-bound BN/SiLU backward of layer L-1.  Measured on B200
             # (profiles/ab_wgrad_side_stream_r1.json): no gain -- the elementwise passes are launched as one full resident
             # wave and hold the register file, so a 512-thread wgrad CTA cannot become co-resident until they drain.
-            self.side = torch.cuda.Stream(device=self.dev) if os.environ.get("YB_WGRAD_STREAM", "0") == "1" else None
+            self.side = (torch.cuda.Stream(device=self.dev)
+                         if os.environ.get("YB_WGRAD_STREAM", "0") == "1" and not parity else None)
             self._bwd_events = []
         self._build()
 
@@ -244,10 +261,10 @@ class _Engine:
         evs[1].record(self.side)
 
     # -- allocation helpers
-    def buf(self, N, H, W, C, grad=None):
-        b = _Buf(N, H, W, C, self.train if grad is None else grad, self.dev)
+    def buf(self, N, H, W, C, grad=None, planes=True):
+        b = _Buf(N, H, W, C, self.train if grad is None else grad, self.dev, self.parity, planes)
         self.bufs.append(b)
-        self.nbytes += b.t.numel() * 2 * (2 if b.g is not None else 1)
+        self.nbytes += b.t.numel() * b.esz * (2 if b.g is not None else 1) + (b.pl.numel() * 2 if b.pl is not None else 0)
         return b
 
     def _stat(self, n):
@@ -269,6 +286,8 @@ class _Engine:
         gam, bet = net._pflat.data_ptr() + 4 * r.g_off, net._pflat.data_ptr() + 4 * r.b_off
         rm, rv, nbt = r.rm.data_ptr(), r.rv.data_ptr(), r.nbt.data_ptr()
         k, s = (31, 1) if r.is_stem else (r.k, r.stride)  # stem: 3x1 over the tap-gathered staging (yb_prep_input)
+        if self.parity:
+            return self._cbl_parity(r, xin, out, res, up, flops, scale, shift, gam, bet, rm, rv, nbt, k, s)
         if not self.train:
             # eval: BN folded into the conv epilogue (running statistics), SiLU + residual in registers
             plan = _lib.checkp(L.yb_conv_fwd_plan(xin.ptr, xin.N, xin.H, xin.W, xin.C, xin.pitch, w_ptr, C, k, s, out.ptr,
@@ -308,6 +327,49 @@ class _Engine:
         self._dy_elems = max(self._dy_elems, y.npix * C)
         self.tape.append(("cbl", r, xin, out, y, res, up, ptrs, flops))
 
+    # -- parity mode (fp32 activations, six bf16-split passes of the same tcgen05 kernels per conv; csrc/parity.cu)
+    def _parity_conv_plans(self, xin, r, k, s, out_ptr, out_pitch, head=False, bias_ptr=None):
+        net, L = self.net, self.L
+        plans = []
+        for n_, (i, j) in enumerate(PARITY_PASSES):
+            w_ptr = net._wstem_pl[j].data_ptr() if r.is_stem else net._wfwd_pl[j].data_ptr() + 2 * r.w_off
+            kind = (1 if n_ == 0 else 4) if head else (2 if n_ == 0 else 3)
+            plans.append(_lib.checkp(L.yb_conv_fwd_plan(xin.plptr(i), xin.N, xin.H, xin.W, xin.C, xin.pitch, w_ptr, r.cout, k, s,
+                                                        out_ptr, out_pitch, kind, None, bias_ptr if n_ == 0 else None, 0,
+                                                        None, 0, None, None, self.net.head.naxs, 5 + self.net.head.nc)))
+        self.plans += plans
+        return plans
+
+    def _cbl_parity(self, r, xin, out, res, up, flops, scale, shift, gam, bet, rm, rv, nbt, k, s):
+        L, C = self.L, r.cout
+        mean, invstd = self._stat(C), self._stat(C)
+        stats = self._stat(2 * self.max_rows * C)
+        y = self.buf(xin.N, out.H, out.W, C, grad=False, planes=False).v()
+        plans = self._parity_conv_plans(xin, r, k, s, y.ptr, C)
+        count = float(y.npix)
+        ptrs = (stats.data_ptr(), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), invstd.data_ptr())
+        resp, resl = (res.ptr, res.pitch) if res is not None else (None, 0)
+        upa = (up.ptr, up.plptr(0), up.pitch, up.plane_stride) if up is not None else (None, None, 0, 0)
+        train, max_rows = self.train, self.max_rows
+
+        def op(st):
+            for pl in plans:
+                _lib.check(L.yb_plan_run(pl, st))
+            if train:
+                rows = ctypes.c_int(0)
+                _lib.check(L.yb_p32_bn_stats(y.ptr, C, y.npix, C, ptrs[0], max_rows, ctypes.byref(rows), st))
+                _lib.check(L.yb_bn_finalize(ptrs[0], rows.value, C, count, gam, bet, BN_EPS, BN_MOMENTUM, rm, rv, nbt, ptrs[1],
+                                            ptrs[2], ptrs[3], ptrs[4], 1, st))
+            else:
+                _lib.check(L.yb_bn_finalize(None, 0, C, 1.0, gam, bet, BN_EPS, BN_MOMENTUM, rm, rv, None, ptrs[1], ptrs[2], None,
+                                            None, 0, st))
+            _lib.check(L.yb_p32_bn_act_fwd(y.ptr, C, y.N, y.H, y.W, C, ptrs[1], ptrs[2], resp, resl, out.ptr, out.plptr(0),
+                                           out.pitch, out.plane_stride, upa[0], upa[1], upa[2], upa[3], st))
+        self.fwd_ops.append(op)
+        if self.train:
+            self._dy_elems = max(self._dy_elems, y.npix * C)
+            self.tape.append(("cbl", r, xin, out, y, res, up, ptrs, flops))
+
     def c3(self, mod, xin, out):
         c_ = mod.hidden
         N, H, W = xin.N, xin.H, xin.W
@@ -335,8 +397,13 @@ class _Engine:
             src, dst = cat.v(i * c_, c_), cat.v((i + 1) * c_, c_)
             am = torch.empty(N, H, W, c_, device=self.dev, dtype=torch.uint8) if self.train else None
             amp = am.data_ptr() if am is not None else None
-            self.fwd_ops.append(lambda st, src=src, dst=dst, amp=amp: _lib.check(
-                L.yb_maxpool5_fwd(src.ptr, src.pitch, N, H, W, c_, dst.ptr, dst.pitch, amp, st)))
+            if self.parity:
+                self.fwd_ops.append(lambda st, src=src, dst=dst, amp=amp: _lib.check(
+                    L.yb_p32_maxpool5_fwd(src.ptr, src.pitch, N, H, W, c_, dst.ptr, dst.plptr(0), dst.pitch, dst.plane_stride,
+                                          amp, st)))
+            else:
+                self.fwd_ops.append(lambda st, src=src, dst=dst, amp=amp: _lib.check(
+                    L.yb_maxpool5_fwd(src.ptr, src.pitch, N, H, W, c_, dst.ptr, dst.pitch, amp, st)))
             if self.train:
                 self.tape.append(("pool", src, dst, am))
         self.cbl(mod.c_out, cat.v(), out)
@@ -346,12 +413,28 @@ class _Engine:
         r = net._rec_of[net.head.out_convs[i]]
         na, no = net.head.naxs, 5 + net.head.nc
         out = torch.empty(xin.N, na, xin.H, xin.W, no, device=self.dev, dtype=torch.float32)
+        flops = 2.0 * xin.npix * r.cout * r.cin
+        self.conv_flops["fwd"] += flops
+        if self.parity:
+            plans = self._parity_conv_plans(xin, r, 1, 1, out.data_ptr(), r.cout, head=True,
+                                            bias_ptr=net._pflat.data_ptr() + 4 * r.bias_off)
+
+            def op(st):
+                for pl in plans:
+                    _lib.check(L.yb_plan_run(pl, st))
+            self.fwd_ops.append(op)
+            self.outs.append(out)
+            if self.train:
+                dyh = torch.zeros(xin.N, xin.H, xin.W, HEAD_PAD, device=self.dev, dtype=torch.float32)
+                dyp = torch.zeros(3, xin.N, xin.H, xin.W, HEAD_PAD, device=self.dev, dtype=torch.bfloat16)
+                self.head_dy.append(dyh)
+                self.head_dy_pl.append(dyp)
+                self.tape.append(("head", r, xin, (dyh, dyp), flops))
+            return
         plan = _lib.checkp(L.yb_conv_fwd_plan(xin.ptr, xin.N, xin.H, xin.W, xin.C, xin.pitch,
                                               net._wfwd.data_ptr() + 2 * r.w_off, r.cout, 1, 1, out.data_ptr(), r.cout, 1,
                                               None, net._pflat.data_ptr() + 4 * r.bias_off, 0, None, 0, None, None, na, no))
         self.plans.append(plan)
-        flops = 2.0 * xin.npix * r.cout * r.cin
-        self.conv_flops["fwd"] += flops
         self.fwd_ops.append(lambda st: self._conv(plan, st, flops, "fwd"))
         self.outs.append(out)
         if self.train:
@@ -363,7 +446,7 @@ class _Engine:
         net, B, H, W = self.net, self.B, self.H, self.W
         bb, nk = net.backbone, net.neck
         c = net._first_out
-        self.outs, self.head_dy = [], []
+        self.outs, self.head_dy, self.head_dy_pl = [], [], []
         self.x16 = self.buf(B, H // 2, W // 2, 48, grad=False)  # stem staging: space-to-depth + gathered horizontal taps
         b0 = self.buf(B, H // 2, W // 2, c); self.cbl(bb[0], self.x16.v(), b0.v())
         b1 = self.buf(B, H // 4, W // 4, 2 * c); self.cbl(bb[1], b0.v(), b1.v())
@@ -391,8 +474,9 @@ class _Engine:
             self.head(i, p.v())
         if self.train:
             ndy = 2 if self.side is not None else 1  # double-buffered when wgrad(L) overlaps the BN backward of L-1
-            self.dy = [torch.empty(self._dy_elems, device=self.dev, dtype=torch.bfloat16) for _ in range(ndy)]
-            self.nbytes += self._dy_elems * 2 * ndy
+            npl = 3 if self.parity else 1            # parity: the three bf16 planes of dy, _dy_elems apart
+            self.dy = [torch.empty(npl * self._dy_elems, device=self.dev, dtype=torch.bfloat16) for _ in range(ndy)]
+            self.nbytes += self._dy_elems * 2 * ndy * npl
             self._build_backward()
 
     def _add_bwd_op(self, op, writes):
@@ -424,8 +508,9 @@ class _Engine:
             if c0 >= view.c0 and c0 + C <= view.c0 + view.C:
                 tgt = view.buf.v(c0, C)
                 acc = 1 if self._contrib_state(tgt) else 0
-                self.bwd_ops.append(lambda st, g, src=src, tgt=tgt, acc=acc: _lib.check(
-                    L.yb_add_into(src.gptr, src.pitch, tgt.gptr, tgt.pitch, tgt.npix, tgt.C, acc, st)))
+                add_into = L.yb_p32_add_into if self.parity else L.yb_add_into
+                self.bwd_ops.append(lambda st, g, src=src, tgt=tgt, acc=acc, add_into=add_into: _lib.check(
+                    add_into(src.gptr, src.pitch, tgt.gptr, tgt.pitch, tgt.npix, tgt.C, acc, st)))
                 view.buf.gw[c0:c0 + C] = True
             else:
                 keep.append((c0, C, src))
@@ -438,6 +523,21 @@ class _Engine:
                 return src
         return None
 
+    def _parity_bwd_plans(self, r, xin, dy_ptr, dy_ps, Cdy, k, s, acc, ws, wsn):
+        """parity mode: the six dgrad passes (dy plane i x weight plane j -> fp32 xin.g, accumulating) and the six wgrad
+        passes (x plane i x dy plane j) of one conv; dy planes are dy_ps elements apart"""
+        net, L = self.net, self.L
+        dplans, wplans = [], []
+        for n_, (i, j) in enumerate(PARITY_PASSES):
+            if not r.is_stem:
+                dplans.append(_lib.checkp(L.yb_conv_dgrad_plan(dy_ptr + 2 * i * dy_ps, xin.N, xin.H, xin.W, Cdy, Cdy,
+                                                               net._wdg_pl[j].data_ptr() + 2 * r.wt_off, xin.C, k, s,
+                                                               xin.gptr, xin.pitch, None, 0, 3 if (acc or n_) else 2)))
+            wplans.append(_lib.checkp(L.yb_conv_wgrad_plan(xin.plptr(i), xin.N, xin.H, xin.W, xin.C, xin.pitch,
+                                                           dy_ptr + 2 * j * dy_ps, Cdy, Cdy, k, s, ws, wsn, 0)))
+        self.plans += dplans + wplans
+        return dplans, wplans
+
     def _build_backward(self):
         net, L = self.net, self.L
         redp, coefp = self.red_partial.data_ptr(), self.coef.data_ptr()
@@ -445,7 +545,24 @@ class _Engine:
         nlayer, done_by_slot = 0, {}
         for rec in reversed(self.tape):
             kind = rec[0]
-            if kind == "head":
+            if kind == "head" and self.parity:
+                _, r, xin, (dyh, dypl), flops = rec
+                npix, ps = xin.npix, dyh.numel()
+                acc = 1 if self._contrib_state(xin) else 0
+                xin.buf.gw[xin.c0:xin.c0 + xin.C] = True
+                dplans, wplans = self._parity_bwd_plans(r, xin, dypl.data_ptr(), ps, HEAD_PAD, 1, 1, acc, ws, wsn)
+
+                def op(st, g, r=r, dyh=dyh, npix=npix, dplans=dplans, wplans=wplans):
+                    rows = ctypes.c_int(0)
+                    _lib.check(L.yb_p32_bn_stats(dyh.data_ptr(), HEAD_PAD, npix, HEAD_PAD, redp, self.red_rows,
+                                                 ctypes.byref(rows), st))
+                    _lib.check(L.yb_reduce_rows(redp, rows.value, 2 * HEAD_PAD, r.cout, g + 4 * r.bias_off, 0, st))
+                    for pl in dplans:
+                        _lib.check(L.yb_plan_run(pl, st))
+                    for n_, pl in enumerate(wplans):
+                        _lib.check(L.yb_wgrad_plan_run(pl, g + 4 * r.w_off, r.cout, None, 1 if n_ else 0, st))
+                self._add_bwd_op(op, [(r.bias_off, r.cout), (r.w_off, r.cout * r.cin)])
+            elif kind == "head":
                 _, r, xin, dyh, flops = rec
                 self.conv_flops["dgrad"] += flops
                 self.conv_flops["wgrad"] += flops
@@ -456,7 +573,7 @@ class _Engine:
                 acc = 1 if self._contrib_state(xin) else 0
                 dplan = _lib.checkp(L.yb_conv_dgrad_plan(dyp, xin.N, xin.H, xin.W, HEAD_PAD, HEAD_PAD,
                                                          net._wdg.data_ptr() + 2 * r.wt_off, xin.C, 1, 1, xin.gptr,
-                                                         xin.pitch, xin.gptr if acc else None, xin.pitch if acc else 0))
+                                                         xin.pitch, xin.gptr if acc else None, xin.pitch if acc else 0, 0))
                 self.plans += [wplan, dplan]
                 xin.buf.gw[xin.c0:xin.c0 + xin.C] = True
                 rows = ctypes.c_int(0)
@@ -474,9 +591,9 @@ class _Engine:
                 self._flush_pending(dst)
                 acc = 1 if self._contrib_state(src) else 0
                 src.buf.gw[src.c0:src.c0 + src.C] = True
-                self.bwd_ops.append(lambda st, g, src=src, dst=dst, am=am, acc=acc: _lib.check(
-                    L.yb_maxpool5_bwd(dst.gptr, dst.pitch, am.data_ptr(), src.N, src.H, src.W, src.C, src.gptr, src.pitch,
-                                      acc, st)))
+                pool_bwd = L.yb_p32_maxpool5_bwd if self.parity else L.yb_maxpool5_bwd
+                self.bwd_ops.append(lambda st, g, src=src, dst=dst, am=am, acc=acc, pool_bwd=pool_bwd: _lib.check(
+                    pool_bwd(dst.gptr, dst.pitch, am.data_ptr(), src.N, src.H, src.W, src.C, src.gptr, src.pitch, acc, st)))
             else:
                 _, r, xin, out, y, res, up, ptrs, flops = rec
                 self.conv_flops["wgrad"] += flops
@@ -496,10 +613,39 @@ class _Engine:
                 assert self._contrib_state(out), f"{r.name}: output gradient never produced"
                 if up is not None:
                     assert self._contrib_state(up), f"{r.name}: upsampled gradient never produced"
-                    self.bwd_ops.append(lambda st, g, up=up, out=out: _lib.check(
-                        L.yb_upsample2x_bwd(up.gptr, up.pitch, out.N, out.H, out.W, out.C, out.gptr, out.pitch, 1, st)))
+                    up_bwd = L.yb_p32_upsample2x_bwd if self.parity else L.yb_upsample2x_bwd
+                    self.bwd_ops.append(lambda st, g, up=up, out=out, up_bwd=up_bwd: _lib.check(
+                        up_bwd(up.gptr, up.pitch, out.N, out.H, out.W, out.C, out.gptr, out.pitch, 1, st)))
                 if res is not None:
                     res.buf.pending.append((res.c0, res.C, out))
+                if self.parity:
+                    acc = 0
+                    if not r.is_stem:
+                        src = self._take_pending_exact(xin)
+                        written = self._contrib_state(xin)
+                        if src is not None:  # identity (residual) contribution: copy / add it first, then accumulate the dgrad
+                            self.bwd_ops.append(lambda st, g, src=src, xin=xin, a=1 if written else 0: _lib.check(
+                                L.yb_p32_add_into(src.gptr, src.pitch, xin.gptr, xin.pitch, xin.npix, xin.C, a, st)))
+                        acc = 1 if (src is not None or written) else 0
+                        xin.buf.gw[xin.c0:xin.c0 + xin.C] = True
+                    dplans, wplans = self._parity_bwd_plans(r, xin, dy_ptr, self._dy_elems, C, k, s, acc, ws, wsn)
+                    mapp = net._stem_map.data_ptr() if r.is_stem else None
+                    count = float(npix)
+
+                    def op(st, g, r=r, out=out, y=y, ptrs=ptrs, C=C, npix=npix, dplans=dplans, wplans=wplans, mapp=mapp,
+                           count=count, dy_ptr=dy_ptr):
+                        rows = ctypes.c_int(0)
+                        _lib.check(L.yb_p32_bn_act_bwd_reduce(out.gptr, out.pitch, y.ptr, C, npix, C, ptrs[1], ptrs[2], ptrs[3],
+                                                              ptrs[4], redp, self.red_rows, ctypes.byref(rows), st))
+                        _lib.check(L.yb_bn_bwd_finalize(redp, rows.value, C, count, g + 4 * r.g_off, g + 4 * r.b_off, coefp, 0, st))
+                        _lib.check(L.yb_p32_bn_act_bwd_apply(out.gptr, out.pitch, y.ptr, C, npix, C, ptrs[1], ptrs[2], ptrs[3],
+                                                             ptrs[4], coefp, None, dy_ptr, C, self._dy_elems, st))
+                        for pl in dplans:
+                            _lib.check(L.yb_plan_run(pl, st))
+                        for n_, pl in enumerate(wplans):
+                            _lib.check(L.yb_wgrad_plan_run(pl, g + 4 * r.w_off, C, mapp, 1 if n_ else 0, st))
+                    self._add_bwd_op(op, [(r.g_off, C), (r.b_off, C), (r.w_off, r.conv.weight.numel())])
+                    continue
                 wplan = _lib.checkp(L.yb_conv_wgrad_plan(xin.ptr, xin.N, xin.H, xin.W, xin.C, xin.pitch, dy_ptr, C, C, k, s,
                                                          ws, wsn, 0))
                 self.plans.append(wplan)
@@ -519,7 +665,7 @@ class _Engine:
                         addp, addl = None, 0
                     dplan = _lib.checkp(L.yb_conv_dgrad_plan(dy_ptr, xin.N, xin.H, xin.W, C, C,
                                                              net._wdg.data_ptr() + 2 * r.wt_off, xin.C, k, s, xin.gptr,
-                                                             xin.pitch, addp, addl))
+                                                             xin.pitch, addp, addl, 0))
                     self.plans.append(dplan)
                     xin.buf.gw[xin.c0:xin.c0 + xin.C] = True
                 mapp = net._stem_map.data_ptr() if r.is_stem else None
@@ -546,7 +692,15 @@ class _Engine:
         st = _lib.stream()
         dt = 0 if x.dtype == torch.float32 else 1
         Hs, Ws = x.shape[2], x.shape[3]
-        if (Hs, Ws) == (self.H, self.W):
+        if self.parity:
+            # three fp32 NCHW planes of the image (each bf16-exact), each staged like the production input
+            if (Hs, Ws) != (self.H, self.W):
+                raise _lib.YBError("parity mode: multi-scale resampling is not available (resize the batch first)")
+            xp = torch.empty((3,) + tuple(x.shape), device=self.dev, dtype=torch.float32)
+            _lib.check(L.yb_p32_split_flat(x.data_ptr(), dt, x.numel(), xp[0].data_ptr(), xp[1].data_ptr(), xp[2].data_ptr(), st))
+            for k in range(3):
+                _lib.check(L.yb_prep_input(xp[k].data_ptr(), 0, self.B, self.H, self.W, self.x16.v().plptr(k), st))
+        elif (Hs, Ws) == (self.H, self.W):
             _lib.check(L.yb_prep_input(x.data_ptr(), dt, self.B, self.H, self.W, self.x16.t.data_ptr(), st))
         else:  # multi-scale training: bilinear resample fused into the stem staging (training_utils.py:11-28)
             _lib.check(L.yb_prep_input_resized(x.data_ptr(), dt, self.B, Hs, Ws, self.H, self.W, self.x16.t.data_ptr(), st))
@@ -602,9 +756,15 @@ class _NetFn(torch.autograd.Function):
             if go is None or sentinel:
                 if not fast:
                     dyh.zero_()
+                    if eng.parity:
+                        eng.head_dy_pl[i].zero_()
                 continue
             go = go.contiguous().float()
             B, na, H, W, no = go.shape
+            if eng.parity:
+                _lib.check(L.yb_p32_head_grad_pack(go.data_ptr(), B, na, H, W, no, dyh.data_ptr(), eng.head_dy_pl[i].data_ptr(),
+                                                   HEAD_PAD, dyh.numel(), 0, st))
+                continue
             _lib.check(L.yb_head_grad_pack(go.data_ptr(), B, na, H, W, no, dyh.data_ptr(), HEAD_PAD, 1 if fast else 0, st))
         eng.head_ready = False
         if net._accumulate_grads and not net.expose_param_grads:
@@ -651,6 +811,9 @@ class YOLOV5m(nn.Module):
         # True: backward publishes p.grad views of the flat gradient bucket (stock torch optimisers work);
         # False: gradients stay only in `flat_grads` (yolov5m_b200.trainer.Adam reads the bucket) -- saves 243 view objects
         self.expose_param_grads = True
+        # fp32 parity mode (csrc/parity.cu): fp32 activations / gradients, every conv = six bf16-split passes of the same
+        # tcgen05 kernels.  A numerics instrument for BASELINE config 2 ("fp32 vs reference", 1e-3), not the fast path.
+        self.parity = os.environ.get("YB_PARITY", "0") == "1"
         self._accumulate_grads = False  # set by trainer.TrainStep around the backward of an accumulated micro-batch
         self._flatten()
 
@@ -745,7 +908,7 @@ class YOLOV5m(nn.Module):
         return self
 
     def _param_signature(self):
-        return sum(p._version for p in self.parameters())
+        return (sum(p._version for p in self.parameters()), self.parity)
 
     def refresh_packed(self, force=False):
         """bf16 tensor-core operands derived from the fp32 master weights (re-run after any parameter update)."""
@@ -755,7 +918,27 @@ class YOLOV5m(nn.Module):
         L, st = _lib.lib(), _lib.stream()
         _lib.check(L.yb_cast_bf16(self._pflat.data_ptr(), self._wfwd.data_ptr(), self._pflat.numel(), st))
         self._repack_derived(st)
+        if self.parity:
+            self._pack_parity(st)
         self._packed_sig = sig
+
+    def _pack_parity(self, st):
+        """parity mode: the three bf16 planes of every tensor-core operand (forward, dgrad and stem layouts), produced by
+        the SAME packing kernels from the three bf16-exact fp32 planes of the master weights"""
+        L, n = _lib.lib(), self._pflat.numel()
+        dev = self._pflat.device
+        if getattr(self, "_wfwd_pl", None) is None or self._wfwd_pl[0].device != dev:
+            self._wfwd_pl = [torch.zeros_like(self._wfwd) for _ in range(3)]
+            self._wdg_pl = [torch.zeros_like(self._wdg) for _ in range(3)]
+            self._wstem_pl = [torch.zeros_like(self._wstem) for _ in range(3)]
+        pf = torch.empty(3, n, device=dev, dtype=torch.float32)
+        _lib.check(L.yb_p32_split_flat(self._pflat.data_ptr(), 0, n, pf[0].data_ptr(), pf[1].data_ptr(), pf[2].data_ptr(), st))
+        s = self._stem_rec
+        for k in range(3):
+            _lib.check(L.yb_cast_bf16(pf[k].data_ptr(), self._wfwd_pl[k].data_ptr(), n, st))
+            _lib.check(L.yb_repack_dgrad(pf[k].data_ptr(), self._wdg_pl[k].data_ptr(), self._dg_table.data_ptr(),
+                                         self._dg_table.shape[0], self._wdg_elems, st))
+            _lib.check(L.yb_repack_stem(pf[k].data_ptr() + 4 * s.w_off, self._wstem_pl[k].data_ptr(), s.cout, st))
 
     def _repack_derived(self, st):
         L = _lib.lib()
@@ -805,10 +988,10 @@ class YOLOV5m(nn.Module):
     _ENGINE_CACHE_BYTES = int(float(os.environ.get("YB_ENGINE_CACHE_GB", "100")) * (1 << 30))
 
     def engine(self, B, H, W, train):
-        key = (B, H, W, bool(train))
+        key = (B, H, W, bool(train), bool(self.parity))
         e = self._engines.get(key)
         if e is None:
-            e = _Engine(self, B, H, W, train)
+            e = _Engine(self, B, H, W, train, bool(self.parity))
             while self._engines and sum(v.nbytes for v in self._engines.values()) + e.nbytes > self._ENGINE_CACHE_BYTES:
                 self._engines.pop(next(iter(self._engines)))
             self._engines[key] = e

@@ -76,6 +76,8 @@ class Adam:
                                   self.grad_norm.data_ptr(), model._wfwd.data_ptr(), st))
         self._device_steps = device_step
         model._repack_derived(st)                     # dgrad-layout / stem operands from the updated masters
+        if model.parity:
+            model._pack_parity(st)
         model._packed_sig = model._param_signature()  # the bf16 operands are current
 
     def steps_taken(self):
