@@ -37,11 +37,21 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--bs", type=int, default=64, help="images per GPU (the metric is quoted at 64)")
-    ap.add_argument("--size", type=int, default=640)
+    ap.add_argument("--workload", default="train", choices=["train", "detect"],
+                    help="train = BASELINE configs[2]/[3] (the headline metric); detect = configs[4]: bs=128 1280x1280 eval "
+                         "forward + cells_to_bboxes + non_max_suppression(conf .25, iou .45), detect.py:50-54")
+    ap.add_argument("--cand-frac", type=float, default=0.02,
+                    help="detect: fraction of cells whose objectness passes conf 0.25 (D1 'realistic' of SURVEY.md 8d; 1.0 = D2)")
+    ap.add_argument("--bs", type=int, default=None, help="images per GPU (train: 64, detect: 128 -- the metrics' configs)")
+    ap.add_argument("--size", type=int, default=None, help="image side (train: 640, detect: 1280)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.bs is None:
+        a.bs = 64 if a.workload == "train" else 128
+    if a.size is None:
+        a.size = 640 if a.workload == "train" else 1280
+    return a
 
 
 def peaks():
@@ -158,6 +168,239 @@ def run_reference(a):
         "cpu_baseline": {"value": ips, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+
+# ---------------------------------------------------------------------------------------------------- detect workload
+DETECT_METRIC = "detect_images_per_sec_1280x1280_bs128"
+DETECT_GFLOP_PER_IMG_640 = 48.872  # forward convs at 640x640; scales with the pixel count
+
+
+def calibrate_detector(model, cal_images, first_batch, cand_frac, conf=0.25):
+    """D1 of SURVEY.md 8(d), made reproducible for a random-init network (both arms use exactly this recipe):
+      1. ONE train-mode forward on `cal_images` with BatchNorm momentum 1.0: the running statistics become that batch's
+         statistics, so the eval-mode activations are normalised (a freshly constructed network with running mean 0 / var 1
+         lets the signal die out: every logit equals its bias and either all or none of the cells pass);
+      2. the objectness bias of the three heads is shifted so that `cand_frac` of the cells of `first_batch` pass `conf`.
+    Works on the reference nn.Module and on the drop-in alike (same attribute surface)."""
+    import math
+    import torch
+    bns = [m for m in model.modules() if hasattr(m, "running_mean") and hasattr(m, "momentum")]
+    old = [m.momentum for m in bns]
+    for m in bns:
+        m.momentum = 1.0
+    model.train()
+    with torch.no_grad():
+        model(cal_images)
+    for m, o in zip(bns, old):
+        m.momentum = o
+    model.eval()
+    if cand_frac >= 1.0:
+        return 1.0
+    with torch.no_grad():
+        out = model(first_batch)
+        obj = torch.cat([o[..., 4].reshape(-1).float() for o in out])
+        k = max(1, int(round(obj.numel() * (1.0 - cand_frac))))
+        q = torch.kthvalue(obj.cpu(), k).values.item()
+        shift = math.log(conf / (1.0 - conf)) - q
+        for conv in model.head.out_convs:
+            conv.bias.data.view(3, -1)[:, 4] += shift
+        out = model(first_batch)
+        frac = float(torch.cat([(o[..., 4].reshape(-1).float() > math.log(conf / (1.0 - conf))).float() for o in out]).mean())
+    return frac
+
+
+def detect_inputs(bs, size, seed=3):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    cal = torch.randint(0, 256, (2, 3, 640, 640), dtype=torch.uint8, generator=g)
+    x = torch.randint(0, 256, (bs, 3, size, size), dtype=torch.uint8, generator=g)
+    return cal, x
+
+
+def run_reference_detect(a):
+    """the reference's own detect path (detect.py:50-54: model -> cells_to_bboxes -> non_max_suppression) on the host cores"""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    try:
+        from baseline.ref_step import RefDetector
+        det, kind = RefDetector(), "reference"
+    except Exception as e:
+        print(json.dumps({"impl": "reference", "unavailable": f"reference not importable for the detect workload: {e!r}"}))
+        return
+    bs = 2
+    cal, x = detect_inputs(bs, a.size)
+    frac = calibrate_detector(det.model, cal.float() / 255, x.float() / 255, a.cand_frac)
+    xf = x.float() / 255
+    steps, warm = max(1, min(a.steps, 3)), min(a.warmup, 1)
+    for _ in range(warm):
+        det.detect(xf)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        kept = det.detect(x.float() / 255)   # detect.py:47: img.float() / 255 is part of the path
+    dt = (time.perf_counter() - t0) / steps
+    ips = bs / dt
+    sample = (f"{steps} timed + {warm} warm-up detect passes at bs={bs}, {a.size}x{a.size}, fp32, the unmodified reference "
+              f"(model.py, utils/plot_utils.py cells_to_bboxes, utils/bboxes_utils.py non_max_suppression)")
+    print(json.dumps({
+        "impl": "reference", "metric": DETECT_METRIC, "value": ips, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": "configs[4]: detect (eval fwd + cells_to_bboxes + NMS conf .25 iou .45), CPU host cores",
+                   "batch_per_step": bs, "image": a.size, "candidate_fraction": frac,
+                   "kept_per_image": sum(len(k) for k in kept) / bs},
+        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": det.threads, "kind": kind, "sample": sample},
+        "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_ours_detect(a):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:  # replicas only: no collective on the detect path (SURVEY.md 8e); the group is used for barrier / max
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+    from yolov5m_b200.build import build
+    build()
+    import yolov5m_b200 as yb
+    from yolov5m_b200 import _lib
+    from yolov5m_b200.boxes import nms_device
+    L = _lib.lib()
+    torch.manual_seed(0)
+    model = yb.YOLOV5m(first_out=yb.FIRST_OUT, nc=80, anchors=yb.ANCHORS, ch=(192, 384, 768)).to(dev)
+    B, S = a.bs, a.size
+    cal, x_host = detect_inputs(B, S, seed=3 + rank)
+    x_host = x_host.pin_memory()
+    x_dev = x_host.to(dev)
+    frac = calibrate_detector(model, cal.to(dev), x_dev, a.cand_frac)
+    model.eval()
+    CONF, IOU, MAXDET = 0.25, 0.45, 300
+
+    def detect(x):  # detect.py:50-54 on device tensors
+        with torch.no_grad():
+            out = model(x)
+            dec = yb.cells_to_bboxes(out, model.head.anchors, model.head.stride, is_pred=True, to_list=False)
+            return nms_device(dec, IOU, CONF, MAXDET), out, dec
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
+    windows = []
+    for _ in range(a.warmup):
+        detect(x_dev)
+    barrier()
+    l0 = L.yb_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
+    e0.record()
+    for _ in range(a.steps):
+        (rows, counts), out, dec = detect(x_dev)
+    e1.record()
+    barrier()
+    windows.append((w0, time.perf_counter()))
+    launches = L.yb_launch_count() - l0
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    value = world * B * a.steps / (ms * 1e-3)
+
+    # per-stage device times (CUDA events on the launching stream) -> rooflines of the stages
+    def stage(fn, n=3):
+        fn()
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(n):
+            r = fn()
+        s1.record()
+        torch.cuda.synchronize()
+        return s0.elapsed_time(s1) / n * 1e-3, r
+
+    with torch.no_grad():
+        t_f, out = stage(lambda: model(x_dev))
+        t_d, dec = stage(lambda: yb.cells_to_bboxes(out, model.head.anchors, model.head.stride, is_pred=True, to_list=False))
+        t_n, (rows, counts) = stage(lambda: nms_device(dec, IOU, CONF, MAXDET))
+    peak_tf, peak_hbm, peak_src = peaks()
+    cells = sum(o.numel() // o.shape[-1] for o in out)
+    dec_bytes = cells * (out[0].shape[-1] * 4 + 6 * 4)            # every logit read once, 6 floats written per cell
+    fwd_flop = DETECT_GFLOP_PER_IMG_640 * 1e9 * (S * S) / (640.0 * 640.0) * B
+    cand = int((dec[..., 1] > CONF).sum().item())
+
+    # end to end through the public API: pinned uint8 batch -> H2D -> forward -> decode -> NMS -> rows + counts D2H
+    e2e = None
+    if not a.no_e2e:
+        stage_x = torch.empty_like(x_dev)
+        rows_h = torch.empty(B, MAXDET, 6, dtype=torch.float32).pin_memory()
+        cnt_h = torch.empty(B, dtype=torch.int32).pin_memory()
+
+        def e2e_loop(n):
+            for _ in range(n):
+                stage_x.copy_(x_host, non_blocking=True)
+                (r, c), _, _ = detect(stage_x)
+                rows_h.copy_(r, non_blocking=True)
+                cnt_h.copy_(c, non_blocking=True)
+                torch.cuda.synchronize()  # the caller consumes the detections of every batch
+        e2e_loop(1)
+        barrier()
+        w0 = time.perf_counter()
+        e0.record()
+        e2e_loop(a.steps)
+        e1.record()
+        barrier()
+        windows.append((w0, time.perf_counter()))
+        ms_e = max_over_ranks(e0.elapsed_time(e1))
+        e2e = {"value": world * B * a.steps / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel()) * world,
+               "d2h_bytes_per_step": int(rows_h.numel() * 4 + cnt_h.numel() * 4) * world, "ms_per_step": ms_e / a.steps}
+
+    if rank == 0:
+        clocks.stop()
+        # keep sets of a few images against the oracle on the SAME decoded tensor (bit-exact contract)
+        from oracle import nms_ref
+        nchk = min(2, B)
+        ref, _ = nms_ref.non_max_suppression(dec[:nchk].cpu(), IOU, CONF, MAXDET)
+        import numpy as np
+        exact = all(int(counts[i]) == len(ref[i]) and
+                    np.array_equal(rows[i, : len(ref[i])].cpu().numpy(), ref[i].astype(np.float32)) for i in range(nchk))
+        out_line = {
+            "metric": DETECT_METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": "configs[4]: detect.py path, bs=128 1280x1280 eval forward + cells_to_bboxes + "
+                                   "non_max_suppression(conf .25, iou .45, max_det 300); replicas only for N > 1",
+                       "batch_per_gpu": B, "image": S, "candidate_fraction": frac, "candidates_per_image": cand / B,
+                       "kept_per_image": float(counts.float().mean().item()), "keep_sets_bit_exact_vs_oracle": bool(exact),
+                       "l2_policy": "inputs larger than L2 (629 MB of images, 4.4 GB of logits per step)"},
+            "roofline": {"bound": "hbm", "kernel": "decode_pred_kernel (cells_to_bboxes, 3 launches / step)",
+                         "achieved": dec_bytes / t_d / 1e9, "peak": peak_hbm, "peak_source": peak_src + " hbm_gbs",
+                         "unit": "GB/s", "frac": dec_bytes / t_d / 1e9 / peak_hbm, "traffic": None,
+                         "algorithmic_bytes_per_step": dec_bytes, "ms_per_step": t_d * 1e3},
+            "stages": {"forward": {"ms": t_f * 1e3, "tflops": fwd_flop / t_f / 1e12, "frac_of_bf16_peak": fwd_flop / t_f / 1e12 / peak_tf},
+                       "decode": {"ms": t_d * 1e3, "GBps": dec_bytes / t_d / 1e9},
+                       "nms": {"ms": t_n * 1e3, "candidates_per_image": cand / B}},
+            "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary(windows),
+        }
+        print(json.dumps(out_line))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # ---------------------------------------------------------------------------------------------------- our arm (GPU)
@@ -347,9 +590,9 @@ def main():
     sys.stdout = real_stdout
     try:
         if a.impl == "reference":
-            run_reference(a)
+            run_reference_detect(a) if a.workload == "detect" else run_reference(a)
         else:
-            run_ours(a)
+            run_ours_detect(a) if a.workload == "detect" else run_ours(a)
     finally:
         real_stdout.flush()
 

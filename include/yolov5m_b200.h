@@ -263,6 +263,11 @@ int yb_yolo_build_targets(const double* labels, const int* offsets, int B, int n
 int yb_decode_level(const float* p, int B, int na, int H, int W, int no, float stride, const float* anchors_px, int is_pred,
                     float* out, int64_t rows_per_image, int64_t level_off, void* stream);
 int64_t yb_nms_scratch_bytes(int B, int64_t N);
+/* YOLO_EVAL.check_class_accuracy for one level (utils/validation_utils.py:58-69): p (cells, no) logits, y (cells, ny) label
+ * rows [x, y, w, h, objectness, class]; over the cells with y[4] == 1: counters[0] += 1, counters[1] += (argmax(p[5:]) ==
+ * y[5]), counters[2] += (sigmoid(p[0]) > conf) -- channel 0, as the reference has it.  counters: device uint64 [3]. */
+int yb_class_accuracy(const float* p, const float* y, int64_t cells, int no, int ny, float conf, uint64_t* counters,
+                      void* stream);
 int yb_nms_batched(const float* boxes, int B, int64_t N, float iou_threshold, float threshold, int max_det, void* scratch,
                    float* out, int* out_count, int* out_index, int* cand_count, void* stream);
 

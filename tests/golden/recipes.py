@@ -96,3 +96,60 @@ def yolo_labels(seed, b, max_boxes=6):
             lab[1, 3:5] = lab[0, 3:5] * 1.05  # near-identical shape: same anchor ranking
         out.append(lab)
     return tuple(out)
+
+
+class StubModel:
+    """stands in for the network in the eval-glue fixtures: returns fixed head tensors batch after batch"""
+
+    class _Head:
+        def __init__(self, anchors):
+            self.nc, self.nl, self.naxs = 80, 3, 3
+            self.anchors = anchors
+            self.stride = [8, 16, 32]
+
+    def __init__(self, outputs, device=None):
+        from oracle import model_ref
+        self.head = StubModel._Head(model_ref.head_anchors() if device is None else model_ref.head_anchors().to(device))
+        self.outputs, self.k, self.device, self.training = outputs, 0, device, False
+
+    def eval(self):
+        self.training = False
+        return self
+
+    def train(self, mode=True):
+        self.training = mode
+        return self
+
+    def __call__(self, images):
+        out = self.outputs[self.k % len(self.outputs)]
+        self.k += 1
+        return [o.clone() if self.device is None else o.to(self.device) for o in out]
+
+
+def eval_batches(nb=2, b=2, h=128, w=96):
+    """[(uint8 images, [label tensors (B,3,H/s,W/s,6)], [head tensors])] for the eval-glue fixtures; the label tensors
+    are Validation_Dataset-style dense targets [x_cell, y_cell, w_cell, h_cell, objectness, class]"""
+    out = []
+    for k in range(nb):
+        g = torch.Generator().manual_seed(900 + k)
+        img = torch.randint(0, 256, (b, 3, h, w), dtype=torch.uint8, generator=g)
+        labels = []
+        for s in (8, 16, 32):
+            t = torch.zeros(b, 3, h // s, w // s, 6)
+            n = 5
+            bi = torch.randint(0, b, (n,), generator=g); ai = torch.randint(0, 3, (n,), generator=g)
+            yi = torch.randint(0, h // s, (n,), generator=g); xi = torch.randint(0, w // s, (n,), generator=g)
+            t[bi, ai, yi, xi, 0:2] = torch.rand(n, 2, generator=g)
+            t[bi, ai, yi, xi, 2:4] = torch.rand(n, 2, generator=g) * 3 + 0.3
+            t[bi, ai, yi, xi, 4] = 1.0
+            t[bi, ai, yi, xi, 5] = torch.randint(0, 80, (n,), generator=g).float()
+            labels.append(t)
+        heads = head_outputs(950 + k, b, h, w, scale=1.5)
+        for lv, t in zip(heads, labels):   # make the "network" right on most labelled cells so the accuracies are not trivial
+            obj = t[..., 4] == 1
+            cls = t[..., 5][obj].long()
+            rows = lv[obj]
+            rows[torch.arange(rows.shape[0]) % 4 != 0, 5 + cls[torch.arange(rows.shape[0]) % 4 != 0]] += 8.0
+            lv[obj] = rows
+        out.append((img, labels, heads))
+    return out

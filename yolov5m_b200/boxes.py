@@ -21,9 +21,17 @@ def cells_to_bboxes(predictions, anchors, strides, is_pred=False, to_list=True, 
     list when ``to_list`` (the reference default) else as a tensor."""
     if list_output is not None:
         to_list = list_output
-    L, st = _lib.lib(), _lib.stream()
     src_dev = predictions[0].device
     dev = src_dev if src_dev.type == "cuda" else _dev()
+    with torch.cuda.device(dev):  # launches follow the tensors' device, whatever the process's current device is
+        out = _decode(predictions, anchors, strides, is_pred, dev)
+    if to_list:
+        return out.tolist()
+    return out if src_dev.type == "cuda" else out.to(src_dev)
+
+
+def _decode(predictions, anchors, strides, is_pred, dev):
+    L, st = _lib.lib(), _lib.stream()
     preds = [p.to(device=dev, dtype=torch.float32).contiguous() for p in predictions]
     anchors = torch.as_tensor(anchors).to(device=dev, dtype=torch.float32)
     B = preds[0].shape[0]
@@ -39,9 +47,7 @@ def cells_to_bboxes(predictions, anchors, strides, is_pred=False, to_list=True, 
         _lib.check(L.yb_decode_level(p.data_ptr(), B, na, H, W, no, float(strides[i]), apx.data_ptr(), 1 if is_pred else 0,
                                      out.data_ptr(), total, off, st))
         off += rows[i]
-    if to_list:
-        return out.tolist()
-    return out if src_dev.type == "cuda" else out.to(src_dev)
+    return out
 
 
 class _NmsScratch:
@@ -56,8 +62,13 @@ class _NmsScratch:
 
 def nms_device(batch_bboxes, iou_threshold, threshold, max_detections=300, want_index=False):
     """(B,N,6) CUDA tensor -> (rows (B,max_det,6), counts (B,) int32[, index (B,max_det) int32]) all on the GPU, no sync."""
-    L, st = _lib.lib(), _lib.stream()
     bb = batch_bboxes
+    with torch.cuda.device(bb.device):
+        return _nms_device(bb, iou_threshold, threshold, max_detections, want_index)
+
+
+def _nms_device(bb, iou_threshold, threshold, max_detections, want_index):
+    L, st = _lib.lib(), _lib.stream()
     B, N, _ = bb.shape
     dev = bb.device
     out = torch.zeros(B, max_detections, 6, device=dev, dtype=torch.float32)
@@ -104,6 +115,7 @@ def intersection_over_union(boxes_preds, boxes_labels, box_format="midpoint", GI
     a, b = a.contiguous(), b.contiguous()
     out = torch.empty(a.shape[:-1] + (1,), device=dev, dtype=torch.float32)
     n = out.numel()
-    _lib.check(_lib.lib().yb_box_iou(a.data_ptr(), b.data_ptr(), n, 1 if box_format == "midpoint" else 0, 1 if GIoU else 0,
-                                     float(eps), out.data_ptr(), _lib.stream()))
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().yb_box_iou(a.data_ptr(), b.data_ptr(), n, 1 if box_format == "midpoint" else 0,
+                                         1 if GIoU else 0, float(eps), out.data_ptr(), _lib.stream()))
     return out if src_dev.type == "cuda" else out.to(src_dev)

@@ -26,7 +26,7 @@ namespace yb {
 __device__ __forceinline__ float sigmoid_t(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // ------------------------------------------------------------------------------------------------ decode
-__global__ void __launch_bounds__(256) decode_kernel(const float* __restrict__ p, long cells, int na, int H, int W, int no,
+__global__ void __launch_bounds__(256) decode_rows_kernel(const float* __restrict__ p, long cells, int na, int H, int W, int no,
                                                      float stride, const float* __restrict__ anchors_px, int is_pred,
                                                      float* __restrict__ out, long rows_per_image, long level_off) {
   const int lane = threadIdx.x & 31;
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256) decode_kernel(const float* __restrict__ p
     for (int k = lane + 96; k < nc; k += 32) lmax = fmaxf(lmax, ps[5 + k]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
-    const float cut = fminf(lmax, 16.0f) - 1e-3f * fmaxf(1.0f, fabsf(lmax));
+    const float cut = fminf(lmax, 16.0f) - fmaxf(1e-3f * fmaxf(1.0f, fabsf(lmax)), 2.4e-7f * __expf(fminf(lmax, 17.0f)));
     float bv = -1.f;
     int bi = 0x7fffffff;
 #pragma unroll
@@ -123,6 +123,127 @@ __global__ void __launch_bounds__(256) decode_kernel(const float* __restrict__ p
       }
       out[(b * rows_per_image + level_off + rem) * 6 + lane] = v;
     }
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------ decode of predictions
+// cells_to_bboxes(is_pred=True) is HBM-bound: 340 bytes of logits in, 24 bytes out per cell (1280x1280, bs=128: 4.39 GB).
+// A warp owns a chunk of 32 consecutive cells = 10,880 contiguous, 16-byte-aligned bytes: ONE bulk asynchronous copy
+// (cp.async.bulk, the TMA engine) brings the chunk into shared memory while the previous chunk is processed (two buffers
+// per warp, 16 chunks = 170 KB in flight per SM), then every lane decodes one cell from shared memory (row stride 85 words
+// is odd -> conflict-free), and the 32 x 6 results leave through a shared-memory transpose as coalesced stores.
+// Arithmetic is unchanged from the row kernel: exact expf sigmoid for the five box / objectness channels, class arg-max =
+// first maximum of sigmoid(logit) (torch.argmax, plot_utils.py:27) found on the logits, with the sigmoid evaluated only for
+// the classes whose logit is within rounding reach of the largest one.  The reach: sigmoid is flat to one fp32 ulp over
+// dx ~ 6e-8 * e^x for large x (and saturates to 1.0f above ~16.6), so the candidate cut is
+// min(lmax, 16) - max(1e-3 * max(1,|lmax|), 2.4e-7 * e^min(lmax,17)).
+static constexpr int kDecWarps = 4;           // warps per CTA
+static constexpr int kDecCells = 32;          // cells per chunk (one per lane)
+static constexpr int kDecMaxNo = 96;          // row length limit (5 + nc <= 96)
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kDecWarps * 32) decode_pred_kernel(const float* __restrict__ p, long cells, int na, int H, int W,
+                                                                     int no, float stride, const float* __restrict__ anchors_px,
+                                                                     float* __restrict__ out, long rows_per_image,
+                                                                     long level_off) {
+  extern __shared__ __align__(128) uint8_t dsm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t chunk_floats = (uint32_t)kDecCells * no;
+  const uint32_t buf_bytes = (chunk_floats * 4u + 127u) & ~127u;
+  float* buf0 = reinterpret_cast<float*>(dsm + (size_t)warp * (2 * buf_bytes + 1024));
+  float* buf1 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(buf0) + buf_bytes);
+  float* stage = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(buf1) + buf_bytes);  // [32][6] output transpose
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage + 32 * 6);                             // [2]
+  if (lane == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  const long nchunks = (cells + kDecCells - 1) / kDecCells;
+  const long wglobal = (long)blockIdx.x * kDecWarps + warp, wstride = (long)gridDim.x * kDecWarps;
+  const int nc = no - 5;
+  const unsigned per_img = (unsigned)(na * H * W), hw = (unsigned)(H * W);
+
+  // a chunk whose byte count and start are multiples of 16 goes through the bulk-copy engine; the (rare) unaligned tail
+  // chunk of odd-sized maps is copied with plain loads
+  auto issue = [&](long ch, int b) {
+    const long c0 = ch * kDecCells;
+    const int n = (int)min((long)kDecCells, cells - c0);
+    const uint32_t bytes = (uint32_t)n * no * 4u;
+    float* dst = b ? buf1 : buf0;
+    const float* src = p + c0 * no;
+    if ((bytes & 15u) == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+      if (lane == 0) {
+        mbar_expect_tx(&bars[b], bytes);
+        bulk_g2s(dst, src, bytes, &bars[b]);
+      }
+    } else {
+      for (uint32_t i = lane; i < (uint32_t)n * no; i += 32) dst[i] = src[i];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[b]);
+    }
+  };
+
+  uint32_t phase[2] = {0, 0};
+  long ch = wglobal;
+  if (ch < nchunks) issue(ch, 0);
+  int b = 0;
+  for (; ch < nchunks; ch += wstride, b ^= 1) {
+    if (ch + wstride < nchunks) issue(ch + wstride, b ^ 1);  // prefetch the next chunk into the other buffer
+    mbar_wait(&bars[b], phase[b]);
+    phase[b] ^= 1;
+    const float* sm = b ? buf1 : buf0;
+    const long c0 = ch * kDecCells;
+    const int n = (int)min((long)kDecCells, cells - c0);
+    if (lane < n) {
+      const float* ps = sm + lane * no;
+      float lmax = -INFINITY;
+      for (int k = 0; k < nc; ++k) lmax = fmaxf(lmax, ps[5 + k]);
+      const float reach = fmaxf(1e-3f * fmaxf(1.0f, fabsf(lmax)), 2.4e-7f * __expf(fminf(lmax, 17.0f)));
+      const float cut = fminf(lmax, 16.0f) - reach;
+      float bv = -1.f;
+      int bi = 0;
+      for (int k = 0; k < nc; ++k) {
+        const float l = ps[5 + k];
+        if (l >= cut) {
+          const float sg = sigmoid_t(l);
+          if (sg > bv) {  // strict: the first maximum wins
+            bv = sg;
+            bi = k;
+          }
+        }
+      }
+      const unsigned cu = (unsigned)(c0 + lane);
+      const unsigned bu = cu / per_img, remu = cu - bu * per_img;
+      const int a = (int)(remu / hw);
+      const unsigned sp = remu - (unsigned)a * hw;
+      const int gy = (int)(sp / (unsigned)W), gx = (int)(sp - (unsigned)gy * (unsigned)W);
+      const float sx = sigmoid_t(ps[0]), sy = sigmoid_t(ps[1]), sw = sigmoid_t(ps[2]), sh = sigmoid_t(ps[3]);
+      const float tw = __fmul_rn(2.f, sw), th = __fmul_rn(2.f, sh);
+      float* so = stage + lane * 6;
+      so[0] = (float)bi;
+      so[1] = sigmoid_t(ps[4]);                                                                  // plot_utils.py:24
+      so[2] = __fmul_rn(__fsub_rn(__fadd_rn(__fmul_rn(2.f, sx), (float)gx), 0.5f), stride);      // :25
+      so[3] = __fmul_rn(__fsub_rn(__fadd_rn(__fmul_rn(2.f, sy), (float)gy), 0.5f), stride);
+      so[4] = __fmul_rn(__fmul_rn(tw, tw), anchors_px[a * 2 + 0]);                               // :26
+      so[5] = __fmul_rn(__fmul_rn(th, th), anchors_px[a * 2 + 1]);
+    }
+    __syncwarp();
+    // coalesced output: the chunk's rows are consecutive in `out` unless it straddles an image boundary
+    for (int i = lane; i < n * 6; i += 32) {
+      const int cell = i / 6, f = i - cell * 6;
+      const unsigned cu = (unsigned)(c0 + cell);
+      const unsigned bu = cu / per_img, remu = cu - bu * per_img;
+      out[((long)bu * rows_per_image + level_off + remu) * 6 + f] = stage[i];
+    }
+    __syncwarp();  // the buffer and the stage are free for the next round
   }
 }
 
@@ -362,6 +483,38 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_image_kernel(const __grid_
   if (tid == 0) P.out_count[img] = s_kept;
 }
 
+// ------------------------------------------------------------------------------------------------ eval counters
+// YOLO_EVAL.check_class_accuracy (utils/validation_utils.py:58-69) for one level: over the cells the label tensor marks as
+// objects (y[...,4] == 1):  class hit = argmax(logits[5:]) == y[...,5] (first maximum, torch.argmax);
+// "obj" hit = (sigmoid(logit[0]) > conf) == y[...,4] -- the reference thresholds channel 0, not the objectness (App. B5);
+// mirrored.  counters[0] += objects, [1] += class hits, [2] += obj hits.
+__global__ void class_accuracy_kernel(const float* __restrict__ p, const float* __restrict__ y, long cells, int no, int ny,
+                                      float conf, unsigned long long* __restrict__ counters) {
+  unsigned long long tot = 0, cc = 0, co = 0;
+  for (long c = (long)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += (long)gridDim.x * blockDim.x) {
+    const float* yr = y + c * ny;
+    if (yr[4] != 1.0f) continue;
+    const float* ps = p + c * no;
+    float best = ps[5];
+    int bi = 0;
+    for (int k = 1; k < no - 5; ++k) {
+      const float v = ps[5 + k];
+      if (v > best || (v != v && best == best)) {  // torch.argmax: first maximum; NaN counts as the maximum
+        best = v;
+        bi = k;
+      }
+    }
+    ++tot;
+    if ((float)bi == yr[5]) ++cc;
+    if (sigmoid_t(ps[0]) > conf) ++co;  // True == 1.0 (the label's objectness)
+  }
+  if (tot) {
+    atomicAdd(&counters[0], tot);
+    atomicAdd(&counters[1], cc);
+    atomicAdd(&counters[2], co);
+  }
+}
+
 static int nms_sm_count() {
   static int sms = 0;
   if (!sms) {
@@ -386,9 +539,36 @@ int yb_decode_level(const float* p, int B, int na, int H, int W, int no, float s
   const long cells = (long)B * na * H * W;
   if (cells == 0) return 0;
   YB_REQUIRE(cells < (1L << 31), "decode: %ld cells (limit 2^31)", cells);
+  if (is_pred && no <= kDecMaxNo) {
+    const size_t buf = ((size_t)kDecCells * no * 4 + 127) & ~(size_t)127;
+    const size_t smem = (size_t)kDecWarps * (2 * buf + 1024);
+    static size_t attr = 0;
+    if (smem > attr) {
+      YB_CHECK_CUDA(cudaFuncSetAttribute(decode_pred_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr = smem;
+    }
+    const long nchunks = (cells + kDecCells - 1) / kDecCells;
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(220 * 1024) / (smem + 1024)));
+    const int blocks = (int)std::max<long>(1, std::min<long>((nchunks + kDecWarps - 1) / kDecWarps, (long)nms_sm_count() * per_sm));
+    decode_pred_kernel<<<blocks, kDecWarps * 32, smem, ST(stream)>>>(p, cells, na, H, W, no, stride, anchors_px, out,
+                                                                     rows_per_image, level_off);
+    YB_LAUNCHED();
+    return 0;
+  }
   const int blocks = (int)std::max<long>(1, std::min<long>((cells + 7) / 8, (long)nms_sm_count() * 32));
-  decode_kernel<<<blocks, 256, 0, ST(stream)>>>(p, cells, na, H, W, no, stride, anchors_px, is_pred, out, rows_per_image,
-                                                level_off);
+  decode_rows_kernel<<<blocks, 256, 0, ST(stream)>>>(p, cells, na, H, W, no, stride, anchors_px, is_pred, out, rows_per_image,
+                                                     level_off);
+  YB_LAUNCHED();
+  return 0;
+}
+
+int yb_class_accuracy(const float* p, const float* y, int64_t cells, int no, int ny, float conf, uint64_t* counters,
+                      void* stream) {
+  YB_REQUIRE(no >= 6 && ny >= 6, "class_accuracy: no=%d ny=%d", no, ny);
+  if (cells == 0) return 0;
+  const int blocks = (int)std::max<long>(1, std::min<long>((cells + 255) / 256, (long)nms_sm_count() * 8));
+  class_accuracy_kernel<<<blocks, 256, 0, ST(stream)>>>(p, y, cells, no, ny, conf,
+                                                        reinterpret_cast<unsigned long long*>(counters));
   YB_LAUNCHED();
   return 0;
 }

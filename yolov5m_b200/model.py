@@ -317,9 +317,11 @@ class _Engine:
         resp, resl = (res.ptr, res.pitch) if res is not None else (None, 0)
         upp, upl = (up.ptr, up.pitch) if up is not None else (None, 0)
 
+        bn = r.bn  # eps / momentum are read at launch time, like nn.BatchNorm2d reads its attributes
+
         def op(st):
             self._conv(plan, st, flops, "fwd")
-            _lib.check(L.yb_bn_finalize(ptrs[0], nrows, C, count, gam, bet, BN_EPS, BN_MOMENTUM, rm, rv, nbt, ptrs[1], ptrs[2],
+            _lib.check(L.yb_bn_finalize(ptrs[0], nrows, C, count, gam, bet, bn.eps, bn.momentum, rm, rv, nbt, ptrs[1], ptrs[2],
                                         ptrs[3], ptrs[4], 1, st))
             _lib.check(L.yb_bn_act_fwd(y.ptr, C, y.N, y.H, y.W, C, ptrs[1], ptrs[2], resp, resl, out.ptr, out.pitch, upp,
                                        upl, st))
@@ -350,7 +352,7 @@ class _Engine:
         ptrs = (stats.data_ptr(), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), invstd.data_ptr())
         resp, resl = (res.ptr, res.pitch) if res is not None else (None, 0)
         upa = (up.ptr, up.plptr(0), up.pitch, up.plane_stride) if up is not None else (None, None, 0, 0)
-        train, max_rows = self.train, self.max_rows
+        train, max_rows, bn = self.train, self.max_rows, r.bn
 
         def op(st):
             for pl in plans:
@@ -358,7 +360,7 @@ class _Engine:
             if train:
                 rows = ctypes.c_int(0)
                 _lib.check(L.yb_p32_bn_stats(y.ptr, C, y.npix, C, ptrs[0], max_rows, ctypes.byref(rows), st))
-                _lib.check(L.yb_bn_finalize(ptrs[0], rows.value, C, count, gam, bet, BN_EPS, BN_MOMENTUM, rm, rv, nbt, ptrs[1],
+                _lib.check(L.yb_bn_finalize(ptrs[0], rows.value, C, count, gam, bet, bn.eps, bn.momentum, rm, rv, nbt, ptrs[1],
                                             ptrs[2], ptrs[3], ptrs[4], 1, st))
             else:
                 _lib.check(L.yb_bn_finalize(None, 0, C, 1.0, gam, bet, BN_EPS, BN_MOMENTUM, rm, rv, None, ptrs[1], ptrs[2], None,
