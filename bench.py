@@ -325,7 +325,9 @@ def run_ours_detect(a):
 
     # per-stage device times (CUDA events on the launching stream) -> rooflines of the stages
     def stage(fn, n=3):
-        fn()
+        for _ in range(3):  # warm-up: the caching allocator settles (a forward returns 4.4 GB of fresh logits)
+            r = fn()
+        del r
         torch.cuda.synchronize()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()

@@ -199,6 +199,14 @@ int yb_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float 
                  float weight_decay, int64_t step, const int64_t* step_dev, float grad_scale, float max_norm,
                  const float* norm, void* w_bf16, void* stream);
 
+/* ---- data-parallel gradient exchange over NVLink peer memory (BASELINE.json configs[3]; the reference is single-GPU) ------
+ * peer_ptrs_host: HOST array of `world` device pointers, entry r = base of rank r's fp32 gradient bucket (symmetric memory,
+ * peer-mapped, 16-byte aligned, n floats each, n % 4 == 0).  Rank `rank` loads its 1/world slice from every peer, sums in
+ * rank order (bit-identical on every rank) and stores the sum into that slice of every peer's bucket: reduce-scatter and
+ * all-gather in one kernel.  The caller orders it across ranks with a barrier before (all buckets complete) and after
+ * (all stores landed).  ctas <= 0: default grid. */
+int yb_allreduce_p2p(const uint64_t* peer_ptrs_host, int rank, int world, int64_t n, int ctas, void* stream);
+
 /* ---- ComputeLoss (ultralytics_loss.py:17-311) ---------------------------------------------------------------------
  * One yb_loss_level per detection level; all pointers are device pointers owned by the caller, `cap` = row capacity of
  * the per-level arrays (>= 5*na*nt, the exact upper bound of build_targets). */

@@ -130,15 +130,15 @@ __global__ void __launch_bounds__(256) decode_rows_kernel(const float* __restric
 // ------------------------------------------------------------------------------------------------ decode of predictions
 // cells_to_bboxes(is_pred=True) is HBM-bound: 340 bytes of logits in, 24 bytes out per cell (1280x1280, bs=128: 4.39 GB).
 // A warp owns a chunk of 32 consecutive cells = 10,880 contiguous, 16-byte-aligned bytes: ONE bulk asynchronous copy
-// (cp.async.bulk, the TMA engine) brings the chunk into shared memory while the previous chunk is processed (two buffers
-// per warp, 16 chunks = 170 KB in flight per SM), then every lane decodes one cell from shared memory (row stride 85 words
-// is odd -> conflict-free), and the 32 x 6 results leave through a shared-memory transpose as coalesced stores.
+// (cp.async.bulk, the TMA engine) brings the chunk into the warp's shared-memory buffer (16 warps per SM: while some wait
+// for their copy the others decode), then every lane decodes one cell from shared memory (row stride 85 words is odd ->
+// conflict-free), and the 32 x 6 results leave through a shared-memory transpose as coalesced stores.
 // Arithmetic is unchanged from the row kernel: exact expf sigmoid for the five box / objectness channels, class arg-max =
 // first maximum of sigmoid(logit) (torch.argmax, plot_utils.py:27) found on the logits, with the sigmoid evaluated only for
 // the classes whose logit is within rounding reach of the largest one.  The reach: sigmoid is flat to one fp32 ulp over
 // dx ~ 6e-8 * e^x for large x (and saturates to 1.0f above ~16.6), so the candidate cut is
 // min(lmax, 16) - max(1e-3 * max(1,|lmax|), 2.4e-7 * e^min(lmax,17)).
-static constexpr int kDecWarps = 4;           // warps per CTA
+static constexpr int kDecWarps = 8;           // warps per CTA (two CTAs per SM: 16 chunks = 170 KB in flight / being decoded)
 static constexpr int kDecCells = 32;          // cells per chunk (one per lane)
 static constexpr int kDecMaxNo = 96;          // row length limit (5 + nc <= 96)
 
@@ -148,102 +148,114 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
-__global__ void __launch_bounds__(kDecWarps * 32) decode_pred_kernel(const float* __restrict__ p, long cells, int na, int H, int W,
-                                                                     int no, float stride, const float* __restrict__ anchors_px,
-                                                                     float* __restrict__ out, long rows_per_image,
-                                                                     long level_off) {
+struct DecGeom {
+  unsigned per_img, hw, w;  // cells per image (na*H*W), per anchor plane (H*W), per row (W)
+};
+
+__global__ void __launch_bounds__(kDecWarps * 32, 2) decode_pred_kernel(const float* __restrict__ p, long cells, int no,
+                                                                        float stride, const float* __restrict__ anchors_px,
+                                                                        float* __restrict__ out, long rows_per_image,
+                                                                        long level_off, const DecGeom g) {
   extern __shared__ __align__(128) uint8_t dsm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t chunk_floats = (uint32_t)kDecCells * no;
-  const uint32_t buf_bytes = (chunk_floats * 4u + 127u) & ~127u;
-  float* buf0 = reinterpret_cast<float*>(dsm + (size_t)warp * (2 * buf_bytes + 1024));
-  float* buf1 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(buf0) + buf_bytes);
-  float* stage = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(buf1) + buf_bytes);  // [32][6] output transpose
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stage + 32 * 6);                             // [2]
+  const uint32_t buf_bytes = ((uint32_t)kDecCells * no * 4u + 127u) & ~127u;
+  float* buf = reinterpret_cast<float*>(dsm + (size_t)warp * (buf_bytes + 1024));
+  float* stage = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(buf) + buf_bytes);  // [32][6] output transpose
+  uint64_t* bar = reinterpret_cast<uint64_t*>(stage + 32 * 6);
   if (lane == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
+    mbar_init(bar, 1);
     fence_mbar_init();
   }
   __syncwarp();
   const long nchunks = (cells + kDecCells - 1) / kDecCells;
   const long wglobal = (long)blockIdx.x * kDecWarps + warp, wstride = (long)gridDim.x * kDecWarps;
   const int nc = no - 5;
-  const unsigned per_img = (unsigned)(na * H * W), hw = (unsigned)(H * W);
-
-  // a chunk whose byte count and start are multiples of 16 goes through the bulk-copy engine; the (rare) unaligned tail
-  // chunk of odd-sized maps is copied with plain loads
-  auto issue = [&](long ch, int b) {
+  const float a0w = anchors_px[0], a0h = anchors_px[1], a1w = anchors_px[2], a1h = anchors_px[3];
+  uint32_t phase = 0;
+  for (long ch = wglobal; ch < nchunks; ch += wstride) {
     const long c0 = ch * kDecCells;
     const int n = (int)min((long)kDecCells, cells - c0);
-    const uint32_t bytes = (uint32_t)n * no * 4u;
-    float* dst = b ? buf1 : buf0;
-    const float* src = p + c0 * no;
-    if ((bytes & 15u) == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
-      if (lane == 0) {
-        mbar_expect_tx(&bars[b], bytes);
-        bulk_g2s(dst, src, bytes, &bars[b]);
+    {  // a chunk whose byte count and start are multiples of 16 goes through the bulk-copy engine; the (rare) unaligned
+       // tail chunk of odd-sized maps is copied with plain loads
+      const uint32_t bytes = (uint32_t)n * no * 4u;
+      const float* src = p + c0 * no;
+      if ((bytes & 15u) == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+        if (lane == 0) {
+          mbar_expect_tx(bar, bytes);
+          bulk_g2s(buf, src, bytes, bar);
+        }
+      } else {
+        for (uint32_t i = lane; i < (uint32_t)n * no; i += 32) buf[i] = src[i];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar);
       }
-    } else {
-      for (uint32_t i = lane; i < (uint32_t)n * no; i += 32) dst[i] = src[i];
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[b]);
     }
-  };
-
-  uint32_t phase[2] = {0, 0};
-  long ch = wglobal;
-  if (ch < nchunks) issue(ch, 0);
-  int b = 0;
-  for (; ch < nchunks; ch += wstride, b ^= 1) {
-    if (ch + wstride < nchunks) issue(ch + wstride, b ^ 1);  // prefetch the next chunk into the other buffer
-    mbar_wait(&bars[b], phase[b]);
-    phase[b] ^= 1;
-    const float* sm = b ? buf1 : buf0;
-    const long c0 = ch * kDecCells;
-    const int n = (int)min((long)kDecCells, cells - c0);
+    // index decode of this lane's cell while the copy is in flight
+    // (32-bit unsigned divisions, three per lane and chunk: cells < 2^31 is checked on the host)
+    const unsigned cu = (unsigned)(c0 + lane);
+    const unsigned remu = cu % g.per_img;
+    const int a = (int)(remu / g.hw);
+    const unsigned sp = remu - (unsigned)a * g.hw;
+    const int gy = (int)(sp / g.w), gx = (int)(sp - (unsigned)gy * g.w);
+    mbar_wait(bar, phase);
+    phase ^= 1;
     if (lane < n) {
-      const float* ps = sm + lane * no;
-      float lmax = -INFINITY;
-      for (int k = 0; k < nc; ++k) lmax = fmaxf(lmax, ps[5 + k]);
-      const float reach = fmaxf(1e-3f * fmaxf(1.0f, fabsf(lmax)), 2.4e-7f * __expf(fminf(lmax, 17.0f)));
-      const float cut = fminf(lmax, 16.0f) - reach;
-      float bv = -1.f;
-      int bi = 0;
+      const float* ps = buf + lane * no;
+      // one pass: largest and second-largest class logit (first index of the largest)
+      float m1 = -INFINITY, m2 = -INFINITY;
+      int i1 = 0;
+#pragma unroll 8
       for (int k = 0; k < nc; ++k) {
         const float l = ps[5 + k];
-        if (l >= cut) {
-          const float sg = sigmoid_t(l);
-          if (sg > bv) {  // strict: the first maximum wins
-            bv = sg;
-            bi = k;
+        const bool gt = l > m1;
+        m2 = gt ? m1 : fmaxf(m2, l);
+        i1 = gt ? k : i1;
+        m1 = gt ? l : m1;
+      }
+      int bi = i1;
+      const float reach = fmaxf(1e-3f * fmaxf(1.0f, fabsf(m1)), 2.4e-7f * __expf(fminf(m1, 17.0f)));
+      const float cut = fminf(m1, 16.0f) - reach;
+      if (m2 >= cut || !(m1 == m1)) {  // another class within rounding reach (or NaN): resolve on the sigmoids, first maximum wins
+        float bv = -1.f;
+        bi = 0;
+        for (int k = 0; k < nc; ++k) {
+          const float l = ps[5 + k];
+          if (l >= cut || l != l) {
+            const float sg = sigmoid_t(l);
+            if (sg > bv || (sg != sg && bv == bv)) {
+              bv = sg;
+              bi = k;
+            }
           }
         }
       }
-      const unsigned cu = (unsigned)(c0 + lane);
-      const unsigned bu = cu / per_img, remu = cu - bu * per_img;
-      const int a = (int)(remu / hw);
-      const unsigned sp = remu - (unsigned)a * hw;
-      const int gy = (int)(sp / (unsigned)W), gx = (int)(sp - (unsigned)gy * (unsigned)W);
       const float sx = sigmoid_t(ps[0]), sy = sigmoid_t(ps[1]), sw = sigmoid_t(ps[2]), sh = sigmoid_t(ps[3]);
       const float tw = __fmul_rn(2.f, sw), th = __fmul_rn(2.f, sh);
+      const float aw = a == 0 ? a0w : (a == 1 ? a1w : anchors_px[a * 2]);
+      const float ah = a == 0 ? a0h : (a == 1 ? a1h : anchors_px[a * 2 + 1]);
       float* so = stage + lane * 6;
       so[0] = (float)bi;
       so[1] = sigmoid_t(ps[4]);                                                                  // plot_utils.py:24
       so[2] = __fmul_rn(__fsub_rn(__fadd_rn(__fmul_rn(2.f, sx), (float)gx), 0.5f), stride);      // :25
       so[3] = __fmul_rn(__fsub_rn(__fadd_rn(__fmul_rn(2.f, sy), (float)gy), 0.5f), stride);
-      so[4] = __fmul_rn(__fmul_rn(tw, tw), anchors_px[a * 2 + 0]);                               // :26
-      so[5] = __fmul_rn(__fmul_rn(th, th), anchors_px[a * 2 + 1]);
+      so[4] = __fmul_rn(__fmul_rn(tw, tw), aw);                                                  // :26
+      so[5] = __fmul_rn(__fmul_rn(th, th), ah);
     }
     __syncwarp();
-    // coalesced output: the chunk's rows are consecutive in `out` unless it straddles an image boundary
-    for (int i = lane; i < n * 6; i += 32) {
-      const int cell = i / 6, f = i - cell * 6;
-      const unsigned cu = (unsigned)(c0 + cell);
-      const unsigned bu = cu / per_img, remu = cu - bu * per_img;
-      out[((long)bu * rows_per_image + level_off + remu) * 6 + f] = stage[i];
+    // coalesced output: the chunk's 32 x 6 floats are consecutive in `out` unless the chunk straddles an image boundary
+    const unsigned q0 = (unsigned)c0 / g.per_img, r0 = (unsigned)c0 - q0 * g.per_img;
+    const unsigned q1 = (unsigned)(c0 + n - 1) / g.per_img;
+    if (q0 == q1) {
+      float* dst = out + ((long)q0 * rows_per_image + level_off + r0) * 6;
+      for (int i = lane; i < n * 6; i += 32) dst[i] = stage[i];
+    } else {
+      for (int i = lane; i < n * 6; i += 32) {
+        const int cell = i / 6, f = i - cell * 6;
+        const unsigned qq = (unsigned)(c0 + cell) / g.per_img, rr = (unsigned)(c0 + cell) - qq * g.per_img;
+        out[((long)qq * rows_per_image + level_off + rr) * 6 + f] = stage[i];
+      }
     }
-    __syncwarp();  // the buffer and the stage are free for the next round
+    __syncwarp();  // the buffer and the stage are free for the next chunk
   }
 }
 
@@ -541,17 +553,21 @@ int yb_decode_level(const float* p, int B, int na, int H, int W, int no, float s
   YB_REQUIRE(cells < (1L << 31), "decode: %ld cells (limit 2^31)", cells);
   if (is_pred && no <= kDecMaxNo) {
     const size_t buf = ((size_t)kDecCells * no * 4 + 127) & ~(size_t)127;
-    const size_t smem = (size_t)kDecWarps * (2 * buf + 1024);
+    const size_t smem = (size_t)kDecWarps * (buf + 1024);
     static size_t attr = 0;
     if (smem > attr) {
       YB_CHECK_CUDA(cudaFuncSetAttribute(decode_pred_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr = smem;
     }
     const long nchunks = (cells + kDecCells - 1) / kDecCells;
-    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(220 * 1024) / (smem + 1024)));
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (size_t)(220 * 1024) / (smem + 1024)));
     const int blocks = (int)std::max<long>(1, std::min<long>((nchunks + kDecWarps - 1) / kDecWarps, (long)nms_sm_count() * per_sm));
-    decode_pred_kernel<<<blocks, kDecWarps * 32, smem, ST(stream)>>>(p, cells, na, H, W, no, stride, anchors_px, out,
-                                                                     rows_per_image, level_off);
+    DecGeom g;
+    g.per_img = (unsigned)(na * H * W);
+    g.hw = (unsigned)(H * W);
+    g.w = (unsigned)W;
+    decode_pred_kernel<<<blocks, kDecWarps * 32, smem, ST(stream)>>>(p, cells, no, stride, anchors_px, out, rows_per_image,
+                                                                     level_off, g);
     YB_LAUNCHED();
     return 0;
   }

@@ -165,11 +165,41 @@ class GradSync:
     large chunks so the collective is not latency-bound.  The 1/world_size average is folded into the
     optimiser's grad_scale, so the bucket is never rescaled in memory."""
 
-    def __init__(self, model, chunks=4, group=None):
+    def __init__(self, model, chunks=4, group=None, mode=None):
+        """mode: "p2p" (default on CUDA when world > 1, $YB_ALLREDUCE): ONE kernel of ours over NVLink peer memory
+        (csrc/allreduce.cu: reduce-scatter + all-gather fused, the bucket lives in symmetric memory); "nccl": ncclAllReduce
+        of the bucket in `chunks` pieces.  If the symmetric-memory rendezvous is not available the NCCL path is used and the
+        reason is kept in ``self.p2p_error``."""
         self.model, self.group = model, group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.chunks = max(1, chunks)
         self._comm, self._b, self._ready, self._next = None, None, set(), -1
+        self.mode = (mode or os.environ.get("YB_ALLREDUCE", "p2p")).lower()
+        self._symm, self._peer_ptrs, self.p2p_error = None, None, None
+        if self.world > 1 and self.mode == "p2p" and model.flat_params.is_cuda:
+            self._setup_p2p()
+        if self.world > 1 and self._symm is None:
+            self.mode = "nccl"
+
+    def _setup_p2p(self):
+        """put the model's flat gradient bucket into symmetric memory and exchange the peer pointers (torch plumbing)"""
+        import ctypes
+        model = self.model
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            n = model.flat_params.numel()
+            bucket = symm_mem.empty(n, dtype=torch.float32, device=model.flat_params.device)
+            hdl = symm_mem.rendezvous(bucket, self.group if self.group is not None else dist.group.WORLD)
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            if len(ptrs) != self.world or any(p == 0 for p in ptrs):
+                raise RuntimeError(f"symmetric memory returned {ptrs}")
+            bucket.zero_()
+            model._gflat[0] = bucket          # every backward now writes its gradients straight into the peer-mapped bucket
+            self._symm, self._bucket = hdl, bucket
+            self._peer_ptrs = (ctypes.c_uint64 * self.world)(*ptrs)
+            self.rank = dist.get_rank(self.group)
+        except Exception as e:  # no symmetric memory on this box / build: NCCL carries the bucket instead
+            self._symm, self.p2p_error = None, repr(e)
 
     def broadcast_parameters(self, src=0):
         if self.world > 1:
@@ -187,6 +217,12 @@ class GradSync:
         if self.world == 1:
             return
         g = self.model.flat_grads if grads is None else grads
+        if self._symm is not None and g.data_ptr() == self._bucket.data_ptr():
+            L, st = _lib.lib(), _lib.stream()
+            self._symm.barrier(channel=0)   # every rank's backward has written its bucket
+            _lib.check(L.yb_allreduce_p2p(self._peer_ptrs, self.rank, self.world, g.numel(), 0, st))
+            self._symm.barrier(channel=1)   # every rank's stores have landed in every bucket
+            return
         b = self._bounds(g.numel())
         # gradients are produced head-first (end of the bucket first): reduce from the tail
         for c in reversed(range(self.chunks)):
@@ -200,7 +236,8 @@ class GradSync:
     #    wait for SMs behind the persistent conv CTAs), so the simple post-backward form stays the default.
     def attach(self, engine):
         """install the chunk-ready hook on a training engine (idempotent); returns False when overlap is off"""
-        if self.world == 1 or os.environ.get("YB_OVERLAP_AR", "0") != "1" or not self.model.flat_params.is_cuda:
+        if (self.world == 1 or self._symm is not None or os.environ.get("YB_OVERLAP_AR", "0") != "1"
+                or not self.model.flat_params.is_cuda):
             engine.on_grad_chunks = None
             return False
         if engine.on_grad_chunks is None or engine.on_grad_chunks[1] != self._chunk_ready:
