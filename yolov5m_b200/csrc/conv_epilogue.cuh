@@ -45,8 +45,13 @@ __device__ __forceinline__ EpiArgs load_epi_args(const P& p) {
 // P: EpiArgs (register copy of the epilogue fields of ConvKParams (stats, scale, shift, act, addend, out_kind, out,
 // Cout, H, W, head_na, head_no).  t_addr: TMEM address of column 0 of this chunk for this warp's lane quarter.
 // (n, h, w): output pixel of this thread's row; opix / apix: element offsets of that pixel in out / addend.
+// stage_row: when non-null, the bf16 result goes to shared memory instead of global memory: the address of this thread's
+// 128-byte row in the FIRST 64-channel slab of the tile's staging area (slabs are 16 KB apart); ccl = index of this
+// 16-channel chunk inside the tile.  The layout is the SWIZZLE_128B box layout the output tensor map stores from: 16-byte
+// unit u of row r sits at unit u ^ (r & 7).
 __device__ __forceinline__ void conv_epilogue_chunk(const EpiArgs& p, uint32_t t_addr, int col0, bool valid, int n, int h, int w,
-                                                    int64_t opix, int64_t apix, float* my_stats, int lane) {
+                                                    int64_t opix, int64_t apix, float* my_stats, int lane,
+                                                    uint8_t* stage_row = nullptr, int ccl = 0, int row = 0) {
     uint32_t vr[16];
     tmem_ld16(t_addr, vr);
     tmem_ld_wait();
@@ -146,7 +151,12 @@ __device__ __forceinline__ void conv_epilogue_chunk(const EpiArgs& p, uint32_t t
         // one 32-byte store per thread (st.global.v8, sm_100): a full L2 sector instead of two half-sector writes
         // (every tensor of the network has a pitch that is a multiple of 16 channels; other pitches take the 2 x 16 B path)
         bf16* op = reinterpret_cast<bf16*>(p.out) + opix + col0;
-        if ((reinterpret_cast<uintptr_t>(op) & 31) == 0) {
+        if (stage_row != nullptr) {
+          uint8_t* slab = stage_row + (size_t)(ccl >> 2) * 16384;
+          const int u0 = (ccl & 3) * 2;
+          *reinterpret_cast<uint4*>(slab + ((u0 ^ (row & 7)) << 4)) = o0;
+          *reinterpret_cast<uint4*>(slab + (((u0 + 1) ^ (row & 7)) << 4)) = o1;
+        } else if ((reinterpret_cast<uintptr_t>(op) & 31) == 0) {
           asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(op), "r"(o0.x), "r"(o0.y),
                        "r"(o0.z), "r"(o0.w), "r"(o1.x), "r"(o1.y), "r"(o1.z), "r"(o1.w)
                        : "memory");

@@ -15,6 +15,7 @@
 #include "conv_epilogue.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace yb {
@@ -57,7 +58,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   ConvTap* s_taps = reinterpret_cast<ConvTap*>(smem + 512);      // [16] shared copies: indexed constant-bank loads are slow
   ConvGroup* s_groups = reinterpret_cast<ConvGroup*>(smem + 640);  // [4]
-  uint8_t* a_smem = smem + kBarRegion;
+  uint8_t* o_stage = smem + kBarRegion;               // TMA-store staging: ceil(BLOCK_N / 64) slabs of [128 px][128 B]
+  uint8_t* a_smem = o_stage + p.stage_bytes;
   uint8_t* b_smem = a_smem + (size_t)p.stages * p.a_stage_bytes;
   float* s_stats = reinterpret_cast<float*>(b_smem + (size_t)p.stages * p.b_stage_bytes);  // [4][2][Cout]
 
@@ -81,6 +83,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmB);
     for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.tmA[i]);
+    if (p.tma_store)
+      for (int i = 0; i < p.ngroups; ++i) tma_prefetch_desc(&p.tmO[i]);
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
   if (p.stats != nullptr && warp >= 4) {
@@ -204,6 +208,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     keep_in_reg(o_thr); keep_in_reg(a_thr);
     const bool row_ok = r < p.PW * p.PH * p.PN;
     const int nchunks = BN / 16;
+    // TMA-store epilogue: the bf16 tile is staged in shared memory (swizzled box layout) and leaves as one bulk tensor
+    // store per 64-channel slab, issued by one thread; per-thread st.global rows (32 sectors per warp instruction) were the
+    // top stall of every small-K layer (store back-pressure)
+    int tma_store = p.tma_store;
+    keep_in_reg(tma_store);
+    uint8_t* stage_row = tma_store ? o_stage + (size_t)r * 128 : nullptr;
+    const bool issuer = threadIdx.x == 128;
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const TileCoord tc = decode_tile(td, t);
@@ -216,16 +227,31 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       const uint32_t aph = (it >> 1) & 1;
       mbar_wait(&tfull_bar[ab], aph);
       tc_fence_after();
+      if (tma_store) {  // the previous tile's stores have finished READING the staging area before anyone overwrites it
+        if (issuer && it > 0) bulk_wait_group_read0();
+        asm volatile("bar.sync 2, %0;" ::"n"(kEpiThreads) : "memory");
+      }
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 256;
       for (int cc = eg; cc < nchunks; cc += kEpiGroups) {
         const int col0 = tc.nt * BN + cc * 16;
         if (col0 >= ea.Cout) break;
-        conv_epilogue_chunk(ea, t_addr + cc * 16, col0, valid, n, h, w, opix, apix, my_stats, lane);
+        conv_epilogue_chunk(ea, t_addr + cc * 16, col0, valid, n, h, w, opix, apix, my_stats, lane, stage_row, cc, r);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[ab]);
+      if (tma_store) {
+        fence_proxy_async();  // generic-proxy writes of the staging area -> visible to the TMA (async proxy)
+        asm volatile("bar.sync 3, %0;" ::"n"(kEpiThreads) : "memory");
+        if (issuer) {
+          const int c0 = tc.nt * BN;
+          for (int s = 0; s * 64 < BN && c0 + s * 64 < ea.Cout; ++s)
+            tma_store_4d(&p.tmO[tc.g], o_stage + (size_t)s * 16384, c0 + s * 64, tc.wb * PW, tc.hb * PH, tc.nb * PN);
+          bulk_commit_group();
+        }
+      }
     }
+    if (tma_store && issuer) bulk_wait_group0();  // all stores complete before the CTA (and its shared memory) goes away
     if (p.stats != nullptr) {
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       float* dst = p.stats + (size_t)blockIdx.x * 2 * p.Cout;
@@ -296,8 +322,35 @@ static int make_a_map(CUtensorMap* m, const TView& v, int KC, int PW, int PH, in
   return encode_tmap(m, base, 4, dims, strides, box, 2 * KC, 2);
 }
 
+// $YB_TMA_STORE=1 turns the TMA-store epilogue on (default off).  Measured on B200 (profiles/ab_tma_store_r2.json, all 29
+// layer shapes at bs=64): correct everywhere, but slower overall -- forward 5.37 vs 4.78 ms, dgrad 4.62 vs 4.38 ms, step 28.8
+// vs 27.8 ms.  The per-tile hand-off (two 384-thread barriers + one issuing thread + wait_group.read before the staging area
+// is reused, and one or two operand stages given up for the staging slabs) costs more than the st.global back-pressure it
+// removes on every layer with many small tiles per CTA (48/96-channel layers at 160x160 / 80x80: +25..57 %); it wins only on
+// the 20x20 maps with <= 4 tiles per CTA (-3..-10 %, ~0.05 ms per step in total).  Kept as a knob, not as the default.
+bool conv_tma_store_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("YB_TMA_STORE");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v != 0;
+}
+
+// output map over (a parity sub-grid of) an NHWC bf16 view: dims (C, W/sx, H/sy, N), box [64 x bw x bh x bn], SWIZZLE_128B.
+// The box may exceed C (64-channel slabs of a 48 / 96-channel tensor): the out-of-bounds part is clipped by the store.
+bool conv_make_out_map(CUtensorMap* m, const TView& v, int bw, int bh, int bn, int py, int px, int sy, int sx) {
+  const bf16* base = reinterpret_cast<const bf16*>(v.ptr) + ((long)py * v.W + px) * v.pitch;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (v.pitch * 2) % 16 != 0 || bw > 256 || bh > 256 || bn > 256) return false;
+  uint64_t dims[4] = {(uint64_t)v.C, (uint64_t)(v.W / sx), (uint64_t)(v.H / sy), (uint64_t)v.N};
+  uint64_t strides[3] = {(uint64_t)v.pitch * sx * 2, (uint64_t)v.pitch * v.W * sy * 2, (uint64_t)v.pitch * v.W * v.H * 2};
+  uint32_t box[4] = {64u, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
+  return encode_tmap(m, base, 4, dims, strides, box, 128, 2) == 0;
+}
+
+// dgrad_stride: 0 = forward (one output group), 1 / 2 = dgrad with that stride (2: four output-parity groups)
 static int finish_plan(ConvPlan& pl, const bf16* wmat, int wrows, long wcols, const TView& out,
-                       const ConvEpilogue& ep) {
+                       const ConvEpilogue& ep, int dgrad_stride = 0) {
   ConvKParams& kp = pl.kp;
   kp.Cout = wrows;
   kp.BLOCK_N = pick_block_n(wrows);
@@ -332,12 +385,30 @@ static int finish_plan(ConvPlan& pl, const bf16* wmat, int wrows, long wcols, co
              "conv: Cout=%d must be a multiple of 16", wrows);
   YB_REQUIRE(ep.scale == nullptr || ep.shift != nullptr, "conv: scale without shift");
   const size_t stats_bytes = ep.stats ? (size_t)4 * 2 * wrows * sizeof(float) : 0;
-  const size_t budget = 227 * 1024 - 1024 /*align slack*/ - kBarRegion - stats_bytes;
+  size_t budget = 227 * 1024 - 1024 /*align slack*/ - kBarRegion - stats_bytes;
+  // TMA-store epilogue (bf16 NHWC outputs): staging = one [128 px][128 B] slab per 64 output channels of the tile, taken
+  // from the operand ring; kept only if at least three pipeline stages remain
+  kp.tma_store = 0;
+  kp.stage_bytes = 0;
+  if (ep.out_kind == OUT_BF16 && conv_tma_store_enabled()) {
+    const size_t st_bytes = (size_t)((kp.BLOCK_N + 63) / 64) * 16384;
+    bool ok = budget > st_bytes && (budget - st_bytes) / (kp.a_stage_bytes + kp.b_stage_bytes) >= 3;
+    const int step = dgrad_stride == 2 ? 2 : 1;
+    for (int g = 0; ok && g < kp.ngroups; ++g) {
+      const int py = step == 2 ? g / 2 : 0, px = step == 2 ? g % 2 : 0;
+      ok = conv_make_out_map(&kp.tmO[g], out, kp.PW, kp.PH, kp.PN, py, px, step, step);
+    }
+    if (ok) {
+      kp.tma_store = 1;
+      kp.stage_bytes = (uint32_t)st_bytes;
+      budget -= st_bytes;
+    }
+  }
   int stages = (int)(budget / (kp.a_stage_bytes + kp.b_stage_bytes));
   stages = std::min(stages, kMaxStages);
   YB_REQUIRE(stages >= 2, "conv: tile does not fit in shared memory");
   kp.stages = stages;
-  pl.smem = (int)(1024 + kBarRegion + (size_t)stages * (kp.a_stage_bytes + kp.b_stage_bytes) + stats_bytes);
+  pl.smem = (int)(1024 + kBarRegion + kp.stage_bytes + (size_t)stages * (kp.a_stage_bytes + kp.b_stage_bytes) + stats_bytes);
   pl.smem = std::max(pl.smem, 120 * 1024);  // one CTA per SM: each CTA allocates all 512 TMEM columns
   for (int g = 0; g < kp.ngroups; ++g)
     YB_REQUIRE(kp.groups[g].tap_end > kp.groups[g].tap_begin, "conv: output group %d has no taps", g);
@@ -477,7 +548,7 @@ int conv_plan_dgrad(ConvPlan& pl, const TView& dy, const bf16* wt, int ks, int s
     kp.as_h = (int64_t)ep.addend_pitch * dx.W * stride;
     kp.as_w = ep.addend_pitch * stride;
   }
-  return finish_plan(pl, wt, dx.C, (long)ks * ks * dy.C, dx, ep);
+  return finish_plan(pl, wt, dx.C, (long)ks * ks * dy.C, dx, ep, stride);
 }
 
 int conv_stats_rows(const ConvPlan& pl) { return pl.grid; }

@@ -37,6 +37,9 @@ enum { OUT_BF16 = 0, OUT_HEAD_F32 = 1, OUT_F32 = 2, OUT_F32_ACC = 3, OUT_HEAD_F3
 struct ConvKParams {
   CUtensorMap tmA[4];
   CUtensorMap tmB;
+  CUtensorMap tmO[4];        // output maps (one per group) of the TMA-store epilogue: box [64 ch x PW x PH x PN], SWIZZLE_128B
+  int32_t tma_store;         // 1: bf16 tiles leave through shared memory + cp.async.bulk.tensor stores (stage_bytes of smem)
+  uint32_t stage_bytes;
   ConvTap taps[16];
   ConvGroup groups[4];
   int32_t ngroups;
@@ -77,6 +80,9 @@ struct PPatch {
 struct PatchKParams {
   CUtensorMap tmA[4];
   CUtensorMap tmB;
+  CUtensorMap tmO[4];        // output maps (one per group) of the TMA-store epilogue: box [64 ch x 8 x 16 x 1], SWIZZLE_128B
+  int32_t tma_store;
+  uint32_t stage_bytes;
   PTap taps[16];
   PPatch patches[4];
   ConvGroup groups[4];  // tap_begin/tap_end index PATCHES here
@@ -138,5 +144,8 @@ int conv_patch_run(const ConvPlan& pl, cudaStream_t st);
 void set_patch_mode(int m);
 int conv_stats_rows(const ConvPlan& pl);  // number of per-CTA partial rows written to ep.stats (= grid)
 int conv_max_grid();
+// output tensor map of the TMA-store epilogue over (a parity sub-grid of) an NHWC bf16 view; false -> not encodable
+bool conv_make_out_map(CUtensorMap* m, const TView& v, int bw, int bh, int bn, int py, int px, int sy, int sx);
+bool conv_tma_store_enabled();  // $YB_TMA_STORE=1 (default off: measured slower, see conv_igemm.cu)
 
 }  // namespace yb

@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
   PTap* s_taps = reinterpret_cast<PTap*>(smem + 512);          // [16] shared copies: indexed constant-bank loads are slow
   PPatch* s_patches = reinterpret_cast<PPatch*>(smem + 640);   // [4] x 28 B
   ConvGroup* s_groups = reinterpret_cast<ConvGroup*>(smem + 768);  // [4] x 24 B
-  uint8_t* a_smem = smem + kBarRegion;
+  uint8_t* o_stage = smem + kBarRegion;  // TMA-store staging: ceil(BLOCK_N / 64) slabs of [128 px][128 B] (conv_igemm.cu)
+  uint8_t* a_smem = o_stage + p.stage_bytes;
   uint8_t* b_smem = a_smem + (size_t)p.sa * p.a_stage_bytes;
   float* s_stats = reinterpret_cast<float*>(b_smem + (size_t)p.sb * p.b_stage_bytes);  // [4][2][Cout]
 
@@ -95,6 +96,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmB);
     for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.tmA[i]);
+    if (p.tma_store)
+      for (int i = 0; i < p.ngroups; ++i) tma_prefetch_desc(&p.tmO[i]);
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
   if (p.stats != nullptr && warp >= 4) {
@@ -268,7 +271,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
     keep_in_reg(BN); keep_in_reg(TWl); keep_in_reg(THl);
     keep_in_reg(os_n); keep_in_reg(os_h); keep_in_reg(os_w); keep_in_reg(as_n); keep_in_reg(as_h); keep_in_reg(as_w);
     const int nchunks = BN / 16;
-    int it = 0;
+    int tma_store = p.tma_store;
+    keep_in_reg(tma_store);
+    uint8_t* stage_row = o_stage + (size_t)r * 128;
+    const bool issuer = threadIdx.x == 128;
+    int it = 0, stores = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
       const STile tc = decode_stile(td, t);
       const ConvGroup grp = s_groups[tc.g];
@@ -277,6 +284,45 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
       const uint32_t aph = (it >> 1) & 1;
       mbar_wait(&tfull_bar[ab], aph);
       tc_fence_after();
+      if (tma_store) {
+        // TMA-store epilogue (see conv_igemm.cu): tile by tile -- stage the bf16 tile in shared memory, one bulk tensor
+        // store per 64-channel slab; box = [64 ch x 8 x 16 x 1] pixels, clipped at the tensor edges
+        int ty = 0, tx = 0;
+        for (int tt = 0; tt < T; ++tt) {
+          const int h0 = (tc.hb * THl + ty) * 16, w0 = (tc.wb * TWl + tx) * 8;
+          const int h = h0 + phh, w = w0 + pw;
+          const bool valid = h < ea.H && w < ea.W;
+          const int64_t opix = o_base + h * os_h + w * os_w;
+          const int64_t apix = a_base + h * as_h + w * as_w;
+          if (issuer && stores > 0) bulk_wait_group_read0();  // the previous tile's stores no longer read the staging area
+          asm volatile("bar.sync 2, %0;" ::"n"(kEpiThreads) : "memory");
+          for (int cc = eg; cc < nchunks; cc += kEpiGroups) {
+            const int col0 = tc.nt * BN + cc * 16;
+            if (col0 >= ea.Cout) break;
+            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 256 + tt * BN + cc * 16;
+            conv_epilogue_chunk(ea, t_addr, col0, valid, tc.n, h, w, opix, apix, my_stats, lane, stage_row, cc, r);
+          }
+          if (tt + 1 == T) {  // all accumulators of this hand-off have been read: the MMA warp may reuse the TMEM buffer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[ab]);
+          }
+          fence_proxy_async();
+          asm volatile("bar.sync 3, %0;" ::"n"(kEpiThreads) : "memory");
+          if (issuer && h0 < ea.H && w0 < ea.W) {
+            const int c0 = tc.nt * BN;
+            for (int s = 0; s * 64 < BN && c0 + s * 64 < ea.Cout; ++s)
+              tma_store_4d(&p.tmO[tc.g], o_stage + (size_t)s * 16384, c0 + s * 64, w0, h0, tc.n);
+            bulk_commit_group();
+            ++stores;
+          }
+          if (++tx == TWl) {
+            tx = 0;
+            ++ty;
+          }
+        }
+        continue;
+      }
       // (tile tt, chunk cc) of the flat index idx = tt * nchunks + cc and (ty, tx) of tt advance incrementally: two
       // runtime integer divisions per chunk were ~100 of the ~300 instructions of a chunk (ncu source page, r1)
       int tt = 0, cc = eg, ty = 0, tx = 0;
@@ -312,6 +358,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[ab]);
     }
+    if (tma_store && issuer) bulk_wait_group0();  // all stores complete before the CTA (and its shared memory) goes away
     if (p.stats != nullptr) {
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       float* dst = p.stats + (size_t)blockIdx.x * 2 * p.Cout;
@@ -470,7 +517,14 @@ int conv_patch_plan_fwd(ConvPlan& pl, const TView& in, const bf16* wp, int ks, i
   if (finish_patch_plan(pl, wp, out.C, (long)ntap_total * in.C, in.C, out, ep, 0, 0)) return -1;
   const size_t stats_bytes = ep.stats ? (size_t)4 * 2 * out.C * sizeof(float) : 0;
   const int halo = ks == 1 ? 0 : (stride == 1 ? 2 : 1);
-  if (!choose_supertile(kp, out.W, out.H, out.N, 1, ks == 31 ? 0 : halo, halo, stats_bytes)) return 1;
+  // TMA-store epilogue: staging slabs come out of the operand budget; fall back to direct stores if the tiling does not fit
+  size_t st_bytes = (ep.out_kind == OUT_BF16 && conv_tma_store_enabled()) ? (size_t)((kp.BLOCK_N + 63) / 64) * 16384 : 0;
+  if (st_bytes && !(conv_make_out_map(&kp.tmO[0], out, 8, 16, 1, 0, 0, 1, 1) &&
+                    choose_supertile(kp, out.W, out.H, out.N, 1, ks == 31 ? 0 : halo, halo, stats_bytes + st_bytes)))
+    st_bytes = 0;
+  if (!st_bytes && !choose_supertile(kp, out.W, out.H, out.N, 1, ks == 31 ? 0 : halo, halo, stats_bytes)) return 1;
+  kp.tma_store = st_bytes ? 1 : 0;
+  kp.stage_bytes = (uint32_t)st_bytes;
   const int SW = 8 * kp.TW, SH = 16 * kp.TH;
   int nt = 0, np = 0;
   if (ks == 1) {
@@ -541,7 +595,8 @@ int conv_patch_plan_fwd(ConvPlan& pl, const TView& in, const bf16* wp, int ks, i
   set_out_strides(kp, out, 1, ep);
   const long total = (long)kp.NB * kp.tiles_h * kp.tiles_w * kp.tiles_c;
   pl.grid = (int)std::min<long>(total, conv_max_grid());
-  pl.smem = (int)(1024 + kBarRegion + (size_t)kp.sa * kp.a_stage_bytes + (size_t)kp.sb * kp.b_stage_bytes + stats_bytes);
+  pl.smem = (int)(1024 + kBarRegion + kp.stage_bytes + (size_t)kp.sa * kp.a_stage_bytes + (size_t)kp.sb * kp.b_stage_bytes +
+                  stats_bytes);
   pl.smem = std::max(pl.smem, 120 * 1024);
   return 0;
 }
@@ -563,7 +618,13 @@ int conv_patch_plan_dgrad(ConvPlan& pl, const TView& dy, const bf16* wt, int ks,
   kp.ngroups = stride == 1 ? 1 : 4;
   if (finish_patch_plan(pl, wt, dx.C, (long)ks * ks * dy.C, dy.C, dx, ep, 0, 0)) return -1;
   const int halo = ks == 1 ? 0 : (stride == 1 ? 2 : 1);
-  if (!choose_supertile(kp, Wg, Hg, dx.N, kp.ngroups, halo, halo, 0)) return 1;
+  size_t st_bytes = (ep.out_kind == OUT_BF16 && conv_tma_store_enabled()) ? (size_t)((kp.BLOCK_N + 63) / 64) * 16384 : 0;
+  for (int g = 0; st_bytes && g < kp.ngroups; ++g)  // stride 2: one map per output-parity group
+    if (!conv_make_out_map(&kp.tmO[g], dx, 8, 16, 1, stride == 2 ? g / 2 : 0, stride == 2 ? g % 2 : 0, stride, stride)) st_bytes = 0;
+  if (st_bytes && !choose_supertile(kp, Wg, Hg, dx.N, kp.ngroups, halo, halo, st_bytes)) st_bytes = 0;
+  if (!st_bytes && !choose_supertile(kp, Wg, Hg, dx.N, kp.ngroups, halo, halo, 0)) return 1;
+  kp.tma_store = st_bytes ? 1 : 0;
+  kp.stage_bytes = (uint32_t)st_bytes;
   const int SW = 8 * kp.TW, SH = 16 * kp.TH;
   int nt = 0;
   if (ks == 1) {
@@ -626,7 +687,7 @@ int conv_patch_plan_dgrad(ConvPlan& pl, const TView& dy, const bf16* wt, int ks,
   set_out_strides(kp, dx, stride, ep);
   const long total = (long)kp.ngroups * kp.NB * kp.tiles_h * kp.tiles_w * kp.tiles_c;
   pl.grid = (int)std::min<long>(total, conv_max_grid());
-  pl.smem = (int)(1024 + kBarRegion + (size_t)kp.sa * kp.a_stage_bytes + (size_t)kp.sb * kp.b_stage_bytes);
+  pl.smem = (int)(1024 + kBarRegion + kp.stage_bytes + (size_t)kp.sa * kp.a_stage_bytes + (size_t)kp.sb * kp.b_stage_bytes);
   pl.smem = std::max(pl.smem, 120 * 1024);
   return 0;
 }
