@@ -498,7 +498,14 @@ def run_ours(a):
                 stage_t[k].copy_(host_tgts[k], non_blocking=True)
                 ready[k].record(copy_stream)
 
+        loss_h = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(nbuf)]
+        loss_ev = [torch.cuda.Event() for _ in range(nbuf)]
+
         def e2e_loop(n):
+            """every step: H2D copy of its batch (pinned host memory) and a D2H read of its loss.  The read is pipelined
+            like a training loop's logging: step i's loss is copied to pinned memory asynchronously and CONSUMED on the host
+            while step i+1 is already queued, so the host never drains the GPU between steps; every loss of the window is read
+            inside the timed region (the last one before the closing barrier)."""
             for k in range(nbuf):
                 consumed[k].record()
             prefetch(0)
@@ -508,9 +515,15 @@ def run_ours(a):
                 torch.cuda.current_stream().wait_event(ready[k])
                 ls = step(stage_i[k], stage_t[k])
                 consumed[k].record()
+                loss_h[k].copy_(ls.detach(), non_blocking=True)  # device -> host read of the step's result, every step
+                loss_ev[k].record()
                 if i + 1 < n:
                     prefetch(i + 1)  # queued after this step's launches: the copy runs under step i, off its critical path
-                tot += float(ls.item())  # device -> host read of the step's result, every step
+                if i > 0:            # consume the previous step's loss (its copy finished long ago)
+                    loss_ev[(i - 1) % nbuf].synchronize()
+                    tot += float(loss_h[(i - 1) % nbuf][0])
+            loss_ev[(n - 1) % nbuf].synchronize()
+            tot += float(loss_h[(n - 1) % nbuf][0])
             return tot
 
         e2e_loop(max(2, a.warmup // 2))

@@ -128,6 +128,28 @@ def test_config2_fp32_parity_mode(oracle_run):
 
 
 @gpu
+def test_config2_production_matches_bf16_storage_oracle():
+    """production mode end to end against the oracle evaluated with the SAME storage points (weights, conv inputs and raw conv
+    outputs rounded to bf16, arithmetic in fp32: model_ref quant=True).  That emulation is itself 0.21 / 0.34 / 0.49 away
+    from the fp32 evaluation at this config (measured in the build container) -- the same distance the GPU shows -- so the
+    distance to fp32 is a property of bf16 storage in a random-init batch-norm network, and the kernels are judged here
+    against the like-for-like emulation."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    x, _ = config2_inputs()
+    sd = model_ref.make_state_dict(0)
+    with torch.no_grad():
+        ref = model_ref.forward(sd, x, train=True, quant=True, update_stats=False)
+    m, _ = make_model()
+    m.train()
+    with torch.no_grad():
+        out = m(x.cuda())
+    errs = [rel(out[i], ref[i]) for i in range(3)]
+    print("\nconfig 2, production bf16 mode vs bf16-storage oracle (train forward):", errs)
+    _record("production_vs_bf16_storage_oracle", {"out_rel": errs})
+    assert max(errs) < 1e-1, errs
+
+
+@gpu
 def test_config2_production_bf16_measured(oracle_run):
     """production mode (bf16 activation storage, bf16 tensor-core operands): the measured distance to the fp32 reference at
     this well-conditioned size; the bounds below are that measurement with headroom, not north_star's fp32 figure"""
