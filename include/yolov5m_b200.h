@@ -128,6 +128,16 @@ int yb_maxpool5_fwd(const void* x, int64_t x_pitch, int N, int H, int W, int C, 
                     uint8_t* argmax, void* stream);                    /* nn.MaxPool2d(5,1,2), model.py:103 */
 int yb_maxpool5_bwd(const void* dy, int64_t dy_pitch, const uint8_t* argmax, int N, int H, int W, int C, void* dx,
                     int64_t dx_pitch, int accumulate, void* stream);
+/* SPPF (model.py:96-112) pools its input three times in a chain: y1 = p(x), y2 = p(y1), y3 = p(y2), p = MaxPool2d(5,1,2).
+ * One launch: the H x W x 16-channel tile lives in shared memory for the three pools (separable row / column maximum with the
+ * reference's "first maximum wins" order).  y1..y3 share y_pitch (the three channel slices of the concat buffer); am1..am3
+ * (optional, all or none) receive the arg-max window slots for the backward pass.  Returns 1 (nothing launched) when the map
+ * does not fit one CTA's shared memory: chain yb_maxpool5_fwd then.  yb_sppf_pool3_bwd is the whole backward chain:
+ * g0 (+)= scatter(g1 + scatter(g2 + scatter(g3, am3), am2), am1), g0..g3 = the gradient slices [x | y1 | y2 | y3]. */
+int yb_sppf_pool3_fwd(const void* x, int64_t x_pitch, int N, int H, int W, int C, void* y1, void* y2, void* y3, int64_t y_pitch,
+                      uint8_t* am1, uint8_t* am2, uint8_t* am3, void* stream);
+int yb_sppf_pool3_bwd(const void* g1, const void* g2, const void* g3, int64_t g_pitch, const uint8_t* am1, const uint8_t* am2,
+                      const uint8_t* am3, int N, int H, int W, int C, void* g0, int64_t g0_pitch, int accumulate, void* stream);
 /* x (N,3,H,W) NCHW, dtype 0 = float32 in [0,1], 1 = uint8 (divided by 255, training_utils.py:98)
  * -> out (N,H/2,W/2,48) bf16: space-to-depth (12 -> 16 channels: (r*2+s)*3+c = x[c][2h+r][2w+s]) with the three horizontal
  * taps gathered (channel kw*16+j = s2d pixel w+kw-1, zero outside), so that the 6x6/s2 stem (model.py:184) becomes a

@@ -12,11 +12,14 @@ production bf16 mode with the MEASURED error reported beside it (written to gpur
 Measured on B200 (round 2): parity mode vs the fp32 oracle: outputs 2.7e-5 / 4.7e-5 / 8.3e-5, loss 0, gradient norm 2.2e-5,
 gradient rel. L2 1.10e-3 -- the last figure is the fp32 ORACLE's own distance to float64 (1.07e-3), hence this file's switch
 to the float64 referee.  Production bf16 mode: loss 1.9e-4, loss parts <= 2.9e-3, gradient norm 4.0e-2; outputs 0.21 / 0.34
-/ 0.48 and gradient direction 0.67 rel. L2: a random-initialised batch-norm network is chaotic (every layer re-normalises,
-perturbations grow by a few % per layer over 80 layers), so ANY reduced-precision storage -- bf16 here, fp16 autocast in the
-reference's own train_loop -- decorrelates the raw logits while the loss, its parts and the gradient scale stay put.  The
-per-layer (teacher-forced) comparison in test_model_gpu.py is what pins the production kernels; this file pins the engine
-end to end through the parity mode.
+/ 0.48 and gradient direction 0.67 rel. L2: a random-initialised batch-norm network amplifies perturbations layer after
+layer (every layer re-normalises; the known gradient / perturbation explosion of BN networks at initialisation), so ANY
+reduced-precision storage -- bf16 here, fp16 autocast in the reference's own train_loop -- decorrelates the raw logits
+while the loss, its parts and the gradient scale stay put.  Measured to make sure this is sensitivity and not a defect: the
+CPU oracle with emulated bf16 storage (model_ref quant=True) is 0.21 / 0.34 / 0.49 away from its own fp32 evaluation at this
+config, and the GPU is 0.15 / 0.25 / 0.38 away from that emulation -- two bf16 evaluations with different rounding details
+are as far from each other as each is from fp32.  The per-layer (teacher-forced) comparison in test_model_gpu.py is what
+pins the production kernels; this file pins the engine end to end through the parity mode.
 """
 import json
 import os
@@ -125,28 +128,6 @@ def test_config2_fp32_parity_mode(oracle_run):
     assert res["loss_rel"] < TOL and max(res["parts_rel"]) < TOL, res
     assert res["grad_norm_rel"] < TOL and res["grad_rel_l2"] < TOL, res
     assert res["grad_per_tensor_max"][1] < 5 * TOL, res
-
-
-@gpu
-def test_config2_production_matches_bf16_storage_oracle():
-    """production mode end to end against the oracle evaluated with the SAME storage points (weights, conv inputs and raw conv
-    outputs rounded to bf16, arithmetic in fp32: model_ref quant=True).  That emulation is itself 0.21 / 0.34 / 0.49 away
-    from the fp32 evaluation at this config (measured in the build container) -- the same distance the GPU shows -- so the
-    distance to fp32 is a property of bf16 storage in a random-init batch-norm network, and the kernels are judged here
-    against the like-for-like emulation."""
-    torch.set_num_threads(os.cpu_count() or 1)
-    x, _ = config2_inputs()
-    sd = model_ref.make_state_dict(0)
-    with torch.no_grad():
-        ref = model_ref.forward(sd, x, train=True, quant=True, update_stats=False)
-    m, _ = make_model()
-    m.train()
-    with torch.no_grad():
-        out = m(x.cuda())
-    errs = [rel(out[i], ref[i]) for i in range(3)]
-    print("\nconfig 2, production bf16 mode vs bf16-storage oracle (train forward):", errs)
-    _record("production_vs_bf16_storage_oracle", {"out_rel": errs})
-    assert max(errs) < 1e-1, errs
 
 
 @gpu

@@ -140,6 +140,47 @@ def test_maxpool5_chain_fwd_bwd():
     assert rel(dcat[..., :C].float().cpu().permute(0, 3, 1, 2), xr.grad) < 2e-2
 
 
+@pytest.mark.parametrize("shape", [(2, 20, 20, 64), (3, 7, 12, 48), (1, 40, 40, 32)])
+def test_sppf_pool3_fused_matches_chain(shape):
+    """the one-launch SPPF pooling (sppf_pool3_*) against the chain of single pools: values and arg-max slots bit for bit
+    (ties included: quantised inputs), backward against fp32 autograd"""
+    N, H, W, C = shape
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(7)
+    x = (torch.randn(N, C, H, W, generator=g) * 2).round().div(2).to(torch.bfloat16)   # many exact ties
+    cat_a = torch.zeros(N, H, W, 4 * C, device="cuda", dtype=torch.bfloat16)
+    cat_a[..., :C] = nhwc(x).cuda()
+    cat_b = cat_a.clone()
+    am_a = torch.zeros(3, N, H, W, C, device="cuda", dtype=torch.uint8)
+    am_b = torch.zeros_like(am_a)
+    for i in range(3):
+        _lib.check(L.yb_maxpool5_fwd(_lib.ptr(cat_a[..., i * C:]), _lib.c_i64(4 * C), N, H, W, C,
+                                     _lib.ptr(cat_a[..., (i + 1) * C:]), _lib.c_i64(4 * C), _lib.ptr(am_a[i]), _lib.stream()))
+    rc = L.yb_sppf_pool3_fwd(_lib.ptr(cat_b), _lib.c_i64(4 * C), N, H, W, C, _lib.ptr(cat_b[..., C:]), _lib.ptr(cat_b[..., 2 * C:]),
+                             _lib.ptr(cat_b[..., 3 * C:]), _lib.c_i64(4 * C), _lib.ptr(am_b[0]), _lib.ptr(am_b[1]),
+                             _lib.ptr(am_b[2]), _lib.stream())
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert torch.equal(cat_a, cat_b)
+    assert torch.equal(am_a, am_b)
+    # backward: fused chain vs fp32 autograd of the three pools
+    xr = x.float().requires_grad_(True)
+    p1 = F.max_pool2d(xr, 5, 1, 2); p2 = F.max_pool2d(p1, 5, 1, 2); p3 = F.max_pool2d(p2, 5, 1, 2)
+    gs = [torch.randn(N, C, H, W, generator=g).to(torch.bfloat16) for _ in range(4)]
+    (xr * gs[0].float() + p1 * gs[1].float() + p2 * gs[2].float() + p3 * gs[3].float()).sum().backward()
+    dcat = torch.cat([nhwc(t) for t in gs], -1).cuda()
+    rc = L.yb_sppf_pool3_bwd(_lib.ptr(dcat[..., C:]), _lib.ptr(dcat[..., 2 * C:]), _lib.ptr(dcat[..., 3 * C:]), _lib.c_i64(4 * C),
+                             _lib.ptr(am_b[0]), _lib.ptr(am_b[1]), _lib.ptr(am_b[2]), N, H, W, C, _lib.ptr(dcat), _lib.c_i64(4 * C),
+                             1, _lib.stream())
+    if H * W * 144 > 200 * 1024:
+        assert rc == 1   # tile too large for the fused backward: the engine chains yb_maxpool5_bwd instead
+        return
+    assert rc == 0
+    torch.cuda.synchronize()
+    # ATen routes a tie to the first maximum of the window too, so the gradients agree up to the bf16 store of the result
+    assert rel(dcat[..., :C].float().cpu().permute(0, 3, 1, 2), xr.grad) < 4e-3
+
+
 def test_upsample_add_prep_pack():
     L = _lib.lib()
     g = torch.Generator().manual_seed(4)

@@ -596,6 +596,225 @@ __global__ void maxpool5_bwd_kernel(const bf16* __restrict__ dy, long dy_pitch, 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ fused SPPF pooling
+// SPPF (model.py:96-112) chains three 5/1/2 max pools: cat[x, p(x), p(p(x)), p(p(p(x)))].  One CTA owns one image x 16
+// channels: the H x W tile is loaded into shared memory once and the three pools run back to back there, each as a
+// separable pass (row maximum over kw, then column maximum over kh of the row results: 10 shared-memory reads per output
+// instead of 25 global loads; "first maximum in row-major window order wins, NaN propagates" is preserved by the
+// separation: the row pass keeps the first maximum of each row, the column pass the first row that holds the window
+// maximum).  Outputs are the three channel slices of the concat buffer plus the 1-byte arg-max window slots for backward.
+// Replaces three maxpool5_fwd launches that each re-read their input 25 times through L1/L2 (0.31 ms -> one launch).
+struct Px16 {
+  uint4 lo, hi;  // 16 bf16 channels
+};
+__device__ __forceinline__ void unpack16(const Px16& p, float (&v)[16]) {
+  const V8 a = cvt8(p.lo), b = cvt8(p.hi);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    v[j] = a.v[j];
+    v[8 + j] = b.v[j];
+  }
+}
+__device__ __forceinline__ Px16 pack16(const float (&v)[16]) {
+  Px16 p;
+  __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&p.lo);
+  __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&p.hi);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    h0[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    h1[j] = __floats2bfloat162_rn(v[8 + 2 * j], v[8 + 2 * j + 1]);
+  }
+  return p;
+}
+
+__global__ void __launch_bounds__(256) sppf_pool3_fwd_kernel(const bf16* __restrict__ x, long x_pitch, int H, int W, int C,
+                                                             bf16* __restrict__ y1, bf16* __restrict__ y2, bf16* __restrict__ y3,
+                                                             long y_pitch, uint8_t* __restrict__ am1, uint8_t* __restrict__ am2,
+                                                             uint8_t* __restrict__ am3) {
+  extern __shared__ __align__(16) uint8_t sp_smem[];
+  const int HW = H * W;
+  Px16* cur = reinterpret_cast<Px16*>(sp_smem);            // [HW] input of the current pool
+  Px16* rmv = cur + HW;                                     // [HW] row maxima
+  uint4* rma = reinterpret_cast<uint4*>(rmv + HW);          // [HW] kw slot of each row maximum, 16 x uint8
+  const int cg = C >> 4;
+  const long n = blockIdx.x / cg;
+  const int c0 = (int)(blockIdx.x - n * cg) << 4;
+  const long pix0 = n * HW;
+  for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+    const bf16* src = x + (pix0 + p) * x_pitch + c0;
+    cur[p].lo = ldraw(src);
+    cur[p].hi = ldraw(src + 8);
+  }
+  __syncthreads();
+  for (int stage = 0; stage < 3; ++stage) {
+    bf16* yo = stage == 0 ? y1 : (stage == 1 ? y2 : y3);
+    uint8_t* am = stage == 0 ? am1 : (stage == 1 ? am2 : am3);
+    // row pass: first maximum over kw = 0..4 (w - 2 .. w + 2) inside the image
+    for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+      const int h = p / W, w = p - h * W;
+      float best[16];
+      unsigned arg[16];
+      const unsigned a0 = (unsigned)max(0, 2 - w);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        best[j] = -INFINITY;
+        arg[j] = a0;
+      }
+#pragma unroll
+      for (int kw = 0; kw < 5; ++kw) {
+        const int iw = w + kw - 2;
+        if (iw < 0 || iw >= W) continue;
+        float v[16];
+        unpack16(cur[h * W + iw], v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (v[j] > best[j] || v[j] != v[j]) {
+            best[j] = v[j];
+            arg[j] = kw;
+          }
+      }
+      rmv[p] = pack16(best);  // values are bf16 already: exact
+      uint4 pk;
+      pk.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+      pk.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
+      pk.z = arg[8] | (arg[9] << 8) | (arg[10] << 16) | (arg[11] << 24);
+      pk.w = arg[12] | (arg[13] << 8) | (arg[14] << 16) | (arg[15] << 24);
+      rma[p] = pk;
+    }
+    __syncthreads();
+    // column pass: first row (kh = 0..4) whose row maximum is the window maximum; slot = kh * 5 + kw
+    for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+      const int h = p / W, w = p - h * W;
+      float best[16];
+      unsigned arg[16];
+      const unsigned a0 = (unsigned)(max(0, 2 - h) * 5 + max(0, 2 - w));
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        best[j] = -INFINITY;
+        arg[j] = a0;
+      }
+#pragma unroll
+      for (int kh = 0; kh < 5; ++kh) {
+        const int ih = h + kh - 2;
+        if (ih < 0 || ih >= H) continue;
+        float v[16];
+        unpack16(rmv[ih * W + w], v);
+        const uint4 ka = rma[ih * W + w];
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (v[j] > best[j] || v[j] != v[j]) {
+            const unsigned word = j < 4 ? ka.x : (j < 8 ? ka.y : (j < 12 ? ka.z : ka.w));
+            best[j] = v[j];
+            arg[j] = (unsigned)kh * 5u + ((word >> (8 * (j & 3))) & 0xffu);
+          }
+      }
+      const Px16 o = pack16(best);
+      bf16* dst = yo + (pix0 + p) * y_pitch + c0;
+      *reinterpret_cast<uint4*>(dst) = o.lo;
+      *reinterpret_cast<uint4*>(dst + 8) = o.hi;
+      if (am != nullptr) {
+        uint4 pk;
+        pk.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+        pk.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
+        pk.z = arg[8] | (arg[9] << 8) | (arg[10] << 16) | (arg[11] << 24);
+        pk.w = arg[12] | (arg[13] << 8) | (arg[14] << 16) | (arg[15] << 24);
+        *reinterpret_cast<uint4*>(am + (pix0 + p) * C + c0) = pk;
+      }
+      __syncwarp();
+      // the output of this pool is the input of the next one; `cur` is no longer read in this stage (the row pass is done)
+      cur[p] = o;
+    }
+    __syncthreads();
+  }
+}
+
+// backward of the chain in one launch: g2 += scatter(g3, am3); g1 += scatter(g2, am2); g0 += scatter(g1, am1), the
+// intermediate sums kept in fp32 in shared memory (gather form: every input pixel sums the <= 25 outputs that point at
+// it).  g0..g3 = gradient slices of the concat buffer ([x | p1 | p2 | p3]); only g0 is written (g1 / g2 have no other reader).
+__global__ void __launch_bounds__(256) sppf_pool3_bwd_kernel(const bf16* __restrict__ g1, const bf16* __restrict__ g2,
+                                                             const bf16* __restrict__ g3, long g_pitch, const uint8_t* __restrict__ am1,
+                                                             const uint8_t* __restrict__ am2, const uint8_t* __restrict__ am3, int H, int W,
+                                                             int C, bf16* __restrict__ g0, long g0_pitch, int accumulate) {
+  extern __shared__ __align__(16) uint8_t sp_smem[];
+  const int HW = H * W;
+  float* up = reinterpret_cast<float*>(sp_smem);            // [HW][16] gradient w.r.t. the output of the current pool
+  float* dn = up + (size_t)HW * 16;                         // [HW][16] gradient w.r.t. its input
+  uint4* am = reinterpret_cast<uint4*>(dn + (size_t)HW * 16);  // [HW] arg-max slots of the current pool
+  const int cg = C >> 4;
+  const long n = blockIdx.x / cg;
+  const int c0 = (int)(blockIdx.x - n * cg) << 4;
+  const long pix0 = n * HW;
+  for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+    Px16 v;
+    const bf16* src = g3 + (pix0 + p) * g_pitch + c0;
+    v.lo = ldraw(src);
+    v.hi = ldraw(src + 8);
+    float f[16];
+    unpack16(v, f);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) up[p * 16 + j] = f[j];
+  }
+  for (int stage = 2; stage >= 0; --stage) {
+    const uint8_t* ams = stage == 2 ? am3 : (stage == 1 ? am2 : am1);
+    for (int p = threadIdx.x; p < HW; p += blockDim.x) am[p] = *reinterpret_cast<const uint4*>(ams + (pix0 + p) * C + c0);
+    __syncthreads();
+    for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+      const int h = p / W, w = p - h * W;
+      float acc[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int kh = 0; kh < 5; ++kh) {
+        const int oh = h - kh + 2;
+        if (oh < 0 || oh >= H) continue;
+#pragma unroll
+        for (int kw = 0; kw < 5; ++kw) {
+          const int ow = w - kw + 2;
+          if (ow < 0 || ow >= W) continue;
+          const int op = oh * W + ow;
+          const uint4 ka = am[op];
+          const unsigned k = kh * 5 + kw;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const unsigned word = j < 4 ? ka.x : (j < 8 ? ka.y : (j < 12 ? ka.z : ka.w));
+            if (((word >> (8 * (j & 3))) & 0xffu) == k) acc[j] += up[op * 16 + j];
+          }
+        }
+      }
+      // add the gradient the concat slice of this pool's INPUT received directly from c_out (stage 0: x's slice, g0)
+      if (stage > 0) {
+        Px16 v;
+        const bf16* src = (stage == 2 ? g2 : g1) + (pix0 + p) * g_pitch + c0;
+        v.lo = ldraw(src);
+        v.hi = ldraw(src + 8);
+        float f[16];
+        unpack16(v, f);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dn[p * 16 + j] = acc[j] + f[j];
+      } else {
+        bf16* dst = g0 + (pix0 + p) * g0_pitch + c0;
+        if (accumulate) {
+          Px16 v;
+          v.lo = ldraw(dst);
+          v.hi = ldraw(dst + 8);
+          float f[16];
+          unpack16(v, f);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] += f[j];
+        }
+        const Px16 o = pack16(acc);
+        *reinterpret_cast<uint4*>(dst) = o.lo;
+        *reinterpret_cast<uint4*>(dst + 8) = o.hi;
+      }
+    }
+    __syncthreads();
+    float* t = up;
+    up = dn;
+    dn = t;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ input staging
 // x (N,3,H,W) float in [0,1] (or uint8, divided by 255) -> out (N,H/2,W/2,48) bf16:
 //   space-to-depth: s2d[ho][wo][(r*2+s)*3+c] = x[c][2ho+r][2wo+s] (12 channels, padded to 16), then the three horizontal taps
@@ -883,6 +1102,38 @@ int yb_maxpool5_bwd(const void* dy, int64_t dy_pitch, const uint8_t* argmax, int
   const long npix = (long)N * H * W;
   maxpool5_bwd_kernel<<<ew_blocks(npix * (C / 8)), 256, 0, ST(stream)>>>(CB16(dy), dy_pitch, argmax, H, W, C, npix,
                                                                           B16(dx), dx_pitch, accumulate);
+  LAUNCH_OK();
+  return 0;
+}
+
+int yb_sppf_pool3_fwd(const void* x, int64_t x_pitch, int N, int H, int W, int C, void* y1, void* y2, void* y3, int64_t y_pitch,
+                      uint8_t* am1, uint8_t* am2, uint8_t* am3, void* stream) {
+  YB_REQUIRE(C % 16 == 0 && x_pitch % 8 == 0 && y_pitch % 8 == 0, "sppf_pool3_fwd: alignment (C %% 16, pitches %% 8)");
+  const size_t smem = (size_t)H * W * (32 + 32 + 16);
+  if (smem > 200 * 1024) return 1;  // map too large for one CTA's shared memory: the caller chains yb_maxpool5_fwd instead
+  static size_t attr = 0;
+  if (smem > attr) {
+    YB_CHECK_CUDA(cudaFuncSetAttribute(sppf_pool3_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  sppf_pool3_fwd_kernel<<<N * (C / 16), 256, smem, ST(stream)>>>(CB16(x), x_pitch, H, W, C, B16(y1), B16(y2), B16(y3), y_pitch,
+                                                                am1, am2, am3);
+  LAUNCH_OK();
+  return 0;
+}
+
+int yb_sppf_pool3_bwd(const void* g1, const void* g2, const void* g3, int64_t g_pitch, const uint8_t* am1, const uint8_t* am2,
+                      const uint8_t* am3, int N, int H, int W, int C, void* g0, int64_t g0_pitch, int accumulate, void* stream) {
+  YB_REQUIRE(C % 16 == 0 && g_pitch % 8 == 0 && g0_pitch % 8 == 0, "sppf_pool3_bwd: alignment (C %% 16, pitches %% 8)");
+  const size_t smem = (size_t)H * W * (64 + 64 + 16);
+  if (smem > 200 * 1024) return 1;
+  static size_t attr = 0;
+  if (smem > attr) {
+    YB_CHECK_CUDA(cudaFuncSetAttribute(sppf_pool3_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  sppf_pool3_bwd_kernel<<<N * (C / 16), 256, smem, ST(stream)>>>(CB16(g1), CB16(g2), CB16(g3), g_pitch, am1, am2, am3, H, W, C,
+                                                                B16(g0), g0_pitch, accumulate);
   LAUNCH_OK();
   return 0;
 }

@@ -395,19 +395,30 @@ class _Engine:
         N, H, W = xin.N, xin.H, xin.W
         cat = self.buf(N, H, W, 4 * c_)
         self.cbl(mod.c1, xin, cat.v(0, c_))
+        views = [cat.v(i * c_, c_) for i in range(4)]
+        ams = [torch.empty(N, H, W, c_, device=self.dev, dtype=torch.uint8) if self.train else None for _ in range(3)]
+        amp = [a.data_ptr() if a is not None else None for a in ams]
+        # the three chained 5x5 pools of model.py:108-110 as ONE launch when the map fits a CTA's shared memory
+        # (csrc/elementwise.cu: sppf_pool3_*); otherwise (and in parity mode) three maxpool launches
+        fused_fwd = not self.parity and c_ % 16 == 0 and H * W * 80 <= 200 * 1024
+        fused_bwd = fused_fwd and H * W * 144 <= 200 * 1024
+        if fused_fwd:
+            v = views
+            self.fwd_ops.append(lambda st: _lib.check(L.yb_sppf_pool3_fwd(v[0].ptr, v[0].pitch, N, H, W, c_, v[1].ptr, v[2].ptr,
+                                                                          v[3].ptr, v[1].pitch, amp[0], amp[1], amp[2], st)))
         for i in range(3):
-            src, dst = cat.v(i * c_, c_), cat.v((i + 1) * c_, c_)
-            am = torch.empty(N, H, W, c_, device=self.dev, dtype=torch.uint8) if self.train else None
-            amp = am.data_ptr() if am is not None else None
+            src, dst = views[i], views[i + 1]
             if self.parity:
-                self.fwd_ops.append(lambda st, src=src, dst=dst, amp=amp: _lib.check(
+                self.fwd_ops.append(lambda st, src=src, dst=dst, a=amp[i]: _lib.check(
                     L.yb_p32_maxpool5_fwd(src.ptr, src.pitch, N, H, W, c_, dst.ptr, dst.plptr(0), dst.pitch, dst.plane_stride,
-                                          amp, st)))
-            else:
-                self.fwd_ops.append(lambda st, src=src, dst=dst, amp=amp: _lib.check(
-                    L.yb_maxpool5_fwd(src.ptr, src.pitch, N, H, W, c_, dst.ptr, dst.pitch, amp, st)))
-            if self.train:
-                self.tape.append(("pool", src, dst, am))
+                                          a, st)))
+            elif not fused_fwd:
+                self.fwd_ops.append(lambda st, src=src, dst=dst, a=amp[i]: _lib.check(
+                    L.yb_maxpool5_fwd(src.ptr, src.pitch, N, H, W, c_, dst.ptr, dst.pitch, a, st)))
+            if self.train and not fused_bwd:
+                self.tape.append(("pool", src, dst, ams[i]))
+        if self.train and fused_bwd:
+            self.tape.append(("pool3", views, ams))
         self.cbl(mod.c_out, cat.v(), out)
 
     def head(self, i, xin):
@@ -588,6 +599,16 @@ class _Engine:
                     self._conv(dplan, st, flops, "dgrad")
                     self._wgrad_async(evs, wplan, st, flops, g + 4 * r.w_off, r.cout, None, 0)
                 self._add_bwd_op(op, [(r.bias_off, r.cout), (r.w_off, r.cout * r.cin)])
+            elif kind == "pool3":
+                _, v, ams = rec
+                for d in v[1:]:
+                    self._flush_pending(d)
+                    assert self._contrib_state(d), "SPPF: pooled-slice gradient never produced"
+                acc = 1 if self._contrib_state(v[0]) else 0
+                v[0].buf.gw[v[0].c0:v[0].c0 + v[0].C] = True
+                self.bwd_ops.append(lambda st, g, v=v, ams=ams, acc=acc: _lib.check(
+                    L.yb_sppf_pool3_bwd(v[1].gptr, v[2].gptr, v[3].gptr, v[1].pitch, ams[0].data_ptr(), ams[1].data_ptr(),
+                                        ams[2].data_ptr(), v[0].N, v[0].H, v[0].W, v[0].C, v[0].gptr, v[0].pitch, acc, st)))
             elif kind == "pool":
                 _, src, dst, am = rec
                 self._flush_pending(dst)
