@@ -541,7 +541,7 @@ def run_ours(a):
 
     # ---- (3) roofline of the dominant kernel: CUDA events around every conv launch (separate instrumented steps)
     #      every rank runs these steps (they contain the gradient all-reduce); only rank 0 records events
-    roof, kern = None, None
+    roof, kern, roof_hbm = None, None, None
     eng = model.engine(B, S, S, True)
     nprof = min(3, a.steps)
     if rank == 0:
@@ -562,11 +562,23 @@ def run_ours(a):
         ach = igemm_f / igemm_t / 1e12
         roof = {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM conv (conv_igemm_kernel + conv_patch_kernel: all fwd + dgrad launches)",
                 "achieved": ach, "peak": peak_tf, "peak_source": peak_src + " bf16_tflops_sustained", "unit": "TFLOP/s",
-                "frac": ach / peak_tf, "traffic": conv_traffic_per_launch(), "traffic_unit": "bytes/launch (dram read+write, ncu)",
+                "frac": ach / peak_tf, "traffic": conv_traffic_per_launch(),
+                "traffic_unit": "bytes/launch (dram read+write); PROFILE CONSTANT from the committed ncu launch list "
+                                "profiles/launch_summary_*.json of this same command, not re-measured at bench time",
                 "launches_per_step": igemm_n // nprof, "avg_launch_us": igemm_t / igemm_n * 1e6,
                 "flop_per_launch": igemm_f / igemm_n, "ms_per_step": igemm_t / nprof * 1e3}
         kern = {k: {"tflops": v[0] / v[1] / 1e12, "ms_per_step": v[1] / nprof * 1e3, "launches_per_step": v[2] // nprof}
-                for k, v in acc.items()}
+                for k, v in acc.items() if not k.startswith("bn_")}
+        # second roofline entry: the HBM-bound share of the step (BN/SiLU passes), algorithmic bytes / CUDA-event time
+        ew = [acc[k] for k in ("bn_fwd", "bn_bwd_reduce", "bn_bwd_apply") if k in acc]
+        if ew:
+            eb, et, en = sum(v[0] for v in ew), sum(v[1] for v in ew), sum(v[2] for v in ew)
+            roof_hbm = {"bound": "hbm", "kernel": "bn_act_fwd + bn_act_bwd_reduce + bn_act_bwd_apply (elementwise.cu)",
+                        "achieved": eb / et / 1e9, "peak": peak_hbm, "peak_source": peak_src + " hbm_gbs", "unit": "GB/s",
+                        "frac": eb / et / 1e9 / peak_hbm, "traffic": None, "launches_per_step": en // nprof,
+                        "bytes_per_launch": eb / en, "avg_launch_us": et / en * 1e6, "ms_per_step": et / nprof * 1e3,
+                        "per_pass": {k: {"GBps": acc[k][0] / acc[k][1] / 1e9, "ms_per_step": acc[k][1] / nprof * 1e3}
+                                     for k in ("bn_fwd", "bn_bwd_reduce", "bn_bwd_apply") if k in acc}}
         kern["whole_step_conv_tflops"] = value / world * TRAIN_GFLOP_PER_IMG * 1e9 / 1e12
     if world > 1:
         dist.barrier()
@@ -586,7 +598,7 @@ def run_ours(a):
                                    "(fwd + ComputeLoss + bwd + grad all-reduce + clip(10) + Adam)",
                        "batch_per_gpu": B, "global_batch": B * world, "image": S, "targets_per_image": 8,
                        "parallelism": f"dp{world}", "l2_policy": "inputs larger than L2 (activations of one step >> 126 MB)"},
-            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roof, "roofline_hbm": roof_hbm, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks.summary(windows), "kernels": kern, "loss": last_loss,
         }
         print(json.dumps(out))

@@ -721,7 +721,6 @@ __global__ void __launch_bounds__(256) sppf_pool3_fwd_kernel(const bf16* __restr
         pk.w = arg[12] | (arg[13] << 8) | (arg[14] << 16) | (arg[15] << 24);
         *reinterpret_cast<uint4*>(am + (pix0 + p) * C + c0) = pk;
       }
-      __syncwarp();
       // the output of this pool is the input of the next one; `cur` is no longer read in this stage (the row pass is done)
       cur[p] = o;
     }

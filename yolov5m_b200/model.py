@@ -230,6 +230,18 @@ class _Engine:
         e1.record()
         self.prof.append((kind, flops, e0, e1))
 
+    def _ew(self, kind, nbytes, fn, *args):
+        """HBM-bound pass (BN/SiLU forward, backward reduce, backward apply): timed like the convs when prof is a list; the
+        second field of the record is the pass's ALGORITHMIC bytes (every tensor read / written once)"""
+        if self.prof is None:
+            _lib.check(fn(*args))
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(fn(*args))
+        e1.record()
+        self.prof.append((kind, nbytes, e0, e1))
+
     def _wgrad(self, plan, st, flops, *args):
         if self.prof is None:
             _lib.check(self.L.yb_wgrad_plan_run(plan, *args, st))
@@ -323,8 +335,8 @@ class _Engine:
             self._conv(plan, st, flops, "fwd")
             _lib.check(L.yb_bn_finalize(ptrs[0], nrows, C, count, gam, bet, bn.eps, bn.momentum, rm, rv, nbt, ptrs[1], ptrs[2],
                                         ptrs[3], ptrs[4], 1, st))
-            _lib.check(L.yb_bn_act_fwd(y.ptr, C, y.N, y.H, y.W, C, ptrs[1], ptrs[2], resp, resl, out.ptr, out.pitch, upp,
-                                       upl, st))
+            self._ew("bn_fwd", ew_bytes, L.yb_bn_act_fwd, y.ptr, C, y.N, y.H, y.W, C, ptrs[1], ptrs[2], resp, resl, out.ptr,
+                     out.pitch, upp, upl, st)
         self.fwd_ops.append(op)
         self._dy_elems = max(self._dy_elems, y.npix * C)
         self.tape.append(("cbl", r, xin, out, y, res, up, ptrs, flops))
@@ -697,13 +709,13 @@ class _Engine:
 
                 def op(st, g, r=r, out=out, y=y, ptrs=ptrs, C=C, npix=npix, wplan=wplan, dplan=dplan, mapp=mapp, rows=rows,
                        count=count, flops=flops, dy_ptr=dy_ptr, evs=evs, dy_free=dy_free):
-                    _lib.check(L.yb_bn_act_bwd_reduce(out.gptr, out.pitch, y.ptr, C, npix, C, ptrs[1], ptrs[2], ptrs[3],
-                                                      ptrs[4], redp, ctypes.byref(rows), st))
+                    self._ew("bn_bwd_reduce", 4.0 * npix * C, L.yb_bn_act_bwd_reduce, out.gptr, out.pitch, y.ptr, C, npix, C,
+                             ptrs[1], ptrs[2], ptrs[3], ptrs[4], redp, ctypes.byref(rows), st)
                     _lib.check(L.yb_bn_bwd_finalize(redp, rows.value, C, count, g + 4 * r.g_off, g + 4 * r.b_off, coefp, 0, st))
                     if dy_free is not None and self._side_on:
                         self._main.wait_event(dy_free)  # the wgrad that still reads this dy buffer (two layers back)
-                    _lib.check(L.yb_bn_act_bwd_apply(out.gptr, out.pitch, y.ptr, C, npix, C, ptrs[1], ptrs[2], ptrs[3],
-                                                     ptrs[4], coefp, dy_ptr, C, st))
+                    self._ew("bn_bwd_apply", 6.0 * npix * C, L.yb_bn_act_bwd_apply, out.gptr, out.pitch, y.ptr, C, npix, C,
+                             ptrs[1], ptrs[2], ptrs[3], ptrs[4], coefp, dy_ptr, C, st)
                     if dplan is not None:
                         self._conv(dplan, st, flops, "dgrad")
                     self._wgrad_async(evs, wplan, st, flops, g + 4 * r.w_off, C, mapp, 0)
