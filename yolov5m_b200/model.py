@@ -328,7 +328,8 @@ class _Engine:
         ptrs = (stats.data_ptr(), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), invstd.data_ptr())
         resp, resl = (res.ptr, res.pitch) if res is not None else (None, 0)
         upp, upl = (up.ptr, up.pitch) if up is not None else (None, 0)
-
+        # algorithmic bytes of the BN+SiLU pass: read y, write a (+ read the residual, + 4 upsampled copies), 2 B / element
+        ew_bytes = 2.0 * y.npix * C * (2 + (1 if res is not None else 0) + (4 if up is not None else 0))
         bn = r.bn  # eps / momentum are read at launch time, like nn.BatchNorm2d reads its attributes
 
         def op(st):
