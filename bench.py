@@ -546,10 +546,16 @@ def run_ours(a):
     nprof = min(3, a.steps)
     if rank == 0:
         eng.prof = []
+        sync.prof = []
     for i in range(nprof):
         step(dev_imgs[i % nbuf], dev_tgts[i % nbuf])
     torch.cuda.synchronize()
+    exch = {"mode": sync.mode if world > 1 else "none", "p2p_fallback_reason": sync.p2p_error}
     if rank == 0:
+        if sync.prof:
+            # includes the wait for the slowest rank (the exchange starts with a cross-rank barrier)
+            exch["ms_per_step_incl_straggler_wait"] = sum(a.elapsed_time(b) for a, b in sync.prof) / len(sync.prof)
+        sync.prof = None
         acc = {}
         for kind, flops, s0, s1 in eng.prof:
             d = acc.setdefault(kind, [0.0, 0.0, 0])
@@ -597,7 +603,7 @@ def run_ours(a):
             "config": {"workload": "configs[2]: full train step bf16 bs=64/GPU 640x640 synthetic COCO-80 "
                                    "(fwd + ComputeLoss + bwd + grad all-reduce + clip(10) + Adam)",
                        "batch_per_gpu": B, "global_batch": B * world, "image": S, "targets_per_image": 8,
-                       "parallelism": f"dp{world}", "l2_policy": "inputs larger than L2 (activations of one step >> 126 MB)"},
+                       "parallelism": f"dp{world}", "grad_exchange": exch, "l2_policy": "inputs larger than L2 (activations of one step >> 126 MB)"},
             "roofline": roof, "roofline_hbm": roof_hbm, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks.summary(windows), "kernels": kern, "loss": last_loss,
         }

@@ -213,9 +213,21 @@ class GradSync:
         per = (n + self.chunks - 1) // self.chunks
         return [min(n, c * per) for c in range(self.chunks + 1)]
 
+    prof = None  # set to a list to record (CUDA event, CUDA event) around every exchange (bench.py: grad_exchange.ms_per_step)
+
     def all_reduce(self, grads=None):
         if self.world == 1:
             return
+        if self.prof is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self._all_reduce(grads)
+            e1.record()
+            self.prof.append((e0, e1))
+            return
+        self._all_reduce(grads)
+
+    def _all_reduce(self, grads=None):
         g = self.model.flat_grads if grads is None else grads
         if self._symm is not None and g.data_ptr() == self._bucket.data_ptr():
             L, st = _lib.lib(), _lib.stream()
