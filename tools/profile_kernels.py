@@ -123,6 +123,11 @@ def main():
         job(lambda pdg=pdg: L.yb_plan_run(pdg, st))
         job(lambda pw=pw, dw=dw, cout=cout: L.yb_wgrad_plan_run(pw, dw.data_ptr(), cout, None, 0, st))
 
+    if len(sys.argv) > 1 and sys.argv[1].startswith("conv:"):   # e.g. conv:96,96,1,80,fwd -> only that conv launch
+        cin, cout, k, hh, which = sys.argv[1][5:].split(",")
+        sel = {(96, 96, 3, 80): 0, (192, 192, 3, 40): 1, (96, 96, 1, 80): 2}[(int(cin), int(cout), int(k), int(hh))]
+        base = len(JOBS) - 9 + 3 * sel + {"fwd": 0, "dgrad": 1, "wgrad": 2}[which]
+        JOBS[:] = [JOBS[base]]
     for fn in JOBS:   # warm-up
         fn()
     torch.cuda.synchronize()
