@@ -45,6 +45,10 @@ __device__ __forceinline__ EpiArgs load_epi_args(const P& p) {
 // P: EpiArgs (register copy of the epilogue fields of ConvKParams (stats, scale, shift, act, addend, out_kind, out,
 // Cout, H, W, head_na, head_no).  t_addr: TMEM address of column 0 of this chunk for this warp's lane quarter.
 // (n, h, w): output pixel of this thread's row; opix / apix: element offsets of that pixel in out / addend.
+__device__ __forceinline__ void conv_epilogue_process(const EpiArgs& p, const uint32_t* vr, int col0, bool valid, int n, int h, int w,
+                                                      int64_t opix, int64_t apix, float* my_stats, int lane, uint8_t* stage_row,
+                                                      int ccl, int row);
+
 // stage_row: when non-null, the bf16 result goes to shared memory instead of global memory: the address of this thread's
 // 128-byte row in the FIRST 64-channel slab of the tile's staging area (slabs are 16 KB apart); ccl = index of this
 // 16-channel chunk inside the tile.  The layout is the SWIZZLE_128B box layout the output tensor map stores from: 16-byte
@@ -55,6 +59,13 @@ __device__ __forceinline__ void conv_epilogue_chunk(const EpiArgs& p, uint32_t t
     uint32_t vr[16];
     tmem_ld16(t_addr, vr);
     tmem_ld_wait();
+    conv_epilogue_process(p, vr, col0, valid, n, h, w, opix, apix, my_stats, lane, stage_row, ccl, row);
+}
+
+// the per-chunk work on 16 accumulator columns already in registers
+__device__ __forceinline__ void conv_epilogue_process(const EpiArgs& p, const uint32_t* vr, int col0, bool valid, int n, int h, int w,
+                                                      int64_t opix, int64_t apix, float* my_stats, int lane, uint8_t* stage_row,
+                                                      int ccl, int row) {
     float v[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(vr[j]);
@@ -190,6 +201,20 @@ __device__ __forceinline__ void conv_epilogue_chunk(const EpiArgs& p, uint32_t t
         }
       }
     }
+}
+
+// two adjacent 16-column chunks with ONE 32-column TMEM load: half as many load -> wait round trips per tile (the
+// epilogue of the small-K layers is bound by that latency: ncu long-scoreboard stalls on the first use of the loaded
+// registers, three epilogue warps per scheduler cannot hide it)
+__device__ __forceinline__ void conv_epilogue_chunk2(const EpiArgs& p, uint32_t t_addr, int col0, bool valid, int n, int h, int w,
+                                                     int64_t opix, int64_t apix, float* my_stats, int lane, uint8_t* stage_row,
+                                                     int ccl, int row) {
+    uint32_t vr[32];
+    tmem_ld32(t_addr, vr);
+    tmem_ld_wait();
+    conv_epilogue_process(p, vr, col0, valid, n, h, w, opix, apix, my_stats, lane, stage_row, ccl, row);
+    if (col0 + 16 < p.Cout)
+      conv_epilogue_process(p, vr + 16, col0 + 16, valid, n, h, w, opix, apix, my_stats, lane, stage_row, ccl + 1, row);
 }
 
 }  // namespace yb

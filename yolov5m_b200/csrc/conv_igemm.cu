@@ -211,8 +211,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     // TMA-store epilogue: the bf16 tile is staged in shared memory (swizzled box layout) and leaves as one bulk tensor
     // store per 64-channel slab, issued by one thread; per-thread st.global rows (32 sectors per warp instruction) were the
     // top stall of every small-K layer (store back-pressure)
-    int tma_store = p.tma_store;
+    int tma_store = p.tma_store, x32 = p.epi_x32;
     keep_in_reg(tma_store);
+    keep_in_reg(x32);
     uint8_t* stage_row = tma_store ? o_stage + (size_t)r * 128 : nullptr;
     const bool issuer = threadIdx.x == 128;
     int it = 0;
@@ -232,10 +233,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         asm volatile("bar.sync 2, %0;" ::"n"(kEpiThreads) : "memory");
       }
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 256;
-      for (int cc = eg; cc < nchunks; cc += kEpiGroups) {
-        const int col0 = tc.nt * BN + cc * 16;
-        if (col0 >= ea.Cout) break;
-        conv_epilogue_chunk(ea, t_addr + cc * 16, col0, valid, n, h, w, opix, apix, my_stats, lane, stage_row, cc, r);
+      if (x32) {
+        for (int cc = 2 * eg; cc < nchunks; cc += 2 * kEpiGroups) {
+          const int col0 = tc.nt * BN + cc * 16;
+          if (col0 >= ea.Cout) break;
+          conv_epilogue_chunk2(ea, t_addr + cc * 16, col0, valid, n, h, w, opix, apix, my_stats, lane, stage_row, cc, r);
+        }
+      } else {
+        for (int cc = eg; cc < nchunks; cc += kEpiGroups) {
+          const int col0 = tc.nt * BN + cc * 16;
+          if (col0 >= ea.Cout) break;
+          conv_epilogue_chunk(ea, t_addr + cc * 16, col0, valid, n, h, w, opix, apix, my_stats, lane, stage_row, cc, r);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -328,6 +337,16 @@ static int make_a_map(CUtensorMap* m, const TView& v, int KC, int PW, int PH, in
 // is reused, and one or two operand stages given up for the staging slabs) costs more than the st.global back-pressure it
 // removes on every layer with many small tiles per CTA (48/96-channel layers at 160x160 / 80x80: +25..57 %); it wins only on
 // the 20x20 maps with <= 4 tiles per CTA (-3..-10 %, ~0.05 ms per step in total).  Kept as a knob, not as the default.
+bool conv_epi_x32(int block_n) {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("YB_EPI_X32");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  const int nchunks = block_n / 16;
+  return v != 0 && block_n % 32 == 0 && (nchunks % 6 == 0 || nchunks >= 12);
+}
+
 bool conv_tma_store_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -404,6 +423,7 @@ static int finish_plan(ConvPlan& pl, const bf16* wmat, int wrows, long wcols, co
       budget -= st_bytes;
     }
   }
+  kp.epi_x32 = (!kp.tma_store && conv_epi_x32(kp.BLOCK_N)) ? 1 : 0;
   int stages = (int)(budget / (kp.a_stage_bytes + kp.b_stage_bytes));
   stages = std::min(stages, kMaxStages);
   YB_REQUIRE(stages >= 2, "conv: tile does not fit in shared memory");

@@ -40,6 +40,7 @@ struct ConvKParams {
   CUtensorMap tmO[4];        // output maps (one per group) of the TMA-store epilogue: box [64 ch x PW x PH x PN], SWIZZLE_128B
   int32_t tma_store;         // 1: bf16 tiles leave through shared memory + cp.async.bulk.tensor stores (stage_bytes of smem)
   uint32_t stage_bytes;
+  int32_t epi_x32;           // 1: the epilogue reads TMEM 32 columns at a time (pairs of 16-column chunks per warp)
   ConvTap taps[16];
   ConvGroup groups[4];
   int32_t ngroups;
@@ -83,6 +84,7 @@ struct PatchKParams {
   CUtensorMap tmO[4];        // output maps (one per group) of the TMA-store epilogue: box [64 ch x 8 x 16 x 1], SWIZZLE_128B
   int32_t tma_store;
   uint32_t stage_bytes;
+  int32_t epi_x32;
   PTap taps[16];
   PPatch patches[4];
   ConvGroup groups[4];  // tap_begin/tap_end index PATCHES here
@@ -146,6 +148,7 @@ int conv_stats_rows(const ConvPlan& pl);  // number of per-CTA partial rows writ
 int conv_max_grid();
 // output tensor map of the TMA-store epilogue over (a parity sub-grid of) an NHWC bf16 view; false -> not encodable
 bool conv_make_out_map(CUtensorMap* m, const TView& v, int bw, int bh, int bn, int py, int px, int sy, int sx);
+bool conv_epi_x32(int block_n);  // $YB_EPI_X32: 32-column TMEM loads in the epilogue where the chunk pairs balance over the warps
 bool conv_tma_store_enabled();  // $YB_TMA_STORE=1 (default off: measured slower, see conv_igemm.cu)
 
 }  // namespace yb

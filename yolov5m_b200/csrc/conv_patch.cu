@@ -271,8 +271,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
     keep_in_reg(BN); keep_in_reg(TWl); keep_in_reg(THl);
     keep_in_reg(os_n); keep_in_reg(os_h); keep_in_reg(os_w); keep_in_reg(as_n); keep_in_reg(as_h); keep_in_reg(as_w);
     const int nchunks = BN / 16;
-    int tma_store = p.tma_store;
+    int tma_store = p.tma_store, x32 = p.epi_x32;
     keep_in_reg(tma_store);
+    keep_in_reg(x32);
+    const int units = x32 ? nchunks / 2 : nchunks;
     uint8_t* stage_row = o_stage + (size_t)r * 128;
     const bool issuer = threadIdx.x == 128;
     int it = 0, stores = 0;
@@ -323,11 +325,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
         }
         continue;
       }
-      // (tile tt, chunk cc) of the flat index idx = tt * nchunks + cc and (ty, tx) of tt advance incrementally: two
-      // runtime integer divisions per chunk were ~100 of the ~300 instructions of a chunk (ncu source page, r1)
+      // (tile tt, unit cc) of the flat index idx = tt * units + cc and (ty, tx) of tt advance incrementally: two
+      // runtime integer divisions per chunk were ~100 of the ~300 instructions of a chunk (ncu source page, r1).
+      // A unit is one 16-column chunk, or a pair of them read with one 32-column TMEM load (epi_x32).
       int tt = 0, cc = eg, ty = 0, tx = 0;
-      while (cc >= nchunks) {
-        cc -= nchunks;
+      while (cc >= units) {
+        cc -= units;
         ++tt;
         if (++tx == TWl) {
           tx = 0;
@@ -335,11 +338,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
         }
       }
       for (; tt < T; ) {
-        const int col0 = tc.nt * BN + cc * 16;
-        const int tt_c = tt, cc_c = cc, ty_c = ty, tx_c = tx;
+        const int ch0 = x32 ? 2 * cc : cc;  // first 16-column chunk of this unit
+        const int col0 = tc.nt * BN + ch0 * 16;
+        const int tt_c = tt, ty_c = ty, tx_c = tx;
         cc += kEpiGroups;
-        while (cc >= nchunks) {
-          cc -= nchunks;
+        while (cc >= units) {
+          cc -= units;
           ++tt;
           if (++tx == TWl) {
             tx = 0;
@@ -351,8 +355,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
         const bool valid = h < ea.H && w < ea.W;
         const int64_t opix = o_base + h * os_h + w * os_w;
         const int64_t apix = a_base + h * as_h + w * as_w;
-        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 256 + tt_c * BN + cc_c * 16;
-        conv_epilogue_chunk(ea, t_addr, col0, valid, tc.n, h, w, opix, apix, my_stats, lane);
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 256 + tt_c * BN + ch0 * 16;
+        if (x32)
+          conv_epilogue_chunk2(ea, t_addr, col0, valid, tc.n, h, w, opix, apix, my_stats, lane, nullptr, 0, 0);
+        else
+          conv_epilogue_chunk(ea, t_addr, col0, valid, tc.n, h, w, opix, apix, my_stats, lane);
       }
       tc_fence_before();
       __syncwarp();
@@ -525,6 +532,7 @@ int conv_patch_plan_fwd(ConvPlan& pl, const TView& in, const bf16* wp, int ks, i
   if (!st_bytes && !choose_supertile(kp, out.W, out.H, out.N, 1, ks == 31 ? 0 : halo, halo, stats_bytes)) return 1;
   kp.tma_store = st_bytes ? 1 : 0;
   kp.stage_bytes = (uint32_t)st_bytes;
+  kp.epi_x32 = (!kp.tma_store && conv_epi_x32(kp.BLOCK_N)) ? 1 : 0;
   const int SW = 8 * kp.TW, SH = 16 * kp.TH;
   int nt = 0, np = 0;
   if (ks == 1) {
@@ -625,6 +633,7 @@ int conv_patch_plan_dgrad(ConvPlan& pl, const TView& dy, const bf16* wt, int ks,
   if (!st_bytes && !choose_supertile(kp, Wg, Hg, dx.N, kp.ngroups, halo, halo, 0)) return 1;
   kp.tma_store = st_bytes ? 1 : 0;
   kp.stage_bytes = (uint32_t)st_bytes;
+  kp.epi_x32 = (!kp.tma_store && conv_epi_x32(kp.BLOCK_N)) ? 1 : 0;
   const int SW = 8 * kp.TW, SH = 16 * kp.TH;
   int nt = 0;
   if (ks == 1) {
