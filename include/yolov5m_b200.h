@@ -101,6 +101,11 @@ int yb_conv2d_wgrad(const void* x, int N, int H, int W, int Cin, int64_t x_pitch
 int yb_bn_finalize(const float* stats, int rows, int C, double count, const float* gamma, const float* beta, float eps,
                    float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked, float* scale,
                    float* shift, float* mean, float* invstd, int training, void* stream);
+/* same, for a layer whose statistics are a channel slice of a wider fused convolution (C3's c1 || c_skipped run as one GEMM,
+ * model.py:90-92): `stats` points at the slice's first channel, a partial row holds 2 * stats_ld floats */
+int yb_bn_finalize_ld(const float* stats, int rows, int C, int stats_ld, double count, const float* gamma, const float* beta,
+                      float eps, float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                      float* scale, float* shift, float* mean, float* invstd, int training, void* stream);
 int yb_bn_act_fwd(const void* y, int64_t y_pitch, int N, int H, int W, int C, const float* scale, const float* shift,
                   const void* res, int64_t res_pitch, void* out, int64_t out_pitch, void* out_up, int64_t up_pitch,
                   void* stream);

@@ -119,15 +119,17 @@ __device__ __forceinline__ V8 ldf8(const float* p) {
 // ------------------------------------------------------------------------------------------------ BN finalize
 // block = 32 channels x 32 row-lanes: the [rows][2][C] partials are summed in double (fixed order: row-lane strided, then a
 // shared-memory tree) so the result is deterministic; 128-byte coalesced reads.
-__device__ __forceinline__ void colsum2_block(const float* __restrict__ part, int rows, int C, int c, bool cvalid,
+// ld = channels per partial row (>= C: the partials may belong to a wider fused convolution, `part` then points at the
+// first channel of this layer's slice)
+__device__ __forceinline__ void colsum2_block(const float* __restrict__ part, int rows, int ld, int c, bool cvalid,
                                               double& s_out, double& q_out) {
   __shared__ double sh_s[32][33], sh_q[32][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   double s = 0.0, q = 0.0;
   if (cvalid) {
     for (int r = ry; r < rows; r += 32) {
-      s += (double)part[(size_t)r * 2 * C + c];
-      q += (double)part[(size_t)r * 2 * C + C + c];
+      s += (double)part[(size_t)r * 2 * ld + c];
+      q += (double)part[(size_t)r * 2 * ld + ld + c];
     }
   }
   sh_s[ry][cx] = s;
@@ -145,7 +147,7 @@ __device__ __forceinline__ void colsum2_block(const float* __restrict__ part, in
 }
 
 // training: mean/var from the per-CTA partial sums written by the conv epilogue.
-__global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restrict__ stats, int rows, int C, double count,
+__global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restrict__ stats, int rows, int C, int ld, double count,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                    float momentum, float* running_mean, float* running_var, long long* nbt,
                                    float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
@@ -156,7 +158,7 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restri
   const bool cvalid = c < C;
   if (blockIdx.x == 0 && threadIdx.x == 0 && training && nbt != nullptr) *nbt += 1;
   double s = 0.0, q = 0.0;
-  if (training) colsum2_block(stats, rows, C, c, cvalid, s, q);
+  if (training) colsum2_block(stats, rows, ld, c, cvalid, s, q);
   if (!cvalid || threadIdx.x >= 32) return;
   float mean, var;
   if (training) {
@@ -955,8 +957,16 @@ extern "C" {
 int yb_bn_finalize(const float* stats, int rows, int C, double count, const float* gamma, const float* beta, float eps,
                    float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked, float* scale,
                    float* shift, float* mean, float* invstd, int training, void* stream) {
+  return yb_bn_finalize_ld(stats, rows, C, C, count, gamma, beta, eps, momentum, running_mean, running_var, num_batches_tracked,
+                           scale, shift, mean, invstd, training, stream);
+}
+
+int yb_bn_finalize_ld(const float* stats, int rows, int C, int stats_ld, double count, const float* gamma, const float* beta,
+                      float eps, float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                      float* scale, float* shift, float* mean, float* invstd, int training, void* stream) {
   YB_REQUIRE(training ? (stats != nullptr && rows > 0) : (running_mean && running_var), "bn_finalize: missing inputs");
-  YB_CHECK_CUDA(launch_pdl(bn_finalize_kernel, dim3((C + 31) / 32), dim3(1024), 0, ST(stream), stats, rows, C, count, gamma, beta, eps, momentum,
+  YB_REQUIRE(stats_ld >= C, "bn_finalize: stats_ld=%d < C=%d", stats_ld, C);
+  YB_CHECK_CUDA(launch_pdl(bn_finalize_kernel, dim3((C + 31) / 32), dim3(1024), 0, ST(stream), stats, rows, C, stats_ld, count, gamma, beta, eps, momentum,
                                                                running_mean, running_var,
                                                                reinterpret_cast<long long*>(num_batches_tracked), scale,
                                                                shift, mean, invstd, training));

@@ -285,7 +285,33 @@ class _Engine:
         return t
 
     # -- forward construction
-    def cbl(self, mod, xin, out, res=None, up=None):
+    def pair_setup(self, c3mod, xin):
+        """C3's c1 and c_skipped (model.py:90-92) read the same input: ONE 1x1 GEMM with N = 2 * c_ (their weights are
+        adjacent in the flat buffer).  Returns the shared state the two cbl() calls use, or None (parity mode / no pair)."""
+        net, L = self.net, self.L
+        if self.parity or c3mod not in net._pairs or os.environ.get("YB_C3_FUSE", "1") == "0":
+            return None
+        ra, rb, wt2 = net._pairs[c3mod]
+        C, N, H, W = ra.cout, xin.N, xin.H, xin.W
+        pr = {"C": C, "wt2": wt2, "ra": ra, "rb": rb, "flops": 2.0 * xin.npix * 2 * C * ra.cin, "xin": xin}
+        w_ptr = net._wfwd.data_ptr() + 2 * ra.w_off
+        if self.train:
+            pr["y"] = self.buf(N, H, W, 2 * C, grad=False)
+            pr["stats"] = self._stat(2 * self.max_rows * 2 * C)
+            rows = ctypes.c_int(0)
+            pr["plan"] = _lib.checkp(L.yb_conv_fwd_plan(xin.ptr, N, H, W, xin.C, xin.pitch, w_ptr, 2 * C, 1, 1, pr["y"].t.data_ptr(),
+                                                        2 * C, 0, None, None, 0, None, 0, pr["stats"].data_ptr(),
+                                                        ctypes.byref(rows), 3, 85))
+            pr["nrows"] = rows.value
+            pr["dy"] = torch.empty(xin.npix * 2 * C, device=self.dev, dtype=torch.bfloat16)
+            self.nbytes += pr["dy"].numel() * 2
+        else:
+            pr["scale"], pr["shift"] = self._stat(2 * C), self._stat(2 * C)
+        if pr.get("plan") is not None:
+            self.plans.append(pr["plan"])
+        return pr
+
+    def cbl(self, mod, xin, out, res=None, up=None, pair=None, half=0):
         net, L = self.net, self.L
         r = net._rec_of[mod.cbl[0]]
         Ho, Wo = xin.H // (1 if r.is_stem else r.stride), xin.W // (1 if r.is_stem else r.stride)
@@ -293,6 +319,8 @@ class _Engine:
         C = r.cout
         flops = 2.0 * xin.N * Ho * Wo * C * r.k * r.k * r.cin  # the reference conv (stem: 6x6 over 3 channels)
         self.conv_flops["fwd"] += flops
+        if pair is not None:
+            return self._cbl_pair(r, xin, out, pair, half, flops)
         scale, shift = self._stat(C), self._stat(C)
         w_ptr = net._wstem.data_ptr() if r.is_stem else net._wfwd.data_ptr() + 2 * r.w_off
         gam, bet = net._pflat.data_ptr() + 4 * r.g_off, net._pflat.data_ptr() + 4 * r.b_off
@@ -342,6 +370,51 @@ class _Engine:
         self._dy_elems = max(self._dy_elems, y.npix * C)
         self.tape.append(("cbl", r, xin, out, y, res, up, ptrs, flops))
 
+    def _cbl_pair(self, r, xin, out, pr, half, flops):
+        """one half (0 = c1, 1 = c_skipped) of a fused C3 input pair; half 0 launches the shared GEMM"""
+        net, L, C = self.net, self.L, pr["C"]
+        gam, bet = net._pflat.data_ptr() + 4 * r.g_off, net._pflat.data_ptr() + 4 * r.b_off
+        rm, rv, nbt = r.rm.data_ptr(), r.rv.data_ptr(), r.nbt.data_ptr()
+        if not self.train:
+            # eval: both halves leave the ONE conv epilogue (folded BN + SiLU) straight into the concat buffer: c1's output
+            # occupies the slot that the last bottleneck overwrites later (it is dead by then: depth >= 2)
+            sp, hp = pr["scale"].data_ptr() + 4 * half * C, pr["shift"].data_ptr() + 4 * half * C
+            if half == 0:
+                assert out.c0 == 0 and out.pitch == 2 * C, "fused C3 pair: c1 must write slot 0 of the concat buffer"
+                plan = _lib.checkp(L.yb_conv_fwd_plan(xin.ptr, xin.N, xin.H, xin.W, xin.C, xin.pitch,
+                                                      net._wfwd.data_ptr() + 2 * pr["ra"].w_off, 2 * C, 1, 1, out.ptr, out.pitch, 0,
+                                                      pr["scale"].data_ptr(), pr["shift"].data_ptr(), 1, None, 0, None, None,
+                                                      3, 85))
+                self.plans.append(plan)
+                rb = pr["rb"]
+                gb, bb = net._pflat.data_ptr() + 4 * rb.g_off, net._pflat.data_ptr() + 4 * rb.b_off
+                sp1, hp1 = pr["scale"].data_ptr() + 4 * C, pr["shift"].data_ptr() + 4 * C
+                pflops = pr["flops"]
+
+                def op(st):
+                    _lib.check(L.yb_bn_finalize(None, 0, C, 1.0, gam, bet, BN_EPS, BN_MOMENTUM, rm, rv, None, sp, hp, None, None, 0, st))
+                    _lib.check(L.yb_bn_finalize(None, 0, C, 1.0, gb, bb, BN_EPS, BN_MOMENTUM, rb.rm.data_ptr(), rb.rv.data_ptr(),
+                                                None, sp1, hp1, None, None, 0, st))
+                    self._conv(plan, st, pflops, "fwd")
+                self.fwd_ops.append(op)
+            return
+        scale, shift, mean, invstd = self._stat(C), self._stat(C), self._stat(C), self._stat(C)
+        y = pr["y"].v(half * C, C)
+        stats_ptr = pr["stats"].data_ptr() + 4 * half * C
+        ptrs = (stats_ptr, scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), invstd.data_ptr())
+        nrows, count, plan, pflops, bn = pr["nrows"], float(y.npix), pr["plan"], pr["flops"], r.bn
+        ew_bytes = 4.0 * y.npix * C
+
+        def op(st):
+            if half == 0:
+                self._conv(plan, st, pflops, "fwd")
+            _lib.check(L.yb_bn_finalize_ld(ptrs[0], nrows, C, 2 * C, count, gam, bet, bn.eps, bn.momentum, rm, rv, nbt, ptrs[1],
+                                           ptrs[2], ptrs[3], ptrs[4], 1, st))
+            self._ew("bn_fwd", ew_bytes, L.yb_bn_act_fwd, y.ptr, y.pitch, y.N, y.H, y.W, C, ptrs[1], ptrs[2], None, 0, out.ptr,
+                     out.pitch, None, 0, st)
+        self.fwd_ops.append(op)
+        self.tape.append(("cbl", r, xin, out, y, None, None, ptrs, flops, (pr, half)))
+
     # -- parity mode (fp32 activations, six bf16-split passes of the same tcgen05 kernels per conv; csrc/parity.cu)
     def _parity_conv_plans(self, xin, r, k, s, out_ptr, out_pitch, head=False, bias_ptr=None):
         net, L = self.net, self.L
@@ -389,8 +462,10 @@ class _Engine:
         c_ = mod.hidden
         N, H, W = xin.N, xin.H, xin.W
         cat = self.buf(N, H, W, 2 * c_)
-        a = self.buf(N, H, W, c_).v()
-        self.cbl(mod.c1, xin, a)
+        pair = self.pair_setup(mod, xin) if mod.depth >= 2 else None
+        # eval + fused pair: c1's output lives in slot 0 of the concat buffer until the last bottleneck overwrites it
+        a = cat.v(0, c_) if (pair is not None and not self.train) else self.buf(N, H, W, c_).v()
+        self.cbl(mod.c1, xin, a, pair=pair, half=0)
         for j in range(mod.depth):
             blk = mod.seq[j]
             first, second = (blk.c1, blk.c2) if mod.is_backbone else (blk[0], blk[1])
@@ -399,7 +474,7 @@ class _Engine:
             dst = cat.v(0, c_) if j == mod.depth - 1 else self.buf(N, H, W, c_).v()
             self.cbl(second, h, dst, res=a if mod.is_backbone else None)
             a = dst
-        self.cbl(mod.c_skipped, xin, cat.v(c_, c_))
+        self.cbl(mod.c_skipped, xin, cat.v(c_, c_), pair=pair, half=1)
         self.cbl(mod.c_out, cat.v(), out)
 
     def sppf(self, mod, xin, out):
@@ -630,6 +705,50 @@ class _Engine:
                 pool_bwd = L.yb_p32_maxpool5_bwd if self.parity else L.yb_maxpool5_bwd
                 self.bwd_ops.append(lambda st, g, src=src, dst=dst, am=am, acc=acc, pool_bwd=pool_bwd: _lib.check(
                     pool_bwd(dst.gptr, dst.pitch, am.data_ptr(), src.N, src.H, src.W, src.C, src.gptr, src.pitch, acc, st)))
+            elif len(rec) == 10:
+                # one half of a fused C3 input pair (c1 || c_skipped as ONE GEMM): its BN/SiLU backward writes its half of the
+                # pair's dy buffer; the half that comes LAST in the backward order (c1) then runs the ONE dgrad (K = 2 c_) and
+                # the ONE wgrad (N = 2 c_, whose output is the two adjacent weight-gradient slices of the flat bucket)
+                _, r, xin, out, y, _res, _up, ptrs, flops, (pr, half) = rec
+                self.conv_flops["wgrad"] += flops
+                self.conv_flops["dgrad"] += flops
+                C, npix = r.cout, y.npix
+                dy2 = pr["dy"].data_ptr()
+                self._flush_pending(out)
+                assert self._contrib_state(out), f"{r.name}: output gradient never produced"
+                dplan = wplan = None
+                if half == 0:
+                    src = self._take_pending_exact(xin)
+                    written = self._contrib_state(xin)
+                    if src is not None and written:
+                        self.bwd_ops.append(lambda st, g, src=src, xin=xin: _lib.check(
+                            L.yb_add_into(src.gptr, src.pitch, xin.gptr, xin.pitch, xin.npix, xin.C, 1, st)))
+                        src = None
+                    addp, addl = (src.gptr, src.pitch) if src is not None else ((xin.gptr, xin.pitch) if written else (None, 0))
+                    dplan = _lib.checkp(L.yb_conv_dgrad_plan(dy2, xin.N, xin.H, xin.W, 2 * C, 2 * C,
+                                                             net._wdg.data_ptr() + 2 * pr["wt2"], xin.C, 1, 1, xin.gptr, xin.pitch,
+                                                             addp, addl, 0))
+                    wplan = _lib.checkp(L.yb_conv_wgrad_plan(xin.ptr, xin.N, xin.H, xin.W, xin.C, xin.pitch, dy2, 2 * C, 2 * C, 1, 1,
+                                                             ws, wsn, 0))
+                    self.plans += [dplan, wplan]
+                    xin.buf.gw[xin.c0:xin.c0 + xin.C] = True
+                rows = ctypes.c_int(0)
+                count, pflops, w0 = float(npix), pr["flops"], pr["ra"].w_off
+
+                def op(st, g, r=r, out=out, y=y, ptrs=ptrs, C=C, npix=npix, wplan=wplan, dplan=dplan, rows=rows, count=count,
+                       pflops=pflops, dy2=dy2, half=half, w0=w0):
+                    self._ew("bn_bwd_reduce", 4.0 * npix * C, L.yb_bn_act_bwd_reduce, out.gptr, out.pitch, y.ptr, y.pitch, npix, C,
+                             ptrs[1], ptrs[2], ptrs[3], ptrs[4], redp, ctypes.byref(rows), st)
+                    _lib.check(L.yb_bn_bwd_finalize(redp, rows.value, C, count, g + 4 * r.g_off, g + 4 * r.b_off, coefp, 0, st))
+                    self._ew("bn_bwd_apply", 6.0 * npix * C, L.yb_bn_act_bwd_apply, out.gptr, out.pitch, y.ptr, y.pitch, npix, C,
+                             ptrs[1], ptrs[2], ptrs[3], ptrs[4], coefp, dy2 + 2 * half * C, 2 * C, st)
+                    if dplan is not None:
+                        self._conv(dplan, st, pflops, "dgrad")
+                        self._wgrad(wplan, st, pflops, g + 4 * w0, 2 * C, None, 0)
+                writes = [(r.g_off, C), (r.b_off, C)]
+                if half == 0:  # the fused wgrad writes both (adjacent) weight-gradient slices
+                    writes += [(pr["ra"].w_off, C * r.cin), (pr["rb"].w_off, C * r.cin)]
+                self._add_bwd_op(op, writes)
             else:
                 _, r, xin, out, y, res, up, ptrs, flops = rec
                 self.conv_flops["wgrad"] += flops
@@ -861,7 +980,18 @@ class YOLOV5m(nn.Module):
         recs, rec_of = [], {}
         off = 0
         offs = {}
-        for p in params:
+        # storage order = parameter order, except that a C3's c_skipped conv weight sits right behind its c1 conv weight:
+        # the two 1x1 convs read the same input (model.py:90-92) and run as ONE GEMM over the [2c_][Cin] matrix they then form
+        # (forward operand, weight gradient and Adam state all become contiguous; state_dict() order is unaffected)
+        order = list(params)
+        for m in self.modules():
+            if isinstance(m, C3):
+                a, b = m.c1.cbl[0].weight, m.c_skipped.cbl[0].weight
+                ib = next(i for i, q in enumerate(order) if q is b)
+                order.pop(ib)
+                ia = next(i for i, q in enumerate(order) if q is a)
+                order.insert(ia + 1, b)
+        for p in order:
             offs[id(p)] = off
             off += (p.numel() + 3) // 4 * 4  # 16-byte aligned slices
         flat = torch.zeros(off, device=dev, dtype=torch.float32)
@@ -905,6 +1035,14 @@ class YOLOV5m(nn.Module):
                 wt_off += r.cin * r.k * r.k * r.cout_pad
             recs.append(r)
             rec_of[r.conv] = r
+        # fused c1 || c_skipped pairs: one more dgrad operand [Cin][2c_] per C3
+        self._pairs = {}
+        for m in self.modules():
+            if isinstance(m, C3):
+                ra, rb = rec_of[m.c1.cbl[0]], rec_of[m.c_skipped.cbl[0]]
+                if rb.w_off == ra.w_off + ra.cout * ra.cin and (ra.cout * ra.cin) % 4 == 0:
+                    self._pairs[m] = (ra, rb, wt_off)
+                    wt_off += ra.cin * 2 * ra.cout
         self._recs, self._rec_of, self._wdg_elems = recs, rec_of, wt_off
         self._engines = {}
         self._packed_sig = None
@@ -924,6 +1062,10 @@ class YOLOV5m(nn.Module):
                 continue
             n = r.cin * r.k * r.k * r.cout_pad
             rows.append([r.w_off, r.wt_off, r.cout, r.k * r.k, r.cin, r.cout_pad, cum, cum + n])
+            cum += n
+        for (ra, rb, wt2) in self._pairs.values():
+            n = ra.cin * 2 * ra.cout
+            rows.append([ra.w_off, wt2, 2 * ra.cout, 1, ra.cin, 2 * ra.cout, cum, cum + n])
             cum += n
         self._dg_table = torch.tensor(rows, dtype=torch.int64, device=dev)
         # stem wgrad: packed 3x3/16ch gradient index -> offset inside the [Cout][6][6][3] master slice
