@@ -24,6 +24,7 @@ __device__ __forceinline__ void keep_in_reg(FDiv& f) {
 }
 
 struct EpiArgs {
+  float* head_scratch;  // OUT_HEAD_F32: shared-memory transpose scratch, 12 epilogue warps x [32][17] floats (or null)
   float* stats;
   const float* scale;
   const float* shift;
@@ -34,6 +35,7 @@ struct EpiArgs {
 template <class P>
 __device__ __forceinline__ EpiArgs load_epi_args(const P& p) {
   EpiArgs e;
+  e.head_scratch = nullptr;
   e.stats = p.stats; e.scale = p.scale; e.shift = p.shift; e.addend = p.addend; e.out = p.out;
   e.act = p.act; e.out_kind = p.out_kind; e.Cout = p.Cout; e.H = p.H; e.W = p.W; e.head_na = p.head_na; e.head_no = p.head_no;
   keep_in_reg(e.stats); keep_in_reg(e.scale); keep_in_reg(e.shift); keep_in_reg(e.addend); keep_in_reg(e.out);
@@ -186,6 +188,8 @@ __device__ __forceinline__ void conv_epilogue_process(const EpiArgs& p, const ui
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      } else if (p.out_kind == OUT_HEAD_F32 && p.head_scratch != nullptr) {
+        // handled below (warp-cooperative transposed store; needs every lane, valid or not)
       } else {  // OUT_HEAD_F32 / OUT_HEAD_F32_ACC
         float* ob = reinterpret_cast<float*>(p.out);
         const int64_t hw = (int64_t)p.H * p.W;
@@ -199,6 +203,30 @@ __device__ __forceinline__ void conv_epilogue_process(const EpiArgs& p, const ui
             *dst = p.out_kind == OUT_HEAD_F32_ACC ? *dst + v[j] : v[j];
           }
         }
+      }
+    }
+    if (p.out_kind == OUT_HEAD_F32 && p.head_scratch != nullptr) {
+      // Head layout (B, na, H, W, no) fp32 (model.py:173): a pixel's `no` floats are contiguous, pixels 4 * no bytes apart.
+      // One thread = one pixel: a direct store instruction would touch 32 sectors for 128 bytes (at bs=128, 1280x1280 the
+      // P3 head took 7.1 ms against a 0.7 ms HBM floor).  Transpose the 32 x 16 chunk through a per-warp scratch instead:
+      // each instruction then writes two pixels x 16 consecutive floats (two 64-byte runs).
+      float* sc = p.head_scratch + (size_t)((threadIdx.x >> 5) - 4) * (32 * 17);
+      const int64_t hw = (int64_t)p.H * p.W;
+      const int64_t pixbase = valid ? (((int64_t)n * p.head_na) * hw + (int64_t)h * p.W + w) * p.head_no : -1;
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) sc[lane * 17 + j] = v[j];
+      __syncwarp();
+      const int cj = lane & 15, col = col0 + cj;
+      const int a = col / p.head_no, o = col - a * p.head_no;
+      const int64_t coff = (int64_t)a * hw * p.head_no + o;
+      float* ob = reinterpret_cast<float*>(p.out);
+#pragma unroll
+      for (int st = 0; st < 16; ++st) {
+        const int r = 2 * st + (lane >> 4);
+        const int64_t pb = __shfl_sync(0xffffffffu, pixbase, r);
+        const float val = sc[r * 17 + cj];
+        if (pb >= 0 && col < p.Cout) ob[pb + coff] = val;
       }
     }
 }

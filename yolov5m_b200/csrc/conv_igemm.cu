@@ -197,7 +197,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     const int pw = r % p.PW;
     float* my_stats = s_stats + (size_t)q * 2 * p.Cout;
     // register copies of everything the per-tile loop reads (see keep_in_reg)
-    const EpiArgs ea = load_epi_args(p);
+    EpiArgs ea = load_epi_args(p);
+    if (p.out_kind == OUT_HEAD_F32) ea.head_scratch = s_stats;  // the head has no BN statistics: the region is the transpose scratch
     const TileDec td = load_tile_dec(p);
     int PW = p.PW, PH = p.PH, PN = p.PN, NB = p.NB, BN = p.BLOCK_N;
     int64_t t_on = p.PN * p.os_n, t_oh = p.PH * p.os_h, t_ow = p.PW * p.os_w;  // element strides between tiles
@@ -403,7 +404,9 @@ static int finish_plan(ConvPlan& pl, const bf16* wmat, int wrows, long wcols, co
   YB_REQUIRE(ep.out_kind == OUT_HEAD_F32 || ep.out_kind == OUT_HEAD_F32_ACC || wrows % 16 == 0,
              "conv: Cout=%d must be a multiple of 16", wrows);
   YB_REQUIRE(ep.scale == nullptr || ep.shift != nullptr, "conv: scale without shift");
-  const size_t stats_bytes = ep.stats ? (size_t)4 * 2 * wrows * sizeof(float) : 0;
+  YB_REQUIRE(!(ep.stats && ep.out_kind == OUT_HEAD_F32), "conv: head output with BN statistics");
+  const size_t stats_bytes = ep.stats ? (size_t)4 * 2 * wrows * sizeof(float)
+                                      : (ep.out_kind == OUT_HEAD_F32 ? (size_t)kEpiGroups * 4 * 32 * 17 * sizeof(float) : 0);
   size_t budget = 227 * 1024 - 1024 /*align slack*/ - kBarRegion - stats_bytes;
   // TMA-store epilogue (bf16 NHWC outputs): staging = one [128 px][128 B] slab per 64 output channels of the tile, taken
   // from the operand ring; kept only if at least three pipeline stages remain
