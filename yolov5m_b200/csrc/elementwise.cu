@@ -84,6 +84,18 @@ __device__ __forceinline__ V8 cvt8(const uint4& r) {
   return o;
 }
 __device__ __forceinline__ uint4 ldraw(const bf16* p) { return *reinterpret_cast<const uint4*>(p); }
+// streaming read of a tensor the kernel never writes: read-only path, no L1 allocation, 256-byte L2 prefetch granule
+__device__ __forceinline__ uint4 ldstream(const bf16* p) {
+#ifdef YB_EW_PLAIN_LOADS
+  return *reinterpret_cast<const uint4*>(p);
+#else
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+#endif
+}
 // SiLU / its derivative through ONE special-function op per element: sigmoid(z) = 0.5 * tanh(z / 2) + 0.5 with
 // tanh.approx.f32 (max relative error 2^-11, below the bf16 rounding of every value these passes store).  exp + reciprocal
 // would be two MUFU ops per element, and at 16 MUFU results / clock / SM that -- not HBM -- bounded these passes.
@@ -231,18 +243,18 @@ __global__ void __launch_bounds__(kEwThreads) bn_act_fwd_kernel(const bf16* __re
     for (; pix + (kEwUnroll - 1) * pstep < npix; pix += kEwUnroll * pstep) {
       uint4 yr[kEwUnroll], rr[kEwUnroll];
 #pragma unroll
-      for (int u = 0; u < kEwUnroll; ++u) yr[u] = ldraw(y + (pix + u * pstep) * y_pitch + c);
+      for (int u = 0; u < kEwUnroll; ++u) yr[u] = ldstream(y + (pix + u * pstep) * y_pitch + c);
       if (res != nullptr) {
 #pragma unroll
-        for (int u = 0; u < kEwUnroll; ++u) rr[u] = ldraw(res + (pix + u * pstep) * res_pitch + c);
+        for (int u = 0; u < kEwUnroll; ++u) rr[u] = ldstream(res + (pix + u * pstep) * res_pitch + c);
       }
 #pragma unroll
       for (int u = 0; u < kEwUnroll; ++u) finish(pix + u * pstep, c, cvt8(yr[u]), sc, sh, res != nullptr ? &rr[u] : nullptr);
     }
     for (; pix < npix; pix += pstep) {
-      const uint4 yr = ldraw(y + pix * y_pitch + c);
+      const uint4 yr = ldstream(y + pix * y_pitch + c);
       uint4 rr = make_uint4(0, 0, 0, 0);
-      if (res != nullptr) rr = ldraw(res + pix * res_pitch + c);
+      if (res != nullptr) rr = ldstream(res + pix * res_pitch + c);
       finish(pix, c, cvt8(yr), sc, sh, res != nullptr ? &rr : nullptr);
     }
   } else {
@@ -250,9 +262,9 @@ __global__ void __launch_bounds__(kEwThreads) bn_act_fwd_kernel(const bf16* __re
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
       const long pix = i / cv;
       const unsigned c = (unsigned)(i - pix * cv) << 3;
-      const uint4 yr = ldraw(y + pix * y_pitch + c);
+      const uint4 yr = ldstream(y + pix * y_pitch + c);
       uint4 rr = make_uint4(0, 0, 0, 0);
-      if (res != nullptr) rr = ldraw(res + pix * res_pitch + c);
+      if (res != nullptr) rr = ldstream(res + pix * res_pitch + c);
       finish(pix, c, cvt8(yr), half8(ldf8(scale + c)), half8(ldf8(shift + c)), res != nullptr ? &rr : nullptr);
     }
   }
@@ -372,18 +384,18 @@ __global__ void __launch_bounds__(256, kReduceOcc) bn_act_bwd_reduce_kernel(cons
     for (; p + (kEwUnroll - 1) * (long)rows_pb < p1; p += kEwUnroll * (long)rows_pb) {
       uint4 gr[kEwUnroll], yr[kEwUnroll];
 #pragma unroll
-      for (int u = 0; u < kEwUnroll; ++u) gr[u] = ldraw(da + (p + u * (long)rows_pb) * da_pitch + c);
+      for (int u = 0; u < kEwUnroll; ++u) gr[u] = ldstream(da + (p + u * (long)rows_pb) * da_pitch + c);
       if (mode == 0) {
 #pragma unroll
-        for (int u = 0; u < kEwUnroll; ++u) yr[u] = ldraw(y + (p + u * (long)rows_pb) * y_pitch + c);
+        for (int u = 0; u < kEwUnroll; ++u) yr[u] = ldstream(y + (p + u * (long)rows_pb) * y_pitch + c);
       }
 #pragma unroll
       for (int u = 0; u < kEwUnroll; ++u) accum(gr[u], yr[u]);
     }
     for (; p < p1; p += rows_pb) {
-      const uint4 gr = ldraw(da + p * da_pitch + c);
+      const uint4 gr = ldstream(da + p * da_pitch + c);
       uint4 yr = make_uint4(0, 0, 0, 0);
-      if (mode == 0) yr = ldraw(y + p * y_pitch + c);
+      if (mode == 0) yr = ldstream(y + p * y_pitch + c);
       accum(gr, yr);
     }
     if (mode == 0) {  // sum dz = s1 / 2;  sum dz * xhat = xa * (s2 / 2) + xb * (s1 / 2),  xa = invstd, xb = -mean * invstd
@@ -476,19 +488,19 @@ __global__ void __launch_bounds__(kEwThreads, 5) bn_act_bwd_apply_kernel(const b
       uint4 gr[kEwUnroll], yr[kEwUnroll];
 #pragma unroll
       for (int u = 0; u < kEwUnroll; ++u) {
-        gr[u] = ldraw(da + (pix + u * pstep) * da_pitch + c);
-        yr[u] = ldraw(y + (pix + u * pstep) * y_pitch + c);
+        gr[u] = ldstream(da + (pix + u * pstep) * da_pitch + c);
+        yr[u] = ldstream(y + (pix + u * pstep) * y_pitch + c);
       }
 #pragma unroll
       for (int u = 0; u < kEwUnroll; ++u) finish(pix + u * pstep, c, gr[u], yr[u], q);
     }
-    for (; pix < npix; pix += pstep) finish(pix, c, ldraw(da + pix * da_pitch + c), ldraw(y + pix * y_pitch + c), q);
+    for (; pix < npix; pix += pstep) finish(pix, c, ldstream(da + pix * da_pitch + c), ldstream(y + pix * y_pitch + c), q);
   } else {
     const long total = npix * cv;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
       const long pix = i / cv;
       const unsigned c = (unsigned)(i - pix * cv) << 3;
-      finish(pix, c, ldraw(da + pix * da_pitch + c), ldraw(y + pix * y_pitch + c), load_par(c));
+      finish(pix, c, ldstream(da + pix * da_pitch + c), ldstream(y + pix * y_pitch + c), load_par(c));
     }
   }
 }
