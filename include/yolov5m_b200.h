@@ -30,6 +30,9 @@ int yb_conv_max_partials(void);
 /* ---- Conv2d forward (model.py:16 CBL conv; model.py:162 head conv) ----------------
  * y[n,ho,wo,co] = epilogue( sum_{kh,kw,ci} x[n, ho*s+kh-p, wo*s+kw-p, ci] * w[co,(kh*ks+kw)*Cin+ci] )
  * ks in {1,3}, p = ks/2, s in {1,2}; ks = 31 means a 3x1 kernel (three vertical taps, stride 1, w_packed [Cout][3*Cin]).
+ * ks = 31 with x_pitch < Cin (the stem: Cin = 48, x_pitch = 16): x is the row-padded 16-channel staging (N,H,W+2,16) of
+ * yb_prep_input and the 48 "channels" of pixel w are the 48 contiguous values that start at padded column w (an
+ * overlapping-window tensor-map view; the same convention holds for yb_conv_wgrad_plan).
  * w_packed: bf16 [Cout][ks*ks*Cin].
  * epilogue: v = acc; if scale: v = v*scale[co]+shift[co]; elif shift: v += shift[co];
  *           if act: v = SiLU(v); if addend: v += addend[n,ho,wo,co]; store.
@@ -144,9 +147,11 @@ int yb_sppf_pool3_fwd(const void* x, int64_t x_pitch, int N, int H, int W, int C
 int yb_sppf_pool3_bwd(const void* g1, const void* g2, const void* g3, int64_t g_pitch, const uint8_t* am1, const uint8_t* am2,
                       const uint8_t* am3, int N, int H, int W, int C, void* g0, int64_t g0_pitch, int accumulate, void* stream);
 /* x (N,3,H,W) NCHW, dtype 0 = float32 in [0,1], 1 = uint8 (divided by 255, training_utils.py:98)
- * -> out (N,H/2,W/2,48) bf16: space-to-depth (12 -> 16 channels: (r*2+s)*3+c = x[c][2h+r][2w+s]) with the three horizontal
- * taps gathered (channel kw*16+j = s2d pixel w+kw-1, zero outside), so that the 6x6/s2 stem (model.py:184) becomes a
- * 3x1 convolution (ks code 31 of yb_conv_fwd_plan / yb_conv_wgrad_plan) with weights [Cout][3][48] = yb_repack_stem */
+ * -> out (N,H/2,W/2+2,16) bf16: space-to-depth (12 -> 16 channels: (r*2+s)*3+c = x[c][2h+r][2w+s]) at column w+1 of rows
+ * that carry one zero pixel on either side.  The three horizontal taps of the stem are then the 48 contiguous values
+ * starting at padded column w (channel kw*16+j = s2d pixel w+kw-1, zero outside), so the 6x6/s2 stem (model.py:184) is a
+ * 3x1 convolution (ks code 31 of yb_conv_fwd_plan / yb_conv_wgrad_plan, Cin = 48, x_pitch = 16) with weights
+ * [Cout][3][48] = yb_repack_stem, and the 48-channel tap-gathered tensor is never written. */
 int yb_prep_input(const void* x, int dtype, int N, int H, int W, void* out, void* stream);
 /* same staging, but the (N,3,Hs,Ws) image is first resampled to (H,W) like the reference's multi_scale()
  * (utils/training_utils.py:11-28: F.interpolate(img, size=(H,W), mode="bilinear", align_corners=False) of the float image);

@@ -219,3 +219,26 @@ def test_conv_fwd_3x1(N, H, W, Cin, Cout, patch):
         assert rel(st[1].cpu() / m, (ref * ref).mean((0, 2, 3))) < 1e-3
     finally:
         L.yb_set_conv_patch_mode(0)
+
+
+@pytest.mark.parametrize("N,H,W,Cout,patch", [(2, 32, 32, 48, 0), (2, 32, 32, 48, 2), (1, 24, 20, 96, 0), (2, 64, 40, 48, 0)])
+def test_conv_fwd_3x1_stem_view(N, H, W, Cout, patch):
+    """ks 31 with x_pitch (16) < Cin (48): the row-padded 16-channel staging of yb_prep_input read through an
+    overlapping-window tensor map -- pixel w's channels are padded columns w, w+1, w+2 (include/yolov5m_b200.h)."""
+    L = _lib.lib()
+    L.yb_set_conv_patch_mode(patch)
+    try:
+        g = torch.Generator().manual_seed(23)
+        xs = torch.zeros(N, H, W + 2, 16)
+        xs[:, :, 1:-1] = torch.randn(N, H, W, 16, generator=g)
+        xs = xs.to(torch.bfloat16)
+        view = xs.flatten(2).unfold(2, 48, 16)                    # (N, H, W, 48), pixel stride 16
+        assert view.shape == (N, H, W, 48) and view.stride(2) == 16
+        w = (torch.randn(Cout, 48, 3, 1, generator=g) / 12.0).to(torch.bfloat16)
+        ref = F.conv2d(view.float().permute(0, 3, 1, 2), w.float(), None, 1, (1, 0))
+        y, _, st = conv_fwd(xs.cuda().flatten(2).unfold(2, 48, 16), pack_fwd(w.float()).cuda(), 31, 1, Cout, stats=True)
+        assert rel(y.float().cpu().permute(0, 3, 1, 2), ref) < TOL
+        m = ref.numel() // Cout
+        assert rel(st[1].cpu() / m, (ref * ref).mean((0, 2, 3))) < 1e-3
+    finally:
+        L.yb_set_conv_patch_mode(0)

@@ -206,7 +206,7 @@ def test_upsample_add_prep_pack():
         x = torch.rand(2, 3, 8, 12, generator=g)
         if dt == torch.uint8:
             x = (x * 255).to(torch.uint8)
-        out = torch.full((2, 4, 6, 48), 9.0, device="cuda", dtype=torch.bfloat16)
+        out = torch.full((2, 4, 6 + 2, 16), 9.0, device="cuda", dtype=torch.bfloat16)
         _lib.check(L.yb_prep_input(_lib.ptr(x.cuda()), 0 if dt == torch.float32 else 1, 2, 8, 12, _lib.ptr(out), _lib.stream()))
         xf = x.float() / 255 if dt == torch.uint8 else x
         s2d = torch.zeros(2, 4, 6, 16)
@@ -214,11 +214,15 @@ def test_upsample_add_prep_pack():
             for s_ in range(2):
                 for c in range(3):
                     s2d[..., (r * 2 + s_) * 3 + c] = xf[:, c, r::2, s_::2]
-        want = torch.zeros(2, 4, 6, 48)            # channel kw*16+j = s2d[w + kw - 1][j], zero outside the image
-        want[..., 16:32] = s2d
-        want[:, :, 1:, 0:16] = s2d[:, :, :-1]
-        want[:, :, :-1, 32:48] = s2d[:, :, 1:]
+        want = torch.zeros(2, 4, 6 + 2, 16)        # s2d pixel w at padded column w + 1, a zero pixel on either side
+        want[:, :, 1:-1] = s2d
         assert torch.equal(out.float().cpu(), want.to(torch.bfloat16).float())
+        # the stem reads it as 48 contiguous values per pixel: channel kw*16+j = s2d[w + kw - 1][j], zero outside
+        view = out.flatten(2).unfold(2, 48, 16)
+        assert view.shape == (2, 4, 6, 48)
+        assert torch.equal(view[..., 16:32].float().cpu(), s2d.to(torch.bfloat16).float())
+        assert torch.equal(view[:, :, 1:, 0:16].float().cpu(), s2d[:, :, :-1].to(torch.bfloat16).float())
+        assert float(view[:, :, 0, 0:16].abs().max()) == 0 and float(view[:, :, -1, 32:48].abs().max()) == 0
     # dense head gradient repack
     gh = torch.randn(2, 3, 4, 6, 85, generator=g)
     dy = torch.ones(2, 4, 6, 256, device="cuda", dtype=torch.bfloat16)
@@ -250,7 +254,7 @@ def test_prep_input_resized_matches_interpolate(dt, src, dst):
     xf = x.float() / 255 if dt == torch.uint8 else x
     want_img = F.interpolate(xf, size=dst, mode="bilinear", align_corners=False).contiguous()
     H, W = dst
-    got = torch.empty(2, H // 2, W // 2, 48, device="cuda", dtype=torch.bfloat16)
+    got = torch.empty(2, H // 2, W // 2 + 2, 16, device="cuda", dtype=torch.bfloat16)
     want = torch.empty_like(got)
     _lib.check(L.yb_prep_input_resized(_lib.ptr(x.cuda()), 0 if dt == torch.float32 else 1, 2, src[0], src[1], H, W,
                                        _lib.ptr(got), _lib.stream()))
@@ -259,7 +263,7 @@ def test_prep_input_resized_matches_interpolate(dt, src, dst):
     assert (a - b).abs().max().item() <= 2 ** -8          # values are in [0, 1]: one bf16 ulp at most
     assert (a != b).float().mean().item() < 0.02           # and almost all are bit-identical
     # identity resize == plain staging, bit for bit
-    same = torch.empty(2, src[0] // 2 * 2 // 2, src[1] // 2 * 2 // 2, 48, device="cuda", dtype=torch.bfloat16)
+    same = torch.empty(2, src[0] // 2 * 2 // 2, src[1] // 2 * 2 // 2 + 2, 16, device="cuda", dtype=torch.bfloat16)
     if src[0] % 2 == 0 and src[1] % 2 == 0:
         ref = torch.empty_like(same)
         _lib.check(L.yb_prep_input_resized(_lib.ptr(x.cuda()), 0 if dt == torch.float32 else 1, 2, src[0], src[1], src[0],

@@ -118,3 +118,24 @@ def test_conv_wgrad_3x1():
                                  _lib.ptr(ws), _lib.c_i64(ws.numel()), 0, _lib.ptr(dw), Cout, None, 0, _lib.stream()))
     torch.cuda.synchronize()
     assert rel(dw.cpu().view(Cout, 3, 1, Cin).permute(0, 3, 1, 2), ref) < TOL
+
+
+def test_conv_wgrad_3x1_stem_view():
+    """ks 31 with x_pitch (16) < Cin (48): x is the row-padded 16-channel staging read as an overlapping window."""
+    N, H, W, Cout = 2, 32, 40, 48
+    g = torch.Generator().manual_seed(10)
+    xs = torch.zeros(N, H, W + 2, 16)
+    xs[:, :, 1:-1] = torch.randn(N, H, W, 16, generator=g)
+    xs = xs.to(torch.bfloat16)
+    view = xs.flatten(2).unfold(2, 48, 16)
+    dy = torch.randn(N, Cout, H, W, generator=g).to(torch.bfloat16)
+    ref = torch.nn.grad.conv2d_weight(view.float().permute(0, 3, 1, 2), (Cout, 48, 3, 1), dy.float(), 1, (1, 0))
+    L = _lib.lib()
+    xd = xs.cuda()
+    dyd = dy.permute(0, 2, 3, 1).contiguous().cuda()
+    ws = torch.empty(4 << 20, device="cuda", dtype=torch.float32)
+    dw = torch.zeros(Cout, 3, 48, device="cuda", dtype=torch.float32)
+    _lib.check(L.yb_conv2d_wgrad(_lib.ptr(xd), N, H, W, 48, _lib.c_i64(16), _lib.ptr(dyd), Cout, _lib.c_i64(Cout), 31, 1,
+                                 _lib.ptr(ws), _lib.c_i64(ws.numel()), 0, _lib.ptr(dw), Cout, None, 0, _lib.stream()))
+    torch.cuda.synchronize()
+    assert rel(dw.cpu().view(Cout, 3, 1, 48).permute(0, 3, 1, 2), ref) < TOL

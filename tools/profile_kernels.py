@@ -59,7 +59,7 @@ def main():
     job(lambda: L.yb_maxpool5_fwd(xp.data_ptr(), 384, 64, 20, 20, 384, yp.data_ptr(), 384, am.data_ptr(), st))
     job(lambda: L.yb_maxpool5_bwd(yp.data_ptr(), 384, am.data_ptr(), 64, 20, 20, 384, xp.data_ptr(), 384, 0, st))
     img = torch.randint(0, 256, (64, 3, 640, 640), device=dev, dtype=torch.uint8)
-    x16 = torch.empty(64, 320, 320, 48, device=dev, dtype=torch.bfloat16)
+    x16 = torch.empty(64, 320, 322, 16, device=dev, dtype=torch.bfloat16)
     job(lambda: L.yb_prep_input(img.data_ptr(), 1, 64, 640, 640, x16.data_ptr(), st))
 
     # ---- ComputeLoss kernels (loss.cu): bs=64 head tensors at 640x640, 512 targets, forward + backward

@@ -26,6 +26,7 @@ int yb_conv2d_fwd(const void* x, int N, int H, int W, int Cin, int64_t x_pitch, 
                   const float* shift, int act, const void* addend, int64_t addend_pitch, float* stats,
                   int* stats_rows, int head_na, int head_no, void* stream) {
   TView in{const_cast<void*>(x), N, H, W, Cin, (long)x_pitch};
+  stem_view(in, ks);
   TView out{y, N, H / stride, W / stride, Cout, (long)y_pitch};
   ConvEpilogue ep;
   ep.out_kind = out_kind;
@@ -71,6 +72,7 @@ void* yb_conv_fwd_plan(const void* x, int N, int H, int W, int Cin, int64_t x_pi
                        const float* shift, int act, const void* addend, int64_t addend_pitch, float* stats,
                        int* stats_rows, int head_na, int head_no) {
   TView in{const_cast<void*>(x), N, H, W, Cin, (long)x_pitch};
+  stem_view(in, ks);
   TView out{y, N, H / stride, W / stride, Cout, (long)y_pitch};
   ConvEpilogue ep;
   ep.out_kind = out_kind;
@@ -126,6 +128,7 @@ void* yb_conv_wgrad_plan(const void* x, int N, int H, int W, int Cin, int64_t x_
                          int64_t dy_pitch, int ks, int stride, float* workspace, int64_t workspace_floats,
                          int max_splits) {
   TView xv{const_cast<void*>(x), N, H, W, Cin, (long)x_pitch};
+  stem_view(xv, ks);
   TView gv{const_cast<void*>(dy), N, H / stride, W / stride, Cout, (long)dy_pitch};
   YbPlan* pl = new YbPlan();
   pl->kind = 1;
@@ -146,6 +149,7 @@ int yb_conv2d_wgrad(const void* x, int N, int H, int W, int Cin, int64_t x_pitch
                     int64_t dy_pitch, int ks, int stride, float* workspace, int64_t workspace_floats, int max_splits,
                     float* dw, int out_rows, const int* index_map, int accumulate, void* stream) {
   TView xv{const_cast<void*>(x), N, H, W, Cin, (long)x_pitch};
+  stem_view(xv, ks);
   TView gv{const_cast<void*>(dy), N, H / stride, W / stride, Cout, (long)dy_pitch};
   WgradPlan pl;
   int rc = wgrad_plan(pl, xv, gv, ks, stride, workspace, (size_t)workspace_floats, max_splits);

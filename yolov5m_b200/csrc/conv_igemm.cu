@@ -324,10 +324,10 @@ static int pick_block_n(int Cout) {
 
 // A tensor map over (a parity sub-grid of) an NHWC view: dims (C, W/sx, H/sy, N).
 static int make_a_map(CUtensorMap* m, const TView& v, int KC, int PW, int PH, int PN, int py, int px, int sy, int sx) {
-  const bf16* base = reinterpret_cast<const bf16*>(v.ptr) + ((long)py * v.W + px) * v.pitch;
+  const bf16* base = reinterpret_cast<const bf16*>(v.ptr) + (long)py * v.rowp() + (long)px * v.pitch;
   uint64_t dims[4] = {(uint64_t)v.C, (uint64_t)(v.W / sx), (uint64_t)(v.H / sy), (uint64_t)v.N};
-  uint64_t strides[3] = {(uint64_t)v.pitch * sx * 2, (uint64_t)v.pitch * v.W * sy * 2,
-                         (uint64_t)v.pitch * v.W * v.H * 2};
+  uint64_t strides[3] = {(uint64_t)v.pitch * sx * 2, (uint64_t)v.rowp() * sy * 2,
+                         (uint64_t)v.rowp() * v.H * 2};
   uint32_t box[4] = {(uint32_t)KC, (uint32_t)PW, (uint32_t)PH, (uint32_t)PN};
   return encode_tmap(m, base, 4, dims, strides, box, 2 * KC, 2);
 }
@@ -360,10 +360,10 @@ bool conv_tma_store_enabled() {
 // output map over (a parity sub-grid of) an NHWC bf16 view: dims (C, W/sx, H/sy, N), box [64 x bw x bh x bn], SWIZZLE_128B.
 // The box may exceed C (64-channel slabs of a 48 / 96-channel tensor): the out-of-bounds part is clipped by the store.
 bool conv_make_out_map(CUtensorMap* m, const TView& v, int bw, int bh, int bn, int py, int px, int sy, int sx) {
-  const bf16* base = reinterpret_cast<const bf16*>(v.ptr) + ((long)py * v.W + px) * v.pitch;
+  const bf16* base = reinterpret_cast<const bf16*>(v.ptr) + (long)py * v.rowp() + (long)px * v.pitch;
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (v.pitch * 2) % 16 != 0 || bw > 256 || bh > 256 || bn > 256) return false;
   uint64_t dims[4] = {(uint64_t)v.C, (uint64_t)(v.W / sx), (uint64_t)(v.H / sy), (uint64_t)v.N};
-  uint64_t strides[3] = {(uint64_t)v.pitch * sx * 2, (uint64_t)v.pitch * v.W * sy * 2, (uint64_t)v.pitch * v.W * v.H * 2};
+  uint64_t strides[3] = {(uint64_t)v.pitch * sx * 2, (uint64_t)v.rowp() * sy * 2, (uint64_t)v.rowp() * v.H * 2};
   uint32_t box[4] = {64u, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
   return encode_tmap(m, base, 4, dims, strides, box, 128, 2) == 0;
 }

@@ -14,8 +14,15 @@ namespace yb {
 struct TView {
   void* ptr;   // points at channel 0 of the slice of pixel (0,0,0)
   int N, H, W, C;
-  long pitch;  // elements per pixel of the underlying buffer (>= C)
+  long pitch;  // elements between consecutive pixels (>= C, except for the stem's overlapping-window view: 16 < 48)
+  long row_pitch = 0;  // elements between image rows; 0 = pitch * W (dense rows)
+  long rowp() const { return row_pitch ? row_pitch : pitch * W; }
 };
+// The stem's operand (ks code 31, Cin = 48, pitch = 16): the three horizontal taps of the 16-channel space-to-depth image
+// are a VIEW of its row-padded storage (N, H, W + 2, 16) -- 48 contiguous values starting at padded column w
+inline void stem_view(TView& v, int ks) {
+  if (ks == 31 && v.pitch < v.C) v.row_pitch = (long)(v.W + 2) * v.pitch;
+}
 
 struct ConvTap {
   int8_t map;  // which A tensor map (input parity for stride 2)

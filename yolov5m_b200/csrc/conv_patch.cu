@@ -393,10 +393,10 @@ static int pick_block_n(int Cout) {
 
 // tensor map over (a parity sub-grid of) an NHWC view with a [64 ch x bw x bh x 1] box
 static int make_patch_map(CUtensorMap* m, const TView& v, int bw, int bh, int py, int px, int sy, int sx) {
-  const bf16* base = reinterpret_cast<const bf16*>(v.ptr) + ((long)py * v.W + px) * v.pitch;
+  const bf16* base = reinterpret_cast<const bf16*>(v.ptr) + (long)py * v.rowp() + (long)px * v.pitch;
   uint64_t dims[4] = {(uint64_t)v.C, (uint64_t)(v.W / sx), (uint64_t)(v.H / sy), (uint64_t)v.N};
-  uint64_t strides[3] = {(uint64_t)v.pitch * sx * 2, (uint64_t)v.pitch * v.W * sy * 2,
-                         (uint64_t)v.pitch * v.W * v.H * 2};
+  uint64_t strides[3] = {(uint64_t)v.pitch * sx * 2, (uint64_t)v.rowp() * sy * 2,
+                         (uint64_t)v.rowp() * v.H * 2};
   uint32_t box[4] = {64u, (uint32_t)bw, (uint32_t)bh, 1u};
   return encode_tmap(m, base, 4, dims, strides, box, 128, 2);
 }

@@ -305,10 +305,10 @@ static bool choose_kpatch(int W, int H, int NB, int maxp, int& PW, int& PH, int&
 }
 
 static int make_map(CUtensorMap* m, const TView& v, int PW, int PH, int PN, int py, int px, int sy, int sx) {
-  const bf16* base = reinterpret_cast<const bf16*>(v.ptr) + ((long)py * v.W + px) * v.pitch;
+  const bf16* base = reinterpret_cast<const bf16*>(v.ptr) + (long)py * v.rowp() + (long)px * v.pitch;
   uint64_t dims[4] = {(uint64_t)v.C, (uint64_t)(v.W / sx), (uint64_t)(v.H / sy), (uint64_t)v.N};
-  uint64_t strides[3] = {(uint64_t)v.pitch * sx * 2, (uint64_t)v.pitch * v.W * sy * 2,
-                         (uint64_t)v.pitch * v.W * v.H * 2};
+  uint64_t strides[3] = {(uint64_t)v.pitch * sx * 2, (uint64_t)v.rowp() * sy * 2,
+                         (uint64_t)v.rowp() * v.H * 2};
   uint32_t box[4] = {(uint32_t)kBoxC, (uint32_t)PW, (uint32_t)PH, (uint32_t)PN};
   return encode_tmap(m, base, 4, dims, strides, box, 128, 2);
 }

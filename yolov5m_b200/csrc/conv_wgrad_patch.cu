@@ -232,7 +232,7 @@ void set_wgrad_patch_mode(int m) { g_wpatch_mode = m; }
 
 static int make_box_map(CUtensorMap* m, const TView& v, int bw, int bh) {
   uint64_t dims[4] = {(uint64_t)v.C, (uint64_t)v.W, (uint64_t)v.H, (uint64_t)v.N};
-  uint64_t strides[3] = {(uint64_t)v.pitch * 2, (uint64_t)v.pitch * v.W * 2, (uint64_t)v.pitch * v.W * v.H * 2};
+  uint64_t strides[3] = {(uint64_t)v.pitch * 2, (uint64_t)v.rowp() * 2, (uint64_t)v.rowp() * v.H * 2};
   uint32_t box[4] = {64u, (uint32_t)bw, (uint32_t)bh, 1u};
   return encode_tmap(m, v.ptr, 4, dims, strides, box, 128, 2);
 }

@@ -829,11 +829,14 @@ __global__ void __launch_bounds__(256) sppf_pool3_bwd_kernel(const bf16* __restr
 }
 
 // ------------------------------------------------------------------------------------------------ input staging
-// x (N,3,H,W) float in [0,1] (or uint8, divided by 255) -> out (N,H/2,W/2,48) bf16:
-//   space-to-depth: s2d[ho][wo][(r*2+s)*3+c] = x[c][2ho+r][2wo+s] (12 channels, padded to 16), then the three horizontal taps
-//   of the stem gathered:  out[ho][wo][kw*16 + j] = s2d[ho][wo+kw-1][j]  (zero outside the image).
-// The 6x6/s2 stem (model.py:184) = 3x3/s1 over s2d = THREE vertical taps over `out` with K = 48 per tap: a third of the
-// TMA boxes / MMA steps of the nine-tap form, and full-width pipeline stages instead of 32-byte rows.
+// x (N,3,H,W) float in [0,1] (or uint8, divided by 255) -> out (N,H/2,W/2+2,16) bf16:
+//   space-to-depth: s2d[ho][wo][(r*2+s)*3+c] = x[c][2ho+r][2wo+s] (12 channels, padded to 16), stored at column wo + 1 of a
+//   row that carries one zero pixel on either side.
+// The 6x6/s2 stem (model.py:184) = 3x3/s1 over s2d = THREE vertical taps with K = 48 per tap over the VIEW
+//   g[ho][wo][kw*16 + j] = s2d[ho][wo+kw-1][j] = 48 contiguous values of `out` starting at padded column wo
+// (tensor-map dims (48, W/2, H/2, N) with a 32-byte pixel stride: overlapping windows, verified by
+// tools/tma_overlap_probe.cu): a third of the TMA boxes / MMA steps of the nine-tap form and full-width pipeline stages,
+// without materialising the 48-channel tensor (3x the bytes: 5.0 GB at bs=128, 1280x1280).
 // RESIZE: the image is first resampled from (Hs, Ws) to (H, W) exactly like the reference's multi_scale()
 // (utils/training_utils.py:11-28: nn.functional.interpolate(img, size, mode="bilinear", align_corners=False) on the
 // float image): src = max(scale * (dst + 0.5) - 0.5, 0), scale = in / out, neighbours (i, min(i + 1, in - 1)).
@@ -918,14 +921,13 @@ __global__ void prep_input_kernel(const T* __restrict__ x, int N, int H, int W, 
       hi.v[j] = v[8 + j];
       z.v[j] = 0.f;
     }
-    // every tap slot is 16 channels = 32 bytes = one L2 sector, 32-byte aligned: one st.global.v8 per slot (two 16-byte
-    // stores would be two half-sector writes)
-    bf16* me = out + i * 48;
-    st16(me + 16, lo, hi);  // centre tap of this pixel
-    if (wo + 1 < Wo) st16(me + 48, lo, hi);  // left tap (kw = 0) of the right neighbour
-    else st16(me + 32, z, z);                // last column: its right tap is outside the image
-    if (wo > 0) st16(me - 48 + 32, lo, hi);  // right tap (kw = 2) of the left neighbour
-    else st16(me, z, z);                     // first column: its left tap is outside the image
+    // one pixel = 16 channels = 32 bytes = one L2 sector (st.global.v8); rows carry one zero pixel on either side, so the
+    // stem's three horizontal taps are the 48 contiguous values starting one pixel to the left (an overlapping-window
+    // tensor-map view, see yb_prep_input in the header): the 48-channel tap-gathered tensor never exists in HBM
+    bf16* me = out + ((n * Ho + ho) * (long)(Wo + 2) + wo + 1) * 16;
+    st16(me, lo, hi);
+    if (wo == 0) st16(me - 16, z, z);
+    if (wo + 1 == Wo) st16(me + 16, z, z);
   }
 }
 

@@ -175,6 +175,16 @@ class _View:
         return self.buf.g[..., self.c0:self.c0 + self.C]
 
 
+class _StemView(_View):
+    """The stem's input: the row-padded 16-channel space-to-depth staging (N, H, W+2, 16) read as (N, H, W, 48) with
+    pitch 16 -- pixel w's 48 channels are padded columns w..w+2, i.e. the three horizontal taps (csrc: stem_view)."""
+
+    def __init__(self, buf):
+        super().__init__(buf, 0, 48)
+        self.W = buf.W - 2
+        self.npix = buf.N * buf.H * self.W
+
+
 class _LayerRec:
     """Flat-buffer bookkeeping of one conv (+BN)."""
     __slots__ = ("name", "conv", "bn", "cin", "cout", "k", "stride", "w_off", "g_off", "b_off", "wt_off", "bias_off",
@@ -548,8 +558,8 @@ class _Engine:
         bb, nk = net.backbone, net.neck
         c = net._first_out
         self.outs, self.head_dy, self.head_dy_pl = [], [], []
-        self.x16 = self.buf(B, H // 2, W // 2, 48, grad=False)  # stem staging: space-to-depth + gathered horizontal taps
-        b0 = self.buf(B, H // 2, W // 2, c); self.cbl(bb[0], self.x16.v(), b0.v())
+        self.x16 = self.buf(B, H // 2, W // 2 + 2, 16, grad=False)  # stem staging: space-to-depth, one zero pixel either side
+        b0 = self.buf(B, H // 2, W // 2, c); self.cbl(bb[0], _StemView(self.x16), b0.v())
         b1 = self.buf(B, H // 4, W // 4, 2 * c); self.cbl(bb[1], b0.v(), b1.v())
         b2 = self.buf(B, H // 4, W // 4, 2 * c); self.c3(bb[2], b1.v(), b2.v())
         b3 = self.buf(B, H // 8, W // 8, 4 * c); self.cbl(bb[3], b2.v(), b3.v())
