@@ -109,6 +109,10 @@ int yb_bn_finalize(const float* stats, int rows, int C, double count, const floa
 int yb_bn_finalize_ld(const float* stats, int rows, int C, int stats_ld, double count, const float* gamma, const float* beta,
                       float eps, float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked,
                       float* scale, float* shift, float* mean, float* invstd, int training, void* stream);
+/* inference (model.eval(), model.py:17 with running statistics): the training=0 form of yb_bn_finalize for ALL the
+ * BatchNorms of the network in one launch.  items (device): n rows of 8 x int64 = {gamma, beta, running_mean, running_var,
+ * scale, shift (device pointers), C, eps (float bits in the low 32)} */
+int yb_bn_fold_batch(const void* items, int n, void* stream);
 int yb_bn_act_fwd(const void* y, int64_t y_pitch, int N, int H, int W, int C, const float* scale, const float* shift,
                   const void* res, int64_t res_pitch, void* out, int64_t out_pitch, void* out_up, int64_t up_pitch,
                   void* stream);

@@ -163,6 +163,14 @@ def test_sppf_pool3_fused_matches_chain(shape):
     torch.cuda.synchronize()
     assert torch.equal(cat_a, cat_b)
     assert torch.equal(am_a, am_b)
+    # inference form (no arg-max planes: packed bf16x2 maxima)
+    cat_c = torch.zeros_like(cat_a)
+    cat_c[..., :C] = cat_a[..., :C]
+    rc = L.yb_sppf_pool3_fwd(_lib.ptr(cat_c), _lib.c_i64(4 * C), N, H, W, C, _lib.ptr(cat_c[..., C:]), _lib.ptr(cat_c[..., 2 * C:]),
+                             _lib.ptr(cat_c[..., 3 * C:]), _lib.c_i64(4 * C), None, None, None, _lib.stream())
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert torch.equal(cat_a, cat_c)
     # backward: fused chain vs fp32 autograd of the three pools
     xr = x.float().requires_grad_(True)
     p1 = F.max_pool2d(xr, 5, 1, 2); p2 = F.max_pool2d(p1, 5, 1, 2); p3 = F.max_pool2d(p2, 5, 1, 2)

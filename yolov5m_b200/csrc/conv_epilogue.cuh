@@ -31,6 +31,7 @@ struct EpiArgs {
   const bf16* addend;
   void* out;
   int act, out_kind, Cout, H, W, head_na, head_no;
+  int ss_vec;  // scale / shift readable as aligned float4 runs of 16 (Cout % 16 == 0, 16-byte aligned pointers)
 };
 template <class P>
 __device__ __forceinline__ EpiArgs load_epi_args(const P& p) {
@@ -41,33 +42,75 @@ __device__ __forceinline__ EpiArgs load_epi_args(const P& p) {
   keep_in_reg(e.stats); keep_in_reg(e.scale); keep_in_reg(e.shift); keep_in_reg(e.addend); keep_in_reg(e.out);
   keep_in_reg(e.act); keep_in_reg(e.out_kind); keep_in_reg(e.Cout); keep_in_reg(e.H); keep_in_reg(e.W);
   keep_in_reg(e.head_na); keep_in_reg(e.head_no);
+  e.ss_vec = (p.scale != nullptr && p.shift != nullptr && (p.Cout & 15) == 0 &&
+              ((reinterpret_cast<uintptr_t>(p.scale) | reinterpret_cast<uintptr_t>(p.shift)) & 15) == 0) ? 1 : 0;
+  keep_in_reg(e.ss_vec);
   return e;
 }
 
 // P: EpiArgs (register copy of the epilogue fields of ConvKParams (stats, scale, shift, act, addend, out_kind, out,
 // Cout, H, W, head_na, head_no).  t_addr: TMEM address of column 0 of this chunk for this warp's lane quarter.
 // (n, h, w): output pixel of this thread's row; opix / apix: element offsets of that pixel in out / addend.
+struct EpiAffine {
+  float sc[16], sh[16];
+};
+// scale / shift of 16 columns.  mode: 0 = none (train fprop, dgrad), 1 = bias only (head convs; sc unused), 2 = scale + shift
+// (folded BN of the inference path).  Called BEFORE the wait on the TMEM load where the registers allow it, so that the
+// (L1-hit) latency overlaps the TMEM round trip: the first dependent FFMA / FADD was the top stall of the inference and
+// head epilogues (ncu source pages, round 2).
+__device__ __forceinline__ int conv_epilogue_affine_mode(const EpiArgs& p) {
+  return p.scale != nullptr ? 2 : (p.shift != nullptr ? 1 : 0);
+}
+__device__ __forceinline__ void conv_epilogue_affine(const EpiArgs& p, int mode, int col0, EpiAffine& a) {
+  if (mode == 2 && p.ss_vec) {
+    // eight 16-byte loads instead of 32 predicated scalar ones (the per-column predicates and loads were ~60 of the ~280
+    // instructions of a chunk, ncu source page of the stem at 1280x1280)
+    const float4* s4 = reinterpret_cast<const float4*>(p.scale + col0);
+    const float4* h4 = reinterpret_cast<const float4*>(p.shift + col0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 x = __ldg(s4 + j), y = __ldg(h4 + j);
+      a.sc[4 * j] = x.x; a.sc[4 * j + 1] = x.y; a.sc[4 * j + 2] = x.z; a.sc[4 * j + 3] = x.w;
+      a.sh[4 * j] = y.x; a.sh[4 * j + 1] = y.y; a.sh[4 * j + 2] = y.z; a.sh[4 * j + 3] = y.w;
+    }
+  } else if (mode == 2) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const bool in = col0 + j < p.Cout;
+      a.sc[j] = in ? __ldg(p.scale + col0 + j) : 1.f;
+      a.sh[j] = in ? __ldg(p.shift + col0 + j) : 0.f;
+    }
+  } else if (mode == 1) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a.sh[j] = col0 + j < p.Cout ? __ldg(p.shift + col0 + j) : 0.f;
+  }
+}
+
 __device__ __forceinline__ void conv_epilogue_process(const EpiArgs& p, const uint32_t* vr, int col0, bool valid, int n, int h, int w,
                                                       int64_t opix, int64_t apix, float* my_stats, int lane, uint8_t* stage_row,
-                                                      int ccl, int row);
+                                                      int ccl, int row, int affine, const EpiAffine* pre);
 
 // stage_row: when non-null, the bf16 result goes to shared memory instead of global memory: the address of this thread's
 // 128-byte row in the FIRST 64-channel slab of the tile's staging area (slabs are 16 KB apart); ccl = index of this
 // 16-channel chunk inside the tile.  The layout is the SWIZZLE_128B box layout the output tensor map stores from: 16-byte
 // unit u of row r sits at unit u ^ (r & 7).
+template <bool PRE = false>
 __device__ __forceinline__ void conv_epilogue_chunk(const EpiArgs& p, uint32_t t_addr, int col0, bool valid, int n, int h, int w,
                                                     int64_t opix, int64_t apix, float* my_stats, int lane,
                                                     uint8_t* stage_row = nullptr, int ccl = 0, int row = 0) {
     uint32_t vr[16];
     tmem_ld16(t_addr, vr);
+    EpiAffine aff;
+    const int affine = conv_epilogue_affine_mode(p);
+    if (PRE) conv_epilogue_affine(p, affine, col0, aff);
     tmem_ld_wait();
-    conv_epilogue_process(p, vr, col0, valid, n, h, w, opix, apix, my_stats, lane, stage_row, ccl, row);
+    conv_epilogue_process(p, vr, col0, valid, n, h, w, opix, apix, my_stats, lane, stage_row, ccl, row, affine, PRE ? &aff : nullptr);
 }
 
 // the per-chunk work on 16 accumulator columns already in registers
 __device__ __forceinline__ void conv_epilogue_process(const EpiArgs& p, const uint32_t* vr, int col0, bool valid, int n, int h, int w,
                                                       int64_t opix, int64_t apix, float* my_stats, int lane, uint8_t* stage_row,
-                                                      int ccl, int row) {
+                                                      int ccl, int row, int affine, const EpiAffine* pre) {
     float v[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(vr[j]);
@@ -120,11 +163,30 @@ __device__ __forceinline__ void conv_epilogue_process(const EpiArgs& p, const ui
     }
 
     if (valid) {
-      if (p.scale != nullptr) {
+      if (pre != nullptr) {  // parameters already in registers (loaded in front of the TMEM wait)
+        if (affine == 2) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fmaf(v[j], pre->sc[j], pre->sh[j]);
+        } else if (affine == 1) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] += pre->sh[j];
+        }
+      } else if (affine == 2 && p.ss_vec) {
+        const float4* s4 = reinterpret_cast<const float4*>(p.scale + col0);
+        const float4* h4 = reinterpret_cast<const float4*>(p.shift + col0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 a = __ldg(s4 + j), b = __ldg(h4 + j);
+          v[4 * j] = fmaf(v[4 * j], a.x, b.x);
+          v[4 * j + 1] = fmaf(v[4 * j + 1], a.y, b.y);
+          v[4 * j + 2] = fmaf(v[4 * j + 2], a.z, b.z);
+          v[4 * j + 3] = fmaf(v[4 * j + 3], a.w, b.w);
+        }
+      } else if (affine == 2) {
 #pragma unroll
         for (int j = 0; j < 16; ++j)
           if (col0 + j < p.Cout) v[j] = fmaf(v[j], __ldg(p.scale + col0 + j), __ldg(p.shift + col0 + j));
-      } else if (p.shift != nullptr) {
+      } else if (affine == 1) {
 #pragma unroll
         for (int j = 0; j < 16; ++j)
           if (col0 + j < p.Cout) v[j] += __ldg(p.shift + col0 + j);
@@ -234,15 +296,22 @@ __device__ __forceinline__ void conv_epilogue_process(const EpiArgs& p, const ui
 // two adjacent 16-column chunks with ONE 32-column TMEM load: half as many load -> wait round trips per tile (the
 // epilogue of the small-K layers is bound by that latency: ncu long-scoreboard stalls on the first use of the loaded
 // registers, three epilogue warps per scheduler cannot hide it)
+template <bool PRE = false>
 __device__ __forceinline__ void conv_epilogue_chunk2(const EpiArgs& p, uint32_t t_addr, int col0, bool valid, int n, int h, int w,
                                                      int64_t opix, int64_t apix, float* my_stats, int lane, uint8_t* stage_row,
                                                      int ccl, int row) {
     uint32_t vr[32];
     tmem_ld32(t_addr, vr);
+    EpiAffine aff;
+    const int affine = conv_epilogue_affine_mode(p);
+    // 32 accumulator registers are live here: only the 16 bias values of the first half fit in front of the wait
+    if (PRE && affine == 1) conv_epilogue_affine(p, 1, col0, aff);
     tmem_ld_wait();
-    conv_epilogue_process(p, vr, col0, valid, n, h, w, opix, apix, my_stats, lane, stage_row, ccl, row);
+    conv_epilogue_process(p, vr, col0, valid, n, h, w, opix, apix, my_stats, lane, stage_row, ccl, row, affine,
+                          PRE && affine == 1 ? &aff : nullptr);
     if (col0 + 16 < p.Cout)
-      conv_epilogue_process(p, vr + 16, col0 + 16, valid, n, h, w, opix, apix, my_stats, lane, stage_row, ccl + 1, row);
+      conv_epilogue_process(p, vr + 16, col0 + 16, valid, n, h, w, opix, apix, my_stats, lane, stage_row, ccl + 1, row, affine,
+                            nullptr);
 }
 
 }  // namespace yb

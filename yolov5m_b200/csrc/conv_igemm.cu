@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         for (int cc = 2 * eg; cc < nchunks; cc += 2 * kEpiGroups) {
           const int col0 = tc.nt * BN + cc * 16;
           if (col0 >= ea.Cout) break;
-          conv_epilogue_chunk2(ea, t_addr + cc * 16, col0, valid, n, h, w, opix, apix, my_stats, lane, stage_row, cc, r);
+          conv_epilogue_chunk2<true>(ea, t_addr + cc * 16, col0, valid, n, h, w, opix, apix, my_stats, lane, stage_row, cc, r);
         }
       } else {
         for (int cc = eg; cc < nchunks; cc += kEpiGroups) {

@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
         if (x32)
           conv_epilogue_chunk2(ea, t_addr, col0, valid, tc.n, h, w, opix, apix, my_stats, lane, nullptr, 0, 0);
         else
-          conv_epilogue_chunk(ea, t_addr, col0, valid, tc.n, h, w, opix, apix, my_stats, lane);
+          conv_epilogue_chunk<true>(ea, t_addr, col0, valid, tc.n, h, w, opix, apix, my_stats, lane);
       }
       tc_fence_before();
       __syncwarp();

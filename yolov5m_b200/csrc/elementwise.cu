@@ -196,6 +196,27 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restri
   if (invstd_out) invstd_out[c] = inv;
 }
 
+// inference: fold the running statistics of EVERY BatchNorm of the network in one launch (one CTA per layer) instead of one
+// bn_finalize launch in front of every conv: 79 launches and as many kernel boundaries less per forward.
+// items: n rows of 8 x int64 = {gamma, beta, running_mean, running_var, scale, shift (device pointers), C, eps (float bits)}
+__global__ void __launch_bounds__(256) bn_fold_batch_kernel(const long long* __restrict__ items) {
+  const long long* it = items + (size_t)blockIdx.x * 8;
+  const float* gamma = reinterpret_cast<const float*>(it[0]);
+  const float* beta = reinterpret_cast<const float*>(it[1]);
+  const float* rm = reinterpret_cast<const float*>(it[2]);
+  const float* rv = reinterpret_cast<const float*>(it[3]);
+  float* scale = reinterpret_cast<float*>(it[4]);
+  float* shift = reinterpret_cast<float*>(it[5]);
+  const int C = (int)it[6];
+  const float eps = __int_as_float((int)it[7]);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {  // same arithmetic as bn_finalize_kernel's inference branch
+    const float inv = rsqrtf(rv[c] + eps);
+    const float sc = gamma[c] * inv;
+    scale[c] = sc;
+    shift[c] = beta[c] - rm[c] * sc;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ BN apply + SiLU
 // kEwThreads = 192 = 2^6 * 3: for every channel count of the network (C/8 in {2,6,12,24,48,96,192}) the grid-stride
 // (gridDim * 192) is a multiple of C/8, so a thread keeps ONE channel vector for its whole life: the per-channel
@@ -742,6 +763,66 @@ __global__ void __launch_bounds__(256) sppf_pool3_fwd_kernel(const bf16* __restr
   }
 }
 
+// inference form (no arg-max planes): packed bf16x2 maxima, NaN-propagating like ATen's `val > max || isnan(val)`; a maximum
+// is a selection, so the result is the chain's bit for bit (up to the sign of a zero that ties with its negative).
+__device__ __forceinline__ uint4 max8(const uint4& a, const uint4& b) {
+  uint4 r;
+  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+  __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) pr[j] = __hmax2_nan(pa[j], pb[j]);
+  return r;
+}
+__global__ void __launch_bounds__(512) sppf_pool3_eval_kernel(const bf16* __restrict__ x, long x_pitch, int H, int W, int C,
+                                                              bf16* __restrict__ y1, bf16* __restrict__ y2, bf16* __restrict__ y3,
+                                                              long y_pitch) {
+  extern __shared__ __align__(16) uint8_t sp_smem[];
+  const int HW = H * W;
+  Px16* cur = reinterpret_cast<Px16*>(sp_smem);  // [HW] input of the current pool
+  Px16* rmv = cur + HW;                           // [HW] row maxima
+  const int cg = C >> 4;
+  const long n = blockIdx.x / cg;
+  const int c0 = (int)(blockIdx.x - n * cg) << 4;
+  const long pix0 = n * HW;
+  for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+    const bf16* src = x + (pix0 + p) * x_pitch + c0;
+    cur[p].lo = ldraw(src);
+    cur[p].hi = ldraw(src + 8);
+  }
+  __syncthreads();
+  for (int stage = 0; stage < 3; ++stage) {
+    bf16* yo = stage == 0 ? y1 : (stage == 1 ? y2 : y3);
+    for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+      const int h = p / W, w = p - h * W;
+      const int lo = max(w - 2, 0), hi = min(w + 2, W - 1);
+      Px16 m = cur[h * W + lo];
+      for (int iw = lo + 1; iw <= hi; ++iw) {
+        const Px16 v = cur[h * W + iw];
+        m.lo = max8(m.lo, v.lo);
+        m.hi = max8(m.hi, v.hi);
+      }
+      rmv[p] = m;
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+      const int h = p / W, w = p - h * W;
+      const int lo = max(h - 2, 0), hi = min(h + 2, H - 1);
+      Px16 m = rmv[lo * W + w];
+      for (int ih = lo + 1; ih <= hi; ++ih) {
+        const Px16 v = rmv[ih * W + w];
+        m.lo = max8(m.lo, v.lo);
+        m.hi = max8(m.hi, v.hi);
+      }
+      bf16* dst = yo + (pix0 + p) * y_pitch + c0;
+      *reinterpret_cast<uint4*>(dst) = m.lo;
+      *reinterpret_cast<uint4*>(dst + 8) = m.hi;
+      cur[p] = m;  // input of the next pool (the row pass of this stage is complete)
+    }
+    __syncthreads();
+  }
+}
+
 // backward of the chain in one launch: g2 += scatter(g3, am3); g1 += scatter(g2, am2); g0 += scatter(g1, am1), the
 // intermediate sums kept in fp32 in shared memory (gather form: every input pixel sums the <= 25 outputs that point at
 // it).  g0..g3 = gradient slices of the concat buffer ([x | p1 | p2 | p3]); only g0 is written (g1 / g2 have no other reader).
@@ -968,6 +1049,14 @@ using namespace yb;
 
 extern "C" {
 
+int yb_bn_fold_batch(const void* items, int n, void* stream) {
+  if (n <= 0) return 0;
+  YB_REQUIRE(items != nullptr, "bn_fold_batch: items");
+  bn_fold_batch_kernel<<<n, 256, 0, ST(stream)>>>(reinterpret_cast<const long long*>(items));
+  LAUNCH_OK();
+  return 0;
+}
+
 int yb_bn_finalize(const float* stats, int rows, int C, double count, const float* gamma, const float* beta, float eps,
                    float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked, float* scale,
                    float* shift, float* mean, float* invstd, int training, void* stream) {
@@ -1132,6 +1221,19 @@ int yb_maxpool5_bwd(const void* dy, int64_t dy_pitch, const uint8_t* argmax, int
 int yb_sppf_pool3_fwd(const void* x, int64_t x_pitch, int N, int H, int W, int C, void* y1, void* y2, void* y3, int64_t y_pitch,
                       uint8_t* am1, uint8_t* am2, uint8_t* am3, void* stream) {
   YB_REQUIRE(C % 16 == 0 && x_pitch % 8 == 0 && y_pitch % 8 == 0, "sppf_pool3_fwd: alignment (C %% 16, pitches %% 8)");
+  if (am1 == nullptr && am2 == nullptr && am3 == nullptr) {  // inference: no arg-max planes
+    const size_t smem_e = (size_t)H * W * 64;
+    if (smem_e > 200 * 1024) return 1;
+    static size_t attr_e = 0;
+    if (smem_e > attr_e) {
+      YB_CHECK_CUDA(cudaFuncSetAttribute(sppf_pool3_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
+      attr_e = smem_e;
+    }
+    sppf_pool3_eval_kernel<<<N * (C / 16), H * W > 512 ? 512 : 256, smem_e, ST(stream)>>>(CB16(x), x_pitch, H, W, C, B16(y1),
+                                                                                         B16(y2), B16(y3), y_pitch);
+    LAUNCH_OK();
+    return 0;
+  }
   const size_t smem = (size_t)H * W * (32 + 32 + 16);
   if (smem > 200 * 1024) return 1;  // map too large for one CTA's shared memory: the caller chains yb_maxpool5_fwd instead
   static size_t attr = 0;

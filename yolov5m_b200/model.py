@@ -127,6 +127,16 @@ class HEADS(nn.Module):  # reference model.py:143-175
 PARITY_PASSES = ((0, 0), (0, 1), (1, 0), (1, 1), (0, 2), (2, 0))  # (activation plane, weight plane) per conv pass
 
 
+class _Work(float):
+    """algorithmic FLOPs of one conv launch, carrying its algorithmic bytes (activation read once + activation written
+    once + weights), so that the timed wrappers can report the launch's roofline floor max(flops / tensor, bytes / HBM)"""
+
+    def __new__(cls, flops, nbytes):
+        o = float.__new__(cls, flops)
+        o.nbytes = float(nbytes)
+        return o
+
+
 class _Buf:
     """NHWC bf16 allocation (+ same-shaped gradient when training).  Parity mode (csrc/parity.cu): the tensor and its
     gradient are fp32 and `pl` holds the three bf16 planes of the 3-way split that the tcgen05 convs read."""
@@ -168,6 +178,10 @@ class _View:
     def plane_stride(self):
         return self.buf.plane_stride
 
+    def pitch_c(self):
+        """channels per pixel a conv over this view actually moves (the stem's window view re-reads its 16 stored ones)"""
+        return min(self.C, self.pitch)
+
     def tensor(self):
         return self.buf.t[..., self.c0:self.c0 + self.C]
 
@@ -203,6 +217,7 @@ class _Engine:
         self.on_grad_chunks = None  # (schedule {op index: [chunk]}, callback(chunk, gflat)) set by trainer.GradSync
         self.prof = None
         self.conv_flops = {"fwd": 0.0, "dgrad": 0.0, "wgrad": 0.0}  # algorithmic FLOPs of the reference convs per step
+        self._fold, self._fold_eps, self._fold_dev = [], None, None  # inference: BatchNorms folded by ONE launch per forward
         self.plans = []
         self.bufs = []
         self.nbytes = 0
@@ -238,7 +253,7 @@ class _Engine:
         e0.record()
         _lib.check(self.L.yb_plan_run(plan, st))
         e1.record()
-        self.prof.append((kind, flops, e0, e1))
+        self.prof.append((kind, flops, e0, e1, getattr(flops, "nbytes", 0.0)))
 
     def _ew(self, kind, nbytes, fn, *args):
         """HBM-bound pass (BN/SiLU forward, backward reduce, backward apply): timed like the convs when prof is a list; the
@@ -250,7 +265,7 @@ class _Engine:
         e0.record()
         _lib.check(fn(*args))
         e1.record()
-        self.prof.append((kind, nbytes, e0, e1))
+        self.prof.append((kind, nbytes, e0, e1, nbytes))
 
     def _wgrad(self, plan, st, flops, *args):
         if self.prof is None:
@@ -260,7 +275,7 @@ class _Engine:
         e0.record()
         _lib.check(self.L.yb_wgrad_plan_run(plan, *args, st))
         e1.record()
-        self.prof.append(("wgrad", flops, e0, e1))
+        self.prof.append(("wgrad", flops, e0, e1, getattr(flops, "nbytes", 0.0)))
 
     def _layer_events(self):
         if self.side is None:
@@ -303,7 +318,7 @@ class _Engine:
             return None
         ra, rb, wt2 = net._pairs[c3mod]
         C, N, H, W = ra.cout, xin.N, xin.H, xin.W
-        pr = {"C": C, "wt2": wt2, "ra": ra, "rb": rb, "flops": 2.0 * xin.npix * 2 * C * ra.cin, "xin": xin}
+        pr = {"C": C, "wt2": wt2, "ra": ra, "rb": rb, "flops": _Work(2.0 * xin.npix * 2 * C * ra.cin, 2.0 * (xin.npix * (xin.C + 2 * C) + 2 * C * ra.cin)), "xin": xin}
         w_ptr = net._wfwd.data_ptr() + 2 * ra.w_off
         if self.train:
             pr["y"] = self.buf(N, H, W, 2 * C, grad=False)
@@ -327,7 +342,8 @@ class _Engine:
         Ho, Wo = xin.H // (1 if r.is_stem else r.stride), xin.W // (1 if r.is_stem else r.stride)
         assert (out.H, out.W, out.C) == (Ho, Wo, r.cout), (r.name, out.H, out.W, out.C)
         C = r.cout
-        flops = 2.0 * xin.N * Ho * Wo * C * r.k * r.k * r.cin  # the reference conv (stem: 6x6 over 3 channels)
+        flops = _Work(2.0 * xin.N * Ho * Wo * C * r.k * r.k * r.cin,  # the reference conv (stem: 6x6 over 3 channels)
+                      2.0 * (xin.npix * xin.pitch_c() + xin.N * Ho * Wo * C + C * r.k * r.k * r.cin))
         self.conv_flops["fwd"] += flops
         if pair is not None:
             return self._cbl_pair(r, xin, out, pair, half, flops)
@@ -345,12 +361,8 @@ class _Engine:
                                                   res.ptr if res is not None else None, res.pitch if res is not None else 0,
                                                   None, None, 3, 85))
             self.plans.append(plan)
-            sp, hp = scale.data_ptr(), shift.data_ptr()
-
-            def op(st, plan=plan):
-                _lib.check(L.yb_bn_finalize(None, 0, C, 1.0, gam, bet, BN_EPS, BN_MOMENTUM, rm, rv, None, sp, hp, None, None, 0, st))
-                self._conv(plan, st, flops, "fwd")
-            self.fwd_ops.append(op)
+            self._fold.append((gam, bet, rm, rv, scale.data_ptr(), shift.data_ptr(), C, r.bn))
+            self.fwd_ops.append(lambda st, plan=plan: self._conv(plan, st, flops, "fwd"))
             if up is not None:
                 self.fwd_ops.append(lambda st: _lib.check(L.yb_upsample2x_fwd(out.ptr, out.pitch, out.N, out.H, out.W, C,
                                                                                up.ptr, up.pitch, st)))
@@ -401,12 +413,9 @@ class _Engine:
                 sp1, hp1 = pr["scale"].data_ptr() + 4 * C, pr["shift"].data_ptr() + 4 * C
                 pflops = pr["flops"]
 
-                def op(st):
-                    _lib.check(L.yb_bn_finalize(None, 0, C, 1.0, gam, bet, BN_EPS, BN_MOMENTUM, rm, rv, None, sp, hp, None, None, 0, st))
-                    _lib.check(L.yb_bn_finalize(None, 0, C, 1.0, gb, bb, BN_EPS, BN_MOMENTUM, rb.rm.data_ptr(), rb.rv.data_ptr(),
-                                                None, sp1, hp1, None, None, 0, st))
-                    self._conv(plan, st, pflops, "fwd")
-                self.fwd_ops.append(op)
+                self._fold.append((gam, bet, rm, rv, sp, hp, C, r.bn))
+                self._fold.append((gb, bb, rb.rm.data_ptr(), rb.rv.data_ptr(), sp1, hp1, C, rb.bn))
+                self.fwd_ops.append(lambda st: self._conv(plan, st, pflops, "fwd"))
             return
         scale, shift, mean, invstd = self._stat(C), self._stat(C), self._stat(C), self._stat(C)
         y = pr["y"].v(half * C, C)
@@ -498,7 +507,7 @@ class _Engine:
         amp = [a.data_ptr() if a is not None else None for a in ams]
         # the three chained 5x5 pools of model.py:108-110 as ONE launch when the map fits a CTA's shared memory
         # (csrc/elementwise.cu: sppf_pool3_*); otherwise (and in parity mode) three maxpool launches
-        fused_fwd = not self.parity and c_ % 16 == 0 and H * W * 80 <= 200 * 1024
+        fused_fwd = not self.parity and c_ % 16 == 0 and H * W * (80 if self.train else 64) <= 200 * 1024
         fused_bwd = fused_fwd and H * W * 144 <= 200 * 1024
         if fused_fwd:
             v = views
@@ -524,7 +533,7 @@ class _Engine:
         r = net._rec_of[net.head.out_convs[i]]
         na, no = net.head.naxs, 5 + net.head.nc
         out = torch.empty(xin.N, na, xin.H, xin.W, no, device=self.dev, dtype=torch.float32)
-        flops = 2.0 * xin.npix * r.cout * r.cin
+        flops = _Work(2.0 * xin.npix * r.cout * r.cin, xin.npix * (2.0 * r.cin + 4.0 * r.cout) + 2.0 * r.cout * r.cin)
         self.conv_flops["fwd"] += flops
         if self.parity:
             plans = self._parity_conv_plans(xin, r, 1, 1, out.data_ptr(), r.cout, head=True,
@@ -869,6 +878,16 @@ class _Engine:
             _lib.check(L.yb_prep_input(x.data_ptr(), dt, self.B, self.H, self.W, self.x16.t.data_ptr(), st))
         else:  # multi-scale training: bilinear resample fused into the stem staging (training_utils.py:11-28)
             _lib.check(L.yb_prep_input_resized(x.data_ptr(), dt, self.B, Hs, Ws, self.H, self.W, self.x16.t.data_ptr(), st))
+        if self._fold:
+            # running statistics -> (scale, shift) of every conv epilogue, re-read on every forward like nn.BatchNorm2d does
+            eps = tuple(float(f[7].eps) for f in self._fold)
+            if eps != self._fold_eps:
+                tab = np.zeros((len(self._fold), 8), np.int64)
+                for i, f in enumerate(self._fold):
+                    tab[i, :7] = f[:7]
+                    tab[i, 7] = int(np.float32(eps[i]).view(np.int32))
+                self._fold_dev, self._fold_eps = torch.from_numpy(tab).to(self.dev), eps
+            _lib.check(L.yb_bn_fold_batch(self._fold_dev.data_ptr(), len(self._fold), st))
         for op in self.fwd_ops:
             op(st)
         return self.outs
