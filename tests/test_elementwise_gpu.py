@@ -279,3 +279,21 @@ def test_prep_input_resized_matches_interpolate(dt, src, dst):
         _lib.check(L.yb_prep_input(_lib.ptr(x.cuda()), 0 if dt == torch.float32 else 1, 2, src[0], src[1], _lib.ptr(ref),
                                    _lib.stream()))
         assert torch.equal(same.cpu(), ref.cpu())
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 16), (3, 20, 24), (1, 64, 640)])
+def test_prep_input_u8_fast_path_bit_exact(shape):
+    """uint8 batches with W % 8 == 0 take the 4-pixels-per-thread kernel (table lookup of bf16(v / 255)): bit-identical to
+    the one-pixel kernel fed the same values as float32 (x.float() / 255, utils/training_utils.py:98)."""
+    N, H, W = shape
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(H * 7 + W)
+    x = torch.randint(0, 256, (N, 3, H, W), generator=g, dtype=torch.uint8)
+    x[0, :, 0, :8] = torch.tensor([0, 1, 2, 127, 128, 254, 255, 3], dtype=torch.uint8)
+    got = torch.full((N, H // 2, W // 2 + 2, 16), 9.0, device="cuda", dtype=torch.bfloat16)
+    want = torch.full_like(got, 7.0)
+    _lib.check(L.yb_prep_input(_lib.ptr(x.cuda()), 1, N, H, W, _lib.ptr(got), _lib.stream()))
+    _lib.check(L.yb_prep_input(_lib.ptr((x.float() / 255).cuda()), 0, N, H, W, _lib.ptr(want), _lib.stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
+    assert float(got[:, :, 0].abs().max()) == 0 and float(got[:, :, -1].abs().max()) == 0
