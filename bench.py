@@ -218,23 +218,16 @@ def detect_inputs(bs, size, seed=3):
     return cal, x
 
 
-def run_reference_detect(a):
-    """the reference's own detect path (detect.py:50-54: model -> cells_to_bboxes -> non_max_suppression) on the host cores"""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def cpu_detect_sample(a, steps, warm):
+    """bounded sample of the reference's own detect path (detect.py:50-54: model -> cells_to_bboxes -> non_max_suppression)
+    on the host cores: (img/s, seconds per pass, cpu_baseline object, candidate fraction, kept per image)"""
     import torch
-    try:
-        from baseline.ref_step import RefDetector
-        det, kind = RefDetector(), "reference"
-    except Exception as e:
-        print(json.dumps({"impl": "reference", "unavailable": f"reference not importable for the detect workload: {e!r}"}))
-        return
+    from baseline.ref_step import RefDetector
+    det = RefDetector()
     bs = 2
     cal, x = detect_inputs(bs, a.size)
     frac = calibrate_detector(det.model, cal.float() / 255, x.float() / 255, a.cand_frac)
     xf = x.float() / 255
-    steps, warm = max(1, min(a.steps, 3)), min(a.warmup, 1)
     for _ in range(warm):
         det.detect(xf)
     t0 = time.perf_counter()
@@ -244,14 +237,28 @@ def run_reference_detect(a):
     ips = bs / dt
     sample = (f"{steps} timed + {warm} warm-up detect passes at bs={bs}, {a.size}x{a.size}, fp32, the unmodified reference "
               f"(model.py, utils/plot_utils.py cells_to_bboxes, utils/bboxes_utils.py non_max_suppression)")
+    cpu = {"value": ips, "unit": UNIT, "cores": det.threads, "kind": "reference", "sample": sample}
+    return ips, dt, cpu, frac, sum(len(k) for k in kept) / bs, bs
+
+
+def run_reference_detect(a):
+    """`--impl reference --workload detect`: the reference's own detect path on the host cores"""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warm = max(1, min(a.steps, 3)), min(a.warmup, 1)
+    try:
+        ips, dt, cpu, frac, kept, bs = cpu_detect_sample(a, steps, warm)
+    except Exception as e:
+        print(json.dumps({"impl": "reference", "unavailable": f"reference not importable for the detect workload: {e!r}"}))
+        return
     print(json.dumps({
         "impl": "reference", "metric": DETECT_METRIC, "value": ips, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "fp32", "data": "synthetic",
         "config": {"workload": "configs[4]: detect (eval fwd + cells_to_bboxes + NMS conf .25 iou .45), CPU host cores",
-                   "batch_per_step": bs, "image": a.size, "candidate_fraction": frac,
-                   "kept_per_image": sum(len(k) for k in kept) / bs},
-        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": det.threads, "kind": kind, "sample": sample},
+                   "batch_per_step": bs, "image": a.size, "candidate_fraction": frac, "kept_per_image": kept},
+        "cpu_baseline": cpu,
         "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -397,8 +404,14 @@ def run_ours_detect(a):
         e2e = {"value": world * B * a.steps / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel()) * world,
                "d2h_bytes_per_step": int(rows_h.numel() * 4 + cnt_h.numel() * 4) * world, "ms_per_step": ms_e / a.steps}
 
+    cpu = None
     if rank == 0:
         clocks.stop()
+        if world == 1 and not a.no_cpu_baseline:
+            try:
+                cpu = cpu_detect_sample(a, 2, 1)[2]
+            except Exception as e:  # baseline/_ref not vendored on this box
+                cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"unavailable: {e!r}"}
         # keep sets of a few images against the oracle on the SAME decoded tensor (bit-exact contract)
         from oracle import nms_ref
         nchk = min(2, B)
@@ -424,7 +437,7 @@ def run_ours_detect(a):
                                    "conv_frac_of_floor": fwd_floor / fwd_conv_t},
                        "decode": {"ms": t_d * 1e3, "GBps": dec_bytes / t_d / 1e9},
                        "nms": {"ms": t_n * 1e3, "candidates_per_image": cand / B}},
-            "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary(windows),
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary(windows),
         }
         print(json.dumps(out_line))
     if world > 1:
