@@ -199,3 +199,52 @@ def test_grad_accumulation_and_flat_views():
     assert p.grad.shape == p.shape
     assert rel(p.grad, 2 * g1[w]) < 1e-3   # same input, same batch statistics: exactly twice the first gradient
     assert m.flat_grads.numel() == m.flat_params.numel()
+
+
+@gpu
+def test_submodule_forward_matches_oracle_blocks():
+    """Blocks called on their own (``model.backbone[0](img)``, reference model.py:27,49,89,106): inference semantics on the
+    fused kernels, against the oracle's block functions with bf16 storage rounding (quant=True).  A block in training mode
+    under grad refuses instead of returning a tensor that would not train."""
+    from yolov5m_b200 import _lib
+    m, sd = make_model()
+    m.eval()
+    ref = model_ref.Net({k: v.clone() for k, v in sd.items()}, train=False, quant=True)
+    g = torch.Generator().manual_seed(5)
+    img = torch.rand(2, 3, 64, 96, generator=g)
+    with torch.no_grad():
+        got = m.backbone[0](img.cuda())                       # stem CBL: the image through the space-to-depth staging
+        want = ref.cbl(img, "backbone.0", 6, 2, 2)
+        assert got.shape == want.shape and got.dtype == torch.float32
+        assert rel(got.cpu(), want) < 1e-2
+        x48 = torch.randn(2, 48, 32, 48, generator=g)
+        got = m.backbone[1](x48.cuda()); want = ref.cbl(x48, "backbone.1", 3, 2, 1)
+        assert got.shape == want.shape and rel(got.cpu(), want) < 1e-2
+        x96 = torch.randn(2, 96, 16, 24, generator=g)
+        got = m.backbone[2](x96.cuda()); want = ref.c3(x96, "backbone.2", 2, True)     # C3 with fused c1 || c_skipped
+        assert got.shape == want.shape and rel(got.cpu(), want) < 2e-2
+        x48b = torch.randn(2, 48, 16, 24, generator=g)
+        blk = m.backbone[2].seq[0]                                                   # Bottleneck: c2(c1(x)) + x
+        h = ref.cbl(x48b, "backbone.2.seq.0.c1", 1, 1, 0)
+        want = ref.cbl(h, "backbone.2.seq.0.c2", 3, 1, 1) + x48b.to(torch.bfloat16).float()
+        got = blk(x48b.cuda())
+        assert got.shape == want.shape and rel(got.cpu(), want) < 2e-2
+        x768 = torch.randn(2, 768, 4, 6, generator=g)
+        got = m.backbone[9](x768.cuda()); want = ref.sppf(x768, "backbone.9")
+        assert got.shape == want.shape and rel(got.cpu(), want) < 2e-2
+        x384 = torch.randn(2, 384, 8, 12, generator=g)
+        got = m.neck[3](x384.cuda()); want = ref.c3(x384, "neck.3", 2, False)       # neck C3 (no shortcut)
+        assert got.shape == want.shape and rel(got.cpu(), want) < 2e-2
+        # the full forward still works afterwards and a second call reuses the cached plan
+        outs = m(img.cuda())
+        assert [tuple(o.shape) for o in outs] == [(2, 3, 8, 12, 85), (2, 3, 4, 6, 85), (2, 3, 2, 3, 85)]
+        again = m.backbone[1](x48.cuda())
+        assert torch.equal(again, m.backbone[1](x48.cuda()))
+    m.train()
+    with pytest.raises(_lib.YBError):
+        m.backbone[1](x48.cuda())
+    with pytest.raises(_lib.YBError):
+        m.backbone[1].cbl[0](x48.cuda())   # a bare conv / BN holder has no arithmetic of its own
+    with pytest.raises(ValueError):
+        with torch.no_grad():
+            m.backbone[1](x96.cuda())      # wrong channel count

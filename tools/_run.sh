@@ -1,3 +1,1 @@
-mkdir -p gpurun_out
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/bench_r2z_8gpu.json 2> gpurun_out/bench_r2z_8gpu.err; tail -c 300 gpurun_out/bench_r2z_8gpu.err; echo; head -c 300 gpurun_out/bench_r2z_8gpu.json
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 4 --steps 20 --warmup 5 > gpurun_out/bench_r2z_4gpu.json 2> gpurun_out/bench_r2z_4gpu.err; head -c 300 gpurun_out/bench_r2z_4gpu.json
+timeout 300 python -m pytest tests/test_model_gpu.py -m gpu -q -x 2>&1 | tail -15

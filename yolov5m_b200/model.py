@@ -19,6 +19,7 @@ There is no CPU / PyTorch fallback: calling forward without the CUDA library or 
 import ctypes
 import math
 import os
+import weakref
 
 import numpy as np
 import torch
@@ -32,6 +33,9 @@ HEAD_PAD = 256     # head conv Cout = 3*(5+nc) padded to a multiple of 16 for th
 
 
 # ------------------------------------------------------------------------------------------------ module tree
+_OWNERS = weakref.WeakValueDictionary()  # id(block) -> the YOLOV5m that owns it (blocks called on their own, run_submodule)
+
+
 class _Conv(nn.Module):
     """Parameter holder for an nn.Conv2d (reference model.py:16,162).  The arithmetic runs in the engine."""
 
@@ -46,7 +50,13 @@ class _Conv(nn.Module):
         return f"{self.in_channels}, {self.out_channels}, k={self.kernel_size}, s={self.stride}, bias={self.bias is not None}"
 
     def forward(self, x):
-        raise _lib.YBError("sub-modules hold parameters only; call YOLOV5m.forward (fused sm_100a engine)")
+        """Sub-modules hold parameters; the arithmetic runs in the owning network's engine.  CBL / Bottleneck / C3 / SPPF
+        blocks can still be called on their own for inspection (``model.backbone[0](img)``): inference semantics (running
+        BN statistics), no autograd -- see YOLOV5m.run_submodule."""
+        net = _OWNERS.get(id(self))
+        if net is None or not isinstance(self, (CBL, Bottleneck, C3, SPPF)) or not any(m is self for m in net.modules()):
+            raise _lib.YBError("this sub-module holds parameters only; call YOLOV5m.forward (fused sm_100a engine)")
+        return net.run_submodule(self, x)
 
 
 class _BN(nn.Module):
@@ -878,6 +888,11 @@ class _Engine:
             _lib.check(L.yb_prep_input(x.data_ptr(), dt, self.B, self.H, self.W, self.x16.t.data_ptr(), st))
         else:  # multi-scale training: bilinear resample fused into the stem staging (training_utils.py:11-28)
             _lib.check(L.yb_prep_input_resized(x.data_ptr(), dt, self.B, Hs, Ws, self.H, self.W, self.x16.t.data_ptr(), st))
+        self._run_fwd_ops(st)
+        return self.outs
+
+    def _run_fwd_ops(self, st):
+        L = self.L
         if self._fold:
             # running statistics -> (scale, shift) of every conv epilogue, re-read on every forward like nn.BatchNorm2d does
             eps = tuple(float(f[7].eps) for f in self._fold)
@@ -890,7 +905,6 @@ class _Engine:
             _lib.check(L.yb_bn_fold_batch(self._fold_dev.data_ptr(), len(self._fold), st))
         for op in self.fwd_ops:
             op(st)
-        return self.outs
 
     def run_backward(self, gflat):
         st = _lib.stream()
@@ -912,6 +926,57 @@ class _Engine:
                 self.L.yb_plan_destroy(p)
         except Exception:
             pass
+
+
+class _SubEngine(_Engine):
+    """Inference plan of ONE block (CBL / Bottleneck / C3 / SPPF) called on its own (reference model.py:27,49,89,106):
+    NCHW float input -> NHWC bf16 -> the block's fused kernels with folded BatchNorm -> NCHW float32."""
+
+    def __init__(self, net, mod, B, C, H, W):
+        self.mod, self.cin = mod, C
+        super().__init__(net, B, H, W, False, False)
+
+    def _build(self):
+        net, mod, B, H, W, C = self.net, self.mod, self.B, self.H, self.W, self.cin
+        self.outs, self.x16, self.xin = [], None, None
+        if isinstance(mod, CBL):
+            r = net._rec_of[mod.cbl[0]]
+            if r.is_stem:  # the 6x6/s2 stem reads the image through the space-to-depth staging (yb_prep_input)
+                if C != 3 or H % 2 or W % 2:
+                    raise ValueError(f"stem CBL: expected (B, 3, even H, even W), got C={C} H={H} W={W}")
+                self.x16 = self.buf(B, H // 2, W // 2 + 2, 16, grad=False)
+                xin, Ho, Wo = _StemView(self.x16), H // 2, W // 2
+            else:
+                if C != r.cin or H % r.stride or W % r.stride:
+                    raise ValueError(f"CBL: expected {r.cin} input channels and a size divisible by {r.stride}")
+                self.xin = self.buf(B, H, W, C, grad=False)
+                xin, Ho, Wo = self.xin.v(), H // r.stride, W // r.stride
+            self.out = self.buf(B, Ho, Wo, r.cout, grad=False)
+            self.cbl(mod, xin, self.out.v())
+            return
+        cin = net._rec_of[mod.c1.cbl[0]].cin
+        if C != cin:
+            raise ValueError(f"{type(mod).__name__}: expected {cin} input channels, got {C}")
+        self.xin = self.buf(B, H, W, C, grad=False)
+        if isinstance(mod, Bottleneck):  # model.py:49: c2(c1(x)) + x
+            cout = net._rec_of[mod.c2.cbl[0]].cout
+            h = self.buf(B, H, W, net._rec_of[mod.c1.cbl[0]].cout, grad=False)
+            self.out = self.buf(B, H, W, cout, grad=False)
+            self.cbl(mod.c1, self.xin.v(), h.v())
+            self.cbl(mod.c2, h.v(), self.out.v(), res=self.xin.v())
+        else:
+            self.out = self.buf(B, H, W, net._rec_of[mod.c_out.cbl[0]].cout, grad=False)
+            (self.c3 if isinstance(mod, C3) else self.sppf)(mod, self.xin.v(), self.out.v())
+
+    def run_forward(self, x):
+        L, st = self.L, _lib.stream()
+        if self.x16 is not None:
+            dt = 0 if x.dtype == torch.float32 else 1
+            _lib.check(L.yb_prep_input(x.data_ptr(), dt, self.B, self.H, self.W, self.x16.t.data_ptr(), st))
+        else:
+            self.xin.t.copy_(x.permute(0, 2, 3, 1))  # layout + dtype plumbing (fp32 NCHW -> bf16 NHWC)
+        self._run_fwd_ops(st)
+        return self.out.t.permute(0, 3, 1, 2).float()
 
 
 class _NetFn(torch.autograd.Function):
@@ -999,6 +1064,9 @@ class YOLOV5m(nn.Module):
         # tcgen05 kernels.  A numerics instrument for BASELINE config 2 ("fp32 vs reference", 1e-3), not the fast path.
         self.parity = os.environ.get("YB_PARITY", "0") == "1"
         self._accumulate_grads = False  # set by trainer.TrainStep around the backward of an accumulated micro-batch
+        for m in self.modules():  # blocks called on their own route to run_submodule (registry: nothing added to the modules)
+            if isinstance(m, (CBL, Bottleneck, C3, SPPF)):
+                _OWNERS[id(m)] = self
         self._flatten()
 
     # -- flat parameter storage -----------------------------------------------------------------
@@ -1205,6 +1273,33 @@ class YOLOV5m(nn.Module):
         else:
             self._engines[key] = self._engines.pop(key)  # most recently used last
         return e
+
+    def run_submodule(self, mod, x):
+        """``mod(x)`` for a CBL / Bottleneck / C3 / SPPF block of this network (reference model.py:27,49,89,106), e.g.
+        ``model.backbone[0](img)`` for feature inspection.  Inference only: BatchNorm uses its running statistics and the
+        result carries no autograd graph -- a block in training mode under grad raises instead of returning a tensor that
+        silently would not train (train through YOLOV5m.forward).  bf16 arithmetic like the full forward."""
+        if mod.training and torch.is_grad_enabled():
+            raise _lib.YBError("sub-module calls are inference-only on the B200 engine: use model.eval() / torch.no_grad(), "
+                               "or train through YOLOV5m.forward")
+        if not (torch.is_tensor(x) and x.is_cuda and x.dim() == 4 and x.device == self._pflat.device):
+            raise _lib.YBError("sub-module input must be a (B, C, H, W) CUDA tensor on the model's device (no CPU fallback)")
+        if x.dtype not in (torch.float32, torch.uint8):
+            x = x.float()
+        x = x.contiguous()
+        B, C, H, W = (int(v) for v in x.shape)
+        with torch.cuda.device(self._pflat.device), torch.no_grad():
+            self.refresh_packed()
+            key = ("sub", id(mod), B, C, H, W)
+            eng = self._engines.get(key)
+            if eng is None:
+                eng = _SubEngine(self, mod, B, C, H, W)
+                while self._engines and sum(v.nbytes for v in self._engines.values()) + eng.nbytes > self._ENGINE_CACHE_BYTES:
+                    self._engines.pop(next(iter(self._engines)))
+                self._engines[key] = eng
+            else:
+                self._engines[key] = self._engines.pop(key)
+            return eng.run_forward(x)
 
     def forward(self, x, size=None):
         """x: (B,3,H,W) float32 in [0,1] or uint8.  ``size=(h, w)`` (extension, both % 32 == 0): run the network on the
