@@ -33,15 +33,36 @@ struct EpiArgs {
   int act, out_kind, Cout, H, W, head_na, head_no;
   int ss_vec;  // scale / shift readable as aligned float4 runs of 16 (Cout % 16 == 0, 16-byte aligned pointers)
 };
-template <class P>
+// MODE: kernel instantiations for bf16 NHWC outputs with direct stores (every conv of the production train step and of
+// the inference forward except the three head convs).  What an instantiation cannot need is a compile-time constant, so the
+// loop the common layers run does not carry the fp32 / head / accumulate / TMA-store code, nor the paths of the other two
+// roles (measured: the extra code of an unused path costs every layer 1-3 %):
+//   0 = everything (heads, fp32 parity outputs, TMA store, any epilogue combination)
+//   1 = train fprop: raw bf16 output + BN statistics, no affine / activation / addend
+//   2 = dgrad: bf16 output, optional addend, no statistics / affine / activation
+//   3 = inference fprop: folded scale + shift, activation, optional addend, no statistics
+enum { EPI_FULL = 0, EPI_TRAIN = 1, EPI_DGRAD = 2, EPI_EVAL = 3 };
+template <int MODE = 0, class P>
 __device__ __forceinline__ EpiArgs load_epi_args(const P& p) {
   EpiArgs e;
   e.head_scratch = nullptr;
-  e.stats = p.stats; e.scale = p.scale; e.shift = p.shift; e.addend = p.addend; e.out = p.out;
-  e.act = p.act; e.out_kind = p.out_kind; e.Cout = p.Cout; e.H = p.H; e.W = p.W; e.head_na = p.head_na; e.head_no = p.head_no;
-  keep_in_reg(e.stats); keep_in_reg(e.scale); keep_in_reg(e.shift); keep_in_reg(e.addend); keep_in_reg(e.out);
-  keep_in_reg(e.act); keep_in_reg(e.out_kind); keep_in_reg(e.Cout); keep_in_reg(e.H); keep_in_reg(e.W);
-  keep_in_reg(e.head_na); keep_in_reg(e.head_no);
+  e.stats = (MODE == EPI_DGRAD || MODE == EPI_EVAL) ? nullptr : p.stats;
+  e.scale = (MODE == EPI_TRAIN || MODE == EPI_DGRAD) ? nullptr : p.scale;
+  e.shift = (MODE == EPI_TRAIN || MODE == EPI_DGRAD) ? nullptr : p.shift;
+  e.addend = MODE == EPI_TRAIN ? nullptr : p.addend;
+  e.out = p.out;
+  e.act = (MODE == EPI_TRAIN || MODE == EPI_DGRAD) ? 0 : p.act;
+  e.out_kind = MODE != EPI_FULL ? (int)OUT_BF16 : p.out_kind; e.Cout = p.Cout; e.H = p.H; e.W = p.W;
+  e.head_na = MODE != EPI_FULL ? 0 : p.head_na; e.head_no = MODE != EPI_FULL ? 1 : p.head_no;
+  keep_in_reg(e.out); keep_in_reg(e.Cout); keep_in_reg(e.H); keep_in_reg(e.W);
+  if (MODE == EPI_FULL || MODE == EPI_TRAIN) keep_in_reg(e.stats);
+  if (MODE == EPI_FULL || MODE == EPI_EVAL) {
+    keep_in_reg(e.scale); keep_in_reg(e.shift); keep_in_reg(e.act);
+  }
+  if (MODE != EPI_TRAIN) keep_in_reg(e.addend);
+  if (MODE == EPI_FULL) {
+    keep_in_reg(e.out_kind); keep_in_reg(e.head_na); keep_in_reg(e.head_no);
+  }
   e.ss_vec = (p.scale != nullptr && p.shift != nullptr && (p.Cout & 15) == 0 &&
               ((reinterpret_cast<uintptr_t>(p.scale) | reinterpret_cast<uintptr_t>(p.shift)) & 15) == 0) ? 1 : 0;
   keep_in_reg(e.ss_vec);

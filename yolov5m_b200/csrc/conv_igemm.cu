@@ -48,6 +48,7 @@ __device__ __forceinline__ TileCoord decode_tile(const TileDec& d, int t) {
   return c;
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -87,7 +88,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       for (int i = 0; i < p.ngroups; ++i) tma_prefetch_desc(&p.tmO[i]);
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
-  if (p.stats != nullptr && warp >= 4) {
+  if (MODE != EPI_DGRAD && MODE != EPI_EVAL && p.stats != nullptr && warp >= 4) {
     for (int i = threadIdx.x - 128; i < 4 * 2 * p.Cout; i += kEpiThreads) s_stats[i] = 0.f;
   }
   tc_fence_before();
@@ -197,8 +198,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     const int pw = r % p.PW;
     float* my_stats = s_stats + (size_t)q * 2 * p.Cout;
     // register copies of everything the per-tile loop reads (see keep_in_reg)
-    EpiArgs ea = load_epi_args(p);
-    if (p.out_kind == OUT_HEAD_F32) ea.head_scratch = s_stats;  // the head has no BN statistics: the region is the transpose scratch
+    EpiArgs ea = load_epi_args<MODE>(p);
+    if (MODE == EPI_FULL && p.out_kind == OUT_HEAD_F32) ea.head_scratch = s_stats;  // the head has no BN statistics: the region is the transpose scratch
     const TileDec td = load_tile_dec(p);
     int PW = p.PW, PH = p.PH, PN = p.PN, NB = p.NB, BN = p.BLOCK_N;
     int64_t t_on = p.PN * p.os_n, t_oh = p.PH * p.os_h, t_ow = p.PW * p.os_w;  // element strides between tiles
@@ -212,8 +213,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     // TMA-store epilogue: the bf16 tile is staged in shared memory (swizzled box layout) and leaves as one bulk tensor
     // store per 64-channel slab, issued by one thread; per-thread st.global rows (32 sectors per warp instruction) were the
     // top stall of every small-K layer (store back-pressure)
-    int tma_store = p.tma_store, x32 = p.epi_x32;
-    keep_in_reg(tma_store);
+    int tma_store = MODE != EPI_FULL ? 0 : p.tma_store, x32 = p.epi_x32;
+    if (MODE == EPI_FULL) keep_in_reg(tma_store);
     keep_in_reg(x32);
     uint8_t* stage_row = tma_store ? o_stage + (size_t)r * 128 : nullptr;
     const bool issuer = threadIdx.x == 128;
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       }
     }
     if (tma_store && issuer) bulk_wait_group0();  // all stores complete before the CTA (and its shared memory) goes away
-    if (p.stats != nullptr) {
+    if (MODE != EPI_DGRAD && MODE != EPI_EVAL && p.stats != nullptr) {
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       float* dst = p.stats + (size_t)blockIdx.x * 2 * p.Cout;
       for (int i = threadIdx.x - 128; i < 2 * p.Cout; i += kEpiThreads) {
@@ -580,10 +581,26 @@ int conv_run(const ConvPlan& pl, cudaStream_t st) {
   if (pl.kind == 1) return conv_patch_run(pl, st);
   static bool attr_set = false;
   if (!attr_set) {
-    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<EPI_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<EPI_TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<EPI_DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<EPI_EVAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  YB_CHECK_CUDA(launch_pdl(conv_igemm_kernel, dim3(pl.grid), dim3(kThreads), pl.smem, st, pl.kp));
+  const auto& kq = pl.kp;
+  int mode = EPI_FULL;
+  if (kq.out_kind == OUT_BF16 && !kq.tma_store && conv_lean_enabled()) {
+    const bool affine = kq.scale != nullptr || kq.shift != nullptr || kq.act != 0;
+    if (kq.stats != nullptr && !affine && kq.addend == nullptr) mode = EPI_TRAIN;
+    else if (kq.stats == nullptr && !affine) mode = EPI_DGRAD;
+    else if (kq.stats == nullptr) mode = EPI_EVAL;
+  }
+  switch (mode) {
+    case EPI_TRAIN: YB_CHECK_CUDA(launch_pdl(conv_igemm_kernel<EPI_TRAIN>, dim3(pl.grid), dim3(kThreads), pl.smem, st, pl.kp)); break;
+    case EPI_DGRAD: YB_CHECK_CUDA(launch_pdl(conv_igemm_kernel<EPI_DGRAD>, dim3(pl.grid), dim3(kThreads), pl.smem, st, pl.kp)); break;
+    case EPI_EVAL: YB_CHECK_CUDA(launch_pdl(conv_igemm_kernel<EPI_EVAL>, dim3(pl.grid), dim3(kThreads), pl.smem, st, pl.kp)); break;
+    default: YB_CHECK_CUDA(launch_pdl(conv_igemm_kernel<EPI_FULL>, dim3(pl.grid), dim3(kThreads), pl.smem, st, pl.kp)); break;
+  }
   YB_LAUNCHED();
   return 0;
 }

@@ -20,6 +20,16 @@ struct TView {
 };
 // The stem's operand (ks code 31, Cin = 48, pitch = 16): the three horizontal taps of the 16-channel space-to-depth image
 // are a VIEW of its row-padded storage (N, H, W + 2, 16) -- 48 contiguous values starting at padded column w
+// YB_CONV_LEAN=0 runs every launch through the full kernel instantiation (A/B knob)
+inline bool conv_lean_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("YB_CONV_LEAN");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+
 inline void stem_view(TView& v, int ks) {
   if (ks == 31 && v.pitch < v.C) v.row_pitch = (long)(v.W + 2) * v.pitch;
 }

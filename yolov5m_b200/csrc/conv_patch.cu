@@ -52,6 +52,7 @@ __device__ __forceinline__ STile decode_stile(const STileDec& d, int t) {
   return c;
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_constant__ PatchKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
       for (int i = 0; i < p.ngroups; ++i) tma_prefetch_desc(&p.tmO[i]);
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
-  if (p.stats != nullptr && warp >= 4) {
+  if (MODE != EPI_DGRAD && MODE != EPI_EVAL && p.stats != nullptr && warp >= 4) {
     for (int i = threadIdx.x - 128; i < 4 * 2 * p.Cout; i += kEpiThreads) s_stats[i] = 0.f;
   }
   tc_fence_before();
@@ -264,15 +265,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
     const int phh = r >> 3, pw = r & 7;
     float* my_stats = s_stats + (size_t)q * 2 * p.Cout;
     // register copies of everything the per-tile loop reads (see keep_in_reg in conv_epilogue.cuh)
-    const EpiArgs ea = load_epi_args(p);
+    const EpiArgs ea = load_epi_args<MODE>(p);
     const STileDec td = load_stile_dec(p);
     int BN = p.BLOCK_N, TWl = p.TW, THl = p.TH;
     int64_t os_n = p.os_n, os_h = p.os_h, os_w = p.os_w, as_n = p.as_n, as_h = p.as_h, as_w = p.as_w;
     keep_in_reg(BN); keep_in_reg(TWl); keep_in_reg(THl);
     keep_in_reg(os_n); keep_in_reg(os_h); keep_in_reg(os_w); keep_in_reg(as_n); keep_in_reg(as_h); keep_in_reg(as_w);
     const int nchunks = BN / 16;
-    int tma_store = p.tma_store, x32 = p.epi_x32;
-    keep_in_reg(tma_store);
+    int tma_store = MODE != EPI_FULL ? 0 : p.tma_store, x32 = p.epi_x32;
+    if (MODE == EPI_FULL) keep_in_reg(tma_store);
     keep_in_reg(x32);
     const int units = x32 ? nchunks / 2 : nchunks;
     uint8_t* stage_row = o_stage + (size_t)r * 128;
@@ -366,7 +367,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
       if (lane == 0) mbar_arrive(&tempty_bar[ab]);
     }
     if (tma_store && issuer) bulk_wait_group0();  // all stores complete before the CTA (and its shared memory) goes away
-    if (p.stats != nullptr) {
+    if (MODE != EPI_DGRAD && MODE != EPI_EVAL && p.stats != nullptr) {
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       float* dst = p.stats + (size_t)blockIdx.x * 2 * p.Cout;
       for (int i = threadIdx.x - 128; i < 2 * p.Cout; i += kEpiThreads) {
@@ -704,10 +705,26 @@ int conv_patch_plan_dgrad(ConvPlan& pl, const TView& dy, const bf16* wt, int ks,
 int conv_patch_run(const ConvPlan& pl, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_patch_kernel<EPI_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_patch_kernel<EPI_TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_patch_kernel<EPI_DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_patch_kernel<EPI_EVAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  YB_CHECK_CUDA(launch_pdl(conv_patch_kernel, dim3(pl.grid), dim3(kThreads), pl.smem, st, pl.pp));
+  const auto& kq = pl.pp;
+  int mode = EPI_FULL;
+  if (kq.out_kind == OUT_BF16 && !kq.tma_store && conv_lean_enabled()) {
+    const bool affine = kq.scale != nullptr || kq.shift != nullptr || kq.act != 0;
+    if (kq.stats != nullptr && !affine && kq.addend == nullptr) mode = EPI_TRAIN;
+    else if (kq.stats == nullptr && !affine) mode = EPI_DGRAD;
+    else if (kq.stats == nullptr) mode = EPI_EVAL;
+  }
+  switch (mode) {
+    case EPI_TRAIN: YB_CHECK_CUDA(launch_pdl(conv_patch_kernel<EPI_TRAIN>, dim3(pl.grid), dim3(kThreads), pl.smem, st, pl.pp)); break;
+    case EPI_DGRAD: YB_CHECK_CUDA(launch_pdl(conv_patch_kernel<EPI_DGRAD>, dim3(pl.grid), dim3(kThreads), pl.smem, st, pl.pp)); break;
+    case EPI_EVAL: YB_CHECK_CUDA(launch_pdl(conv_patch_kernel<EPI_EVAL>, dim3(pl.grid), dim3(kThreads), pl.smem, st, pl.pp)); break;
+    default: YB_CHECK_CUDA(launch_pdl(conv_patch_kernel<EPI_FULL>, dim3(pl.grid), dim3(kThreads), pl.smem, st, pl.pp)); break;
+  }
   YB_LAUNCHED();
   return 0;
 }
