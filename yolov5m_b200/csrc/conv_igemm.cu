@@ -48,7 +48,7 @@ __device__ __forceinline__ TileCoord decode_tile(const TileDec& d, int t) {
   return c;
 }
 
-template <int MODE>
+template <int MODE, bool X32>
 __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -213,9 +213,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     // TMA-store epilogue: the bf16 tile is staged in shared memory (swizzled box layout) and leaves as one bulk tensor
     // store per 64-channel slab, issued by one thread; per-thread st.global rows (32 sectors per warp instruction) were the
     // top stall of every small-K layer (store back-pressure)
-    int tma_store = MODE != EPI_FULL ? 0 : p.tma_store, x32 = p.epi_x32;
+    int tma_store = MODE != EPI_FULL ? 0 : p.tma_store, x32 = MODE == EPI_FULL ? p.epi_x32 : (X32 ? 1 : 0);  // compile-time in the role instantiations
     if (MODE == EPI_FULL) keep_in_reg(tma_store);
-    keep_in_reg(x32);
+    if (MODE == EPI_FULL) keep_in_reg(x32);
     uint8_t* stage_row = tma_store ? o_stage + (size_t)r * 128 : nullptr;
     const bool issuer = threadIdx.x == 128;
     int it = 0;
@@ -581,10 +581,14 @@ int conv_run(const ConvPlan& pl, cudaStream_t st) {
   if (pl.kind == 1) return conv_patch_run(pl, st);
   static bool attr_set = false;
   if (!attr_set) {
-    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<EPI_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<EPI_TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<EPI_DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<EPI_EVAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    const int big = 227 * 1024;
+    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<EPI_FULL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<EPI_TRAIN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<EPI_TRAIN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<EPI_DGRAD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<EPI_DGRAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<EPI_EVAL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<EPI_EVAL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     attr_set = true;
   }
   const auto& kq = pl.kp;
@@ -595,12 +599,16 @@ int conv_run(const ConvPlan& pl, cudaStream_t st) {
     else if (kq.stats == nullptr && !affine) mode = EPI_DGRAD;
     else if (kq.stats == nullptr) mode = EPI_EVAL;
   }
+#define YB_LAUNCH_ROLE(M, X) YB_CHECK_CUDA(launch_pdl(conv_igemm_kernel<M, X>, dim3(pl.grid), dim3(kThreads), pl.smem, st, pl.kp))
+  const bool x32 = kq.epi_x32 != 0;
   switch (mode) {
-    case EPI_TRAIN: YB_CHECK_CUDA(launch_pdl(conv_igemm_kernel<EPI_TRAIN>, dim3(pl.grid), dim3(kThreads), pl.smem, st, pl.kp)); break;
-    case EPI_DGRAD: YB_CHECK_CUDA(launch_pdl(conv_igemm_kernel<EPI_DGRAD>, dim3(pl.grid), dim3(kThreads), pl.smem, st, pl.kp)); break;
-    case EPI_EVAL: YB_CHECK_CUDA(launch_pdl(conv_igemm_kernel<EPI_EVAL>, dim3(pl.grid), dim3(kThreads), pl.smem, st, pl.kp)); break;
-    default: YB_CHECK_CUDA(launch_pdl(conv_igemm_kernel<EPI_FULL>, dim3(pl.grid), dim3(kThreads), pl.smem, st, pl.kp)); break;
+    case EPI_TRAIN: if (x32) YB_LAUNCH_ROLE(EPI_TRAIN, true); else YB_LAUNCH_ROLE(EPI_TRAIN, false); break;
+    case EPI_DGRAD: if (x32) YB_LAUNCH_ROLE(EPI_DGRAD, true); else YB_LAUNCH_ROLE(EPI_DGRAD, false); break;
+    case EPI_EVAL: if (x32) YB_LAUNCH_ROLE(EPI_EVAL, true); else YB_LAUNCH_ROLE(EPI_EVAL, false); break;
+    default: YB_LAUNCH_ROLE(EPI_FULL, false); break;
   }
+#undef YB_LAUNCH_ROLE
+
   YB_LAUNCHED();
   return 0;
 }
