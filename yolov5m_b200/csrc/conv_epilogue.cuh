@@ -32,6 +32,7 @@ struct EpiArgs {
   void* out;
   int act, out_kind, Cout, H, W, head_na, head_no;
   int ss_vec;  // scale / shift readable as aligned float4 runs of 16 (Cout % 16 == 0, 16-byte aligned pointers)
+  int affine;  // 0 = none, 1 = bias only, 2 = scale + shift (see conv_epilogue_affine)
 };
 // MODE: kernel instantiations for bf16 NHWC outputs with direct stores (every conv of the production train step and of
 // the inference forward except the three head convs).  What an instantiation cannot need is a compile-time constant, so the
@@ -51,21 +52,24 @@ __device__ __forceinline__ EpiArgs load_epi_args(const P& p) {
   e.shift = (MODE == EPI_TRAIN || MODE == EPI_DGRAD) ? nullptr : p.shift;
   e.addend = MODE == EPI_TRAIN ? nullptr : p.addend;
   e.out = p.out;
-  e.act = (MODE == EPI_TRAIN || MODE == EPI_DGRAD) ? 0 : p.act;
+  e.act = (MODE == EPI_TRAIN || MODE == EPI_DGRAD) ? 0 : (MODE == EPI_EVAL ? 1 : p.act);
   e.out_kind = MODE != EPI_FULL ? (int)OUT_BF16 : p.out_kind; e.Cout = p.Cout; e.H = p.H; e.W = p.W;
   e.head_na = MODE != EPI_FULL ? 0 : p.head_na; e.head_no = MODE != EPI_FULL ? 1 : p.head_no;
   keep_in_reg(e.out); keep_in_reg(e.Cout); keep_in_reg(e.H); keep_in_reg(e.W);
   if (MODE == EPI_FULL || MODE == EPI_TRAIN) keep_in_reg(e.stats);
   if (MODE == EPI_FULL || MODE == EPI_EVAL) {
-    keep_in_reg(e.scale); keep_in_reg(e.shift); keep_in_reg(e.act);
+    keep_in_reg(e.scale); keep_in_reg(e.shift);
   }
+  if (MODE == EPI_FULL) keep_in_reg(e.act);
   if (MODE != EPI_TRAIN) keep_in_reg(e.addend);
   if (MODE == EPI_FULL) {
     keep_in_reg(e.out_kind); keep_in_reg(e.head_na); keep_in_reg(e.head_no);
   }
-  e.ss_vec = (p.scale != nullptr && p.shift != nullptr && (p.Cout & 15) == 0 &&
+  e.ss_vec = MODE == EPI_EVAL ? 1 : (p.scale != nullptr && p.shift != nullptr && (p.Cout & 15) == 0 &&
               ((reinterpret_cast<uintptr_t>(p.scale) | reinterpret_cast<uintptr_t>(p.shift)) & 15) == 0) ? 1 : 0;
-  keep_in_reg(e.ss_vec);
+  if (MODE != EPI_EVAL) keep_in_reg(e.ss_vec);
+  e.affine = (MODE == EPI_TRAIN || MODE == EPI_DGRAD) ? 0 : (MODE == EPI_EVAL ? 2 : (p.scale != nullptr ? 2 : (p.shift != nullptr ? 1 : 0)));
+  if (MODE == EPI_FULL) keep_in_reg(e.affine);
   return e;
 }
 
@@ -79,9 +83,7 @@ struct EpiAffine {
 // (folded BN of the inference path).  Called BEFORE the wait on the TMEM load where the registers allow it, so that the
 // (L1-hit) latency overlaps the TMEM round trip: the first dependent FFMA / FADD was the top stall of the inference and
 // head epilogues (ncu source pages, round 2).
-__device__ __forceinline__ int conv_epilogue_affine_mode(const EpiArgs& p) {
-  return p.scale != nullptr ? 2 : (p.shift != nullptr ? 1 : 0);
-}
+__device__ __forceinline__ int conv_epilogue_affine_mode(const EpiArgs& p) { return p.affine; }
 __device__ __forceinline__ void conv_epilogue_affine(const EpiArgs& p, int mode, int col0, EpiAffine& a) {
   if (mode == 2 && p.ss_vec) {
     // eight 16-byte loads instead of 32 predicated scalar ones (the per-column predicates and loads were ~60 of the ~280

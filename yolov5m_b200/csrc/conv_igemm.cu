@@ -597,7 +597,9 @@ int conv_run(const ConvPlan& pl, cudaStream_t st) {
     const bool affine = kq.scale != nullptr || kq.shift != nullptr || kq.act != 0;
     if (kq.stats != nullptr && !affine && kq.addend == nullptr) mode = EPI_TRAIN;
     else if (kq.stats == nullptr && !affine) mode = EPI_DGRAD;
-    else if (kq.stats == nullptr) mode = EPI_EVAL;
+    else if (kq.stats == nullptr && kq.act == 1 && kq.scale != nullptr && kq.shift != nullptr && kq.Cout % 16 == 0 &&
+             ((reinterpret_cast<uintptr_t>(kq.scale) | reinterpret_cast<uintptr_t>(kq.shift)) & 15) == 0)
+      mode = EPI_EVAL;  // folded BatchNorm + SiLU with 16-byte readable parameters: what every inference CBL has
   }
 #define YB_LAUNCH_ROLE(M, X) YB_CHECK_CUDA(launch_pdl(conv_igemm_kernel<M, X>, dim3(pl.grid), dim3(kThreads), pl.smem, st, pl.kp))
   const bool x32 = kq.epi_x32 != 0;
