@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       for (int i = 0; i < p.ngroups; ++i) tma_prefetch_desc(&p.tmO[i]);
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
-  if (MODE != EPI_DGRAD && MODE != EPI_EVAL && p.stats != nullptr && warp >= 4) {
+  if (MODE != EPI_DGRAD && MODE != EPI_EVAL && MODE != EPI_HEAD && p.stats != nullptr && warp >= 4) {
     for (int i = threadIdx.x - 128; i < 4 * 2 * p.Cout; i += kEpiThreads) s_stats[i] = 0.f;
   }
   tc_fence_before();
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     float* my_stats = s_stats + (size_t)q * 2 * p.Cout;
     // register copies of everything the per-tile loop reads (see keep_in_reg)
     EpiArgs ea = load_epi_args<MODE>(p);
-    if (MODE == EPI_FULL && p.out_kind == OUT_HEAD_F32) ea.head_scratch = s_stats;  // the head has no BN statistics: the region is the transpose scratch
+    if ((MODE == EPI_FULL && p.out_kind == OUT_HEAD_F32) || MODE == EPI_HEAD) ea.head_scratch = s_stats;  // the head has no BN statistics: the region is the transpose scratch
     const TileDec td = load_tile_dec(p);
     int PW = p.PW, PH = p.PH, PN = p.PN, NB = p.NB, BN = p.BLOCK_N;
     int64_t t_on = p.PN * p.os_n, t_oh = p.PH * p.os_h, t_ow = p.PW * p.os_w;  // element strides between tiles
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       }
     }
     if (tma_store && issuer) bulk_wait_group0();  // all stores complete before the CTA (and its shared memory) goes away
-    if (MODE != EPI_DGRAD && MODE != EPI_EVAL && p.stats != nullptr) {
+    if (MODE != EPI_DGRAD && MODE != EPI_EVAL && MODE != EPI_HEAD && p.stats != nullptr) {
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       float* dst = p.stats + (size_t)blockIdx.x * 2 * p.Cout;
       for (int i = threadIdx.x - 128; i < 2 * p.Cout; i += kEpiThreads) {
@@ -589,6 +589,7 @@ int conv_run(const ConvPlan& pl, cudaStream_t st) {
     YB_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<EPI_DGRAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     YB_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<EPI_EVAL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     YB_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<EPI_EVAL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<EPI_HEAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     attr_set = true;
   }
   const auto& kq = pl.kp;
@@ -601,12 +602,16 @@ int conv_run(const ConvPlan& pl, cudaStream_t st) {
              ((reinterpret_cast<uintptr_t>(kq.scale) | reinterpret_cast<uintptr_t>(kq.shift)) & 15) == 0)
       mode = EPI_EVAL;  // folded BatchNorm + SiLU with 16-byte readable parameters: what every inference CBL has
   }
+  if (kq.out_kind == OUT_HEAD_F32 && kq.epi_x32 && conv_lean_enabled() && kq.stats == nullptr && kq.scale == nullptr &&
+      kq.shift != nullptr && kq.act == 0 && kq.addend == nullptr)
+    mode = EPI_HEAD;
 #define YB_LAUNCH_ROLE(M, X) YB_CHECK_CUDA(launch_pdl(conv_igemm_kernel<M, X>, dim3(pl.grid), dim3(kThreads), pl.smem, st, pl.kp))
   const bool x32 = kq.epi_x32 != 0;
   switch (mode) {
     case EPI_TRAIN: if (x32) YB_LAUNCH_ROLE(EPI_TRAIN, true); else YB_LAUNCH_ROLE(EPI_TRAIN, false); break;
     case EPI_DGRAD: if (x32) YB_LAUNCH_ROLE(EPI_DGRAD, true); else YB_LAUNCH_ROLE(EPI_DGRAD, false); break;
     case EPI_EVAL: if (x32) YB_LAUNCH_ROLE(EPI_EVAL, true); else YB_LAUNCH_ROLE(EPI_EVAL, false); break;
+    case EPI_HEAD: YB_LAUNCH_ROLE(EPI_HEAD, true); break;
     default: YB_LAUNCH_ROLE(EPI_FULL, false); break;
   }
 #undef YB_LAUNCH_ROLE
