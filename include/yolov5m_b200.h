@@ -89,6 +89,10 @@ void* yb_conv_wgrad_plan(const void* x, int N, int H, int W, int Cin, int64_t x_
                          int64_t dy_pitch, int ks, int stride, float* workspace, int64_t workspace_floats,
                          int max_splits);
 int yb_wgrad_plan_run(void* plan, float* dw, int out_rows, const int* index_map, int accumulate, void* stream);
+/* the same in two halves, so that a caller can order them across streams: phase 1 = the split-K tensor-core kernel (writes the
+ * plan's workspace), phase 2 = the fixed-order reduction of the partials into dw (reads the workspace), phase 0 = both.
+ * The workspace may be overwritten by another plan only after phase 2 has completed. */
+int yb_wgrad_plan_run_phase(void* plan, float* dw, int out_rows, const int* index_map, int accumulate, int phase, void* stream);
 int yb_conv2d_wgrad(const void* x, int N, int H, int W, int Cin, int64_t x_pitch, const void* dy, int Cout,
                     int64_t dy_pitch, int ks, int stride, float* workspace, int64_t workspace_floats, int max_splits,
                     float* dw, int out_rows, const int* index_map, int accumulate, void* stream);

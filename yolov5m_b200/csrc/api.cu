@@ -145,6 +145,13 @@ int yb_wgrad_plan_run(void* plan, float* dw, int out_rows, const int* index_map,
   return wgrad_run(pl->wgrad, dw, out_rows, index_map, accumulate, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int yb_wgrad_plan_run_phase(void* plan, float* dw, int out_rows, const int* index_map, int accumulate, int phase, void* stream) {
+  YbPlan* pl = reinterpret_cast<YbPlan*>(plan);
+  YB_REQUIRE(pl != nullptr && pl->kind == 1, "yb_wgrad_plan_run_phase: not a wgrad plan");
+  YB_REQUIRE(phase >= 0 && phase <= 2, "yb_wgrad_plan_run_phase: phase=%d", phase);
+  return wgrad_run(pl->wgrad, dw, out_rows, index_map, accumulate, reinterpret_cast<cudaStream_t>(stream), phase);
+}
+
 int yb_conv2d_wgrad(const void* x, int N, int H, int W, int Cin, int64_t x_pitch, const void* dy, int Cout,
                     int64_t dy_pitch, int ks, int stride, float* workspace, int64_t workspace_floats, int max_splits,
                     float* dw, int out_rows, const int* index_map, int accumulate, void* stream) {

@@ -486,19 +486,24 @@ int wgrad_max_grid() {
   return g_sms;
 }
 
-int wgrad_run(const WgradPlan& pl, float* out, int out_rows, const int* map, int accumulate, cudaStream_t st) {
+// phase: 0 = both kernels on `st`; 1 = the tcgen05 split-K kernel only; 2 = the partial reduction only (the caller orders the
+// two across streams: the reduction is a small L2-resident kernel that can run beside the next layer's backward passes)
+int wgrad_run(const WgradPlan& pl, float* out, int out_rows, const int* map, int accumulate, cudaStream_t st, int phase) {
   static bool attr_set = false;
   if (!attr_set) {
     YB_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   YB_REQUIRE(out_rows > 0 && out_rows <= pl.kp.Cout, "wgrad: out_rows=%d", out_rows);
-  if (pl.kind == 1) {
-    if (wgrad_patch_launch(pl, st)) return -2;
-  } else {
-    YB_CHECK_CUDA(launch_pdl(conv_wgrad_kernel, dim3(pl.grid), dim3(kThreads), pl.smem, st, pl.kp));
-    YB_LAUNCHED();
+  if (phase != 2) {
+    if (pl.kind == 1) {
+      if (wgrad_patch_launch(pl, st)) return -2;
+    } else {
+      YB_CHECK_CUDA(launch_pdl(conv_wgrad_kernel, dim3(pl.grid), dim3(kThreads), pl.smem, st, pl.kp));
+      YB_LAUNCHED();
+    }
   }
+  if (phase == 1) return 0;
   const WgradKParams& kp = pl.kp;  // the patch planner fills the reduce-relevant fields of kp as well
   // split-lanes: enough threads to fill the machine even when the output is tiny and the split count large
   int SL = 1;

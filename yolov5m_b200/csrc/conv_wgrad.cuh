@@ -68,7 +68,7 @@ int wgrad_plan(WgradPlan& pl, const TView& x, const TView& dy, int ks, int strid
                size_t partial_floats, int max_splits);
 // runs the split-K GEMM and the ordered reduction + transpose:
 //   out[map ? map[i] : i] (+)= sum_s partial[s][tap*Cin_pad+ci][co],  i = co*ldo + tap*Cin + ci,  co < out_rows
-int wgrad_run(const WgradPlan& pl, float* out, int out_rows, const int* map, int accumulate, cudaStream_t st);
+int wgrad_run(const WgradPlan& pl, float* out, int out_rows, const int* map, int accumulate, cudaStream_t st, int phase = 0);
 // minimum workspace (one split) for a layer
 size_t wgrad_min_workspace_floats(int Cin, int Cout, int ks);
 

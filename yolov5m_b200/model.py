@@ -243,6 +243,17 @@ class _Engine:
             self.red_partial = torch.zeros(self.red_rows * 2 * cmax, device=self.dev, dtype=torch.float32)
             self.coef = torch.zeros(2 * cmax, device=self.dev, dtype=torch.float32)
             self.wg_ws = torch.empty(32 << 20, device=self.dev, dtype=torch.float32)
+            # The split-K reduction of a weight gradient (wgrad_reduce_kernel: small, reads L2-resident partials) runs on a
+            # second stream beside the next layer's backward kernels instead of serialising 74 short launches into the main
+            # stream.  Two workspaces alternate, so a wgrad kernel never waits for the reduction that read "its" buffer two
+            # layers ago; run_backward joins the stream before the gradient bucket is used.  YB_WGRAD_REDUCE_STREAM=0: off.
+            self.rstream = (torch.cuda.Stream(device=self.dev)
+                            if os.environ.get("YB_WGRAD_REDUCE_STREAM", "1") != "0" and not parity else None)
+            self.wg_ws2 = torch.empty_like(self.wg_ws) if self.rstream is not None else None
+            self._ws_toggle, self._plan_ws, self._rs_on = 0, {}, False
+            self._ws_mma_ev = [torch.cuda.Event(), torch.cuda.Event()]
+            self._ws_red_ev = [torch.cuda.Event(), torch.cuda.Event()]
+            self._ws_pending = [False, False]
             self.dy = None  # allocated after the forward build (max conv output size)
             self._dy_elems = 0
             # YB_WGRAD_STREAM=1 (experiment, off by default): weight-gradient kernels on a second stream, meant to overlap
@@ -277,9 +288,29 @@ class _Engine:
         e1.record()
         self.prof.append((kind, nbytes, e0, e1, nbytes))
 
+    def _next_ws(self):
+        """workspace of the next weight-gradient plan: (pointer, floats, buffer index)"""
+        if self.rstream is None:
+            return self.wg_ws.data_ptr(), self.wg_ws.numel(), 0
+        i = self._ws_toggle
+        self._ws_toggle ^= 1
+        t = self.wg_ws if i == 0 else self.wg_ws2
+        return t.data_ptr(), t.numel(), i
+
     def _wgrad(self, plan, st, flops, *args):
         if self.prof is None:
-            _lib.check(self.L.yb_wgrad_plan_run(plan, *args, st))
+            b = self._plan_ws.get(plan) if self._rs_on else None
+            if b is None:
+                _lib.check(self.L.yb_wgrad_plan_run(plan, *args, st))
+                return
+            if self._ws_pending[b]:
+                self._main.wait_event(self._ws_red_ev[b])  # the reduction that last read this workspace has finished
+            _lib.check(self.L.yb_wgrad_plan_run_phase(plan, *args, 1, st))
+            self._ws_mma_ev[b].record(self._main)
+            self.rstream.wait_event(self._ws_mma_ev[b])
+            _lib.check(self.L.yb_wgrad_plan_run_phase(plan, *args, 2, self.rstream.cuda_stream))
+            self._ws_red_ev[b].record(self.rstream)
+            self._ws_pending[b] = True
             return
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -698,8 +729,10 @@ class _Engine:
                 self.conv_flops["wgrad"] += flops
                 dyp = dyh.data_ptr()
                 npix = xin.npix
+                ws, wsn, wsi = self._next_ws()
                 wplan = _lib.checkp(L.yb_conv_wgrad_plan(xin.ptr, xin.N, xin.H, xin.W, xin.C, xin.pitch, dyp, HEAD_PAD,
                                                          HEAD_PAD, 1, 1, ws, wsn, 0))
+                self._plan_ws[wplan] = wsi
                 acc = 1 if self._contrib_state(xin) else 0
                 dplan = _lib.checkp(L.yb_conv_dgrad_plan(dyp, xin.N, xin.H, xin.W, HEAD_PAD, HEAD_PAD,
                                                          net._wdg.data_ptr() + 2 * r.wt_off, xin.C, 1, 1, xin.gptr,
@@ -757,8 +790,10 @@ class _Engine:
                     dplan = _lib.checkp(L.yb_conv_dgrad_plan(dy2, xin.N, xin.H, xin.W, 2 * C, 2 * C,
                                                              net._wdg.data_ptr() + 2 * pr["wt2"], xin.C, 1, 1, xin.gptr, xin.pitch,
                                                              addp, addl, 0))
+                    ws, wsn, wsi = self._next_ws()
                     wplan = _lib.checkp(L.yb_conv_wgrad_plan(xin.ptr, xin.N, xin.H, xin.W, xin.C, xin.pitch, dy2, 2 * C, 2 * C, 1, 1,
                                                              ws, wsn, 0))
+                    self._plan_ws[wplan] = wsi
                     self.plans += [dplan, wplan]
                     xin.buf.gw[xin.c0:xin.c0 + xin.C] = True
                 rows = ctypes.c_int(0)
@@ -830,8 +865,10 @@ class _Engine:
                             _lib.check(L.yb_wgrad_plan_run(pl, g + 4 * r.w_off, C, mapp, 1 if n_ else 0, st))
                     self._add_bwd_op(op, [(r.g_off, C), (r.b_off, C), (r.w_off, r.conv.weight.numel())])
                     continue
+                ws, wsn, wsi = self._next_ws()
                 wplan = _lib.checkp(L.yb_conv_wgrad_plan(xin.ptr, xin.N, xin.H, xin.W, xin.C, xin.pitch, dy_ptr, C, C, k, s,
                                                          ws, wsn, 0))
+                self._plan_ws[wplan] = wsi
                 self.plans.append(wplan)
                 dplan = None
                 if not r.is_stem:
@@ -912,6 +949,10 @@ class _Engine:
         self._main = torch.cuda.current_stream(self.dev)
         self._side_on = self.side is not None and self.prof is None  # the per-kernel timing pass stays on one stream
         hook = self.on_grad_chunks if not self._side_on and self.prof is None else None
+        # reductions on the second stream: not under the per-kernel timing pass, not with the whole wgrad already on a side
+        # stream, and not when chunks of the bucket are handed to an overlapped all-reduce as soon as the main stream wrote them
+        self._rs_on = self.rstream is not None and self.prof is None and not self._side_on and hook is None
+        self._ws_pending = [False, False]
         for i, op in enumerate(self.bwd_ops):
             op(st, g)
             if hook is not None and i in hook[0]:
@@ -919,6 +960,11 @@ class _Engine:
                     hook[1](c, gflat)  # this chunk of the bucket is final: its all-reduce overlaps the remaining ops
         if self._side_on:
             self._main.wait_stream(self.side)  # every weight gradient is in the bucket before all-reduce / optimiser
+        if self._rs_on:
+            for b in range(2):
+                if self._ws_pending[b]:
+                    self._main.wait_event(self._ws_red_ev[b])
+            self._ws_pending = [False, False]
 
     def __del__(self):
         try:
