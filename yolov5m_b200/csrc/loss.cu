@@ -374,6 +374,10 @@ __global__ void __launch_bounds__(256) loss_bwd_kernel(const __grid_constant__ L
             my_heads[a] = Ll.cell_head[cell];
             my_xs[a] = Ll.p[cell * P.no + 4];
           }
+        // sigmoid of this lane's own cells, once (the pixel loop below used to evaluate it on every lane for every pixel)
+#pragma unroll
+        for (int a = 0; a < kMaxNa; ++a)
+          if (a < P.na) my_xs[a] = sigmoid_acc(my_xs[a]);
       }
     }
     const int npx = (int)min(32L, pix_total - base);
@@ -433,7 +437,7 @@ __global__ void __launch_bounds__(256) loss_bwd_kernel(const __grid_constant__ L
         }
         tobj = L.row_val[last - 1];
       }
-      const float gobj = (sigmoid_acc(x) - tobj) * cobj;
+      const float gobj = (x - tobj) * cobj;  // x = sigmoid(objectness logit), evaluated by the owning lane above
       if (L.grad_f32 != nullptr) {
         float* go = L.grad_f32 + cell * P.no;
         if (lane == 4) f0 = gobj;
