@@ -43,37 +43,38 @@ struct EpiArgs {
 //   2 = dgrad: bf16 output, optional addend, no statistics / affine / activation
 //   3 = inference fprop: folded scale + shift, activation, optional addend, no statistics
 //   4 = head conv (igemm kernel only): fp32 (B, na, H, W, no) output through the per-warp transpose scratch, bias only
-enum { EPI_FULL = 0, EPI_TRAIN = 1, EPI_DGRAD = 2, EPI_EVAL = 3, EPI_HEAD = 4 };
+//   + EPI_NOADD (dgrad / inference fprop): the launch has no addend either
+enum { EPI_FULL = 0, EPI_TRAIN = 1, EPI_DGRAD = 2, EPI_EVAL = 3, EPI_HEAD = 4, EPI_NOADD = 8 };
 template <int MODE = 0, class P>
 __device__ __forceinline__ EpiArgs load_epi_args(const P& p) {
   EpiArgs e;
   e.head_scratch = nullptr;
-  e.stats = (MODE == EPI_DGRAD || MODE == EPI_EVAL || MODE == EPI_HEAD) ? nullptr : p.stats;
-  e.scale = (MODE == EPI_TRAIN || MODE == EPI_DGRAD || MODE == EPI_HEAD) ? nullptr : p.scale;
-  e.shift = (MODE == EPI_TRAIN || MODE == EPI_DGRAD) ? nullptr : p.shift;
-  e.addend = (MODE == EPI_TRAIN || MODE == EPI_HEAD) ? nullptr : p.addend;
+  e.stats = ((MODE & 7) == EPI_DGRAD || (MODE & 7) == EPI_EVAL || (MODE & 7) == EPI_HEAD) ? nullptr : p.stats;
+  e.scale = ((MODE & 7) == EPI_TRAIN || (MODE & 7) == EPI_DGRAD || (MODE & 7) == EPI_HEAD) ? nullptr : p.scale;
+  e.shift = ((MODE & 7) == EPI_TRAIN || (MODE & 7) == EPI_DGRAD) ? nullptr : p.shift;
+  e.addend = ((MODE & 7) == EPI_TRAIN || (MODE & 7) == EPI_HEAD || (MODE & EPI_NOADD)) ? nullptr : p.addend;
   e.out = p.out;
-  e.act = (MODE == EPI_TRAIN || MODE == EPI_DGRAD || MODE == EPI_HEAD) ? 0 : (MODE == EPI_EVAL ? 1 : p.act);
-  e.out_kind = MODE == EPI_HEAD ? (int)OUT_HEAD_F32 : (MODE != EPI_FULL ? (int)OUT_BF16 : p.out_kind);
+  e.act = ((MODE & 7) == EPI_TRAIN || (MODE & 7) == EPI_DGRAD || (MODE & 7) == EPI_HEAD) ? 0 : ((MODE & 7) == EPI_EVAL ? 1 : p.act);
+  e.out_kind = (MODE & 7) == EPI_HEAD ? (int)OUT_HEAD_F32 : ((MODE & 7) != EPI_FULL ? (int)OUT_BF16 : p.out_kind);
   e.Cout = p.Cout; e.H = p.H; e.W = p.W;
-  const bool heads = MODE == EPI_FULL || MODE == EPI_HEAD;
+  const bool heads = (MODE & 7) == EPI_FULL || (MODE & 7) == EPI_HEAD;
   e.head_na = heads ? p.head_na : 0; e.head_no = heads ? p.head_no : 1;
   keep_in_reg(e.out); keep_in_reg(e.Cout); keep_in_reg(e.H); keep_in_reg(e.W);
-  if (MODE == EPI_FULL || MODE == EPI_TRAIN) keep_in_reg(e.stats);
-  if (MODE == EPI_FULL || MODE == EPI_EVAL) keep_in_reg(e.scale);
-  if (MODE == EPI_FULL || MODE == EPI_EVAL || MODE == EPI_HEAD) keep_in_reg(e.shift);
-  if (MODE == EPI_FULL) keep_in_reg(e.act);
-  if (MODE != EPI_TRAIN && MODE != EPI_HEAD) keep_in_reg(e.addend);
-  if (MODE == EPI_FULL) keep_in_reg(e.out_kind);
+  if ((MODE & 7) == EPI_FULL || (MODE & 7) == EPI_TRAIN) keep_in_reg(e.stats);
+  if ((MODE & 7) == EPI_FULL || (MODE & 7) == EPI_EVAL) keep_in_reg(e.scale);
+  if ((MODE & 7) == EPI_FULL || (MODE & 7) == EPI_EVAL || (MODE & 7) == EPI_HEAD) keep_in_reg(e.shift);
+  if ((MODE & 7) == EPI_FULL) keep_in_reg(e.act);
+  if ((MODE & 7) != EPI_TRAIN && (MODE & 7) != EPI_HEAD && !(MODE & EPI_NOADD)) keep_in_reg(e.addend);
+  if ((MODE & 7) == EPI_FULL) keep_in_reg(e.out_kind);
   if (heads) {
     keep_in_reg(e.head_na); keep_in_reg(e.head_no);
   }
-  e.ss_vec = MODE == EPI_EVAL ? 1 : (p.scale != nullptr && p.shift != nullptr && (p.Cout & 15) == 0 &&
+  e.ss_vec = (MODE & 7) == EPI_EVAL ? 1 : (p.scale != nullptr && p.shift != nullptr && (p.Cout & 15) == 0 &&
               ((reinterpret_cast<uintptr_t>(p.scale) | reinterpret_cast<uintptr_t>(p.shift)) & 15) == 0) ? 1 : 0;
-  if (MODE != EPI_EVAL) keep_in_reg(e.ss_vec);
-  e.affine = (MODE == EPI_TRAIN || MODE == EPI_DGRAD) ? 0
-             : (MODE == EPI_EVAL ? 2 : (MODE == EPI_HEAD ? 1 : (p.scale != nullptr ? 2 : (p.shift != nullptr ? 1 : 0))));
-  if (MODE == EPI_FULL) keep_in_reg(e.affine);
+  if ((MODE & 7) != EPI_EVAL) keep_in_reg(e.ss_vec);
+  e.affine = ((MODE & 7) == EPI_TRAIN || (MODE & 7) == EPI_DGRAD) ? 0
+             : ((MODE & 7) == EPI_EVAL ? 2 : ((MODE & 7) == EPI_HEAD ? 1 : (p.scale != nullptr ? 2 : (p.shift != nullptr ? 1 : 0))));
+  if ((MODE & 7) == EPI_FULL) keep_in_reg(e.affine);
   return e;
 }
 

@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       for (int i = 0; i < p.ngroups; ++i) tma_prefetch_desc(&p.tmO[i]);
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
-  if (MODE != EPI_DGRAD && MODE != EPI_EVAL && MODE != EPI_HEAD && p.stats != nullptr && warp >= 4) {
+  if ((MODE & 7) != EPI_DGRAD && (MODE & 7) != EPI_EVAL && (MODE & 7) != EPI_HEAD && p.stats != nullptr && warp >= 4) {
     for (int i = threadIdx.x - 128; i < 4 * 2 * p.Cout; i += kEpiThreads) s_stats[i] = 0.f;
   }
   tc_fence_before();
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     float* my_stats = s_stats + (size_t)q * 2 * p.Cout;
     // register copies of everything the per-tile loop reads (see keep_in_reg)
     EpiArgs ea = load_epi_args<MODE>(p);
-    if ((MODE == EPI_FULL && p.out_kind == OUT_HEAD_F32) || MODE == EPI_HEAD) ea.head_scratch = s_stats;  // the head has no BN statistics: the region is the transpose scratch
+    if (((MODE & 7) == EPI_FULL && p.out_kind == OUT_HEAD_F32) || (MODE & 7) == EPI_HEAD) ea.head_scratch = s_stats;  // the head has no BN statistics: the region is the transpose scratch
     const TileDec td = load_tile_dec(p);
     int PW = p.PW, PH = p.PH, PN = p.PN, NB = p.NB, BN = p.BLOCK_N;
     int64_t t_on = p.PN * p.os_n, t_oh = p.PH * p.os_h, t_ow = p.PW * p.os_w;  // element strides between tiles
@@ -213,9 +213,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     // TMA-store epilogue: the bf16 tile is staged in shared memory (swizzled box layout) and leaves as one bulk tensor
     // store per 64-channel slab, issued by one thread; per-thread st.global rows (32 sectors per warp instruction) were the
     // top stall of every small-K layer (store back-pressure)
-    int tma_store = MODE != EPI_FULL ? 0 : p.tma_store, x32 = MODE == EPI_FULL ? p.epi_x32 : (X32 ? 1 : 0);  // compile-time in the role instantiations
-    if (MODE == EPI_FULL) keep_in_reg(tma_store);
-    if (MODE == EPI_FULL) keep_in_reg(x32);
+    int tma_store = (MODE & 7) != EPI_FULL ? 0 : p.tma_store, x32 = (MODE & 7) == EPI_FULL ? p.epi_x32 : (X32 ? 1 : 0);  // compile-time in the role instantiations
+    if ((MODE & 7) == EPI_FULL) keep_in_reg(tma_store);
+    if ((MODE & 7) == EPI_FULL) keep_in_reg(x32);
     uint8_t* stage_row = tma_store ? o_stage + (size_t)r * 128 : nullptr;
     const bool issuer = threadIdx.x == 128;
     int it = 0;
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       }
     }
     if (tma_store && issuer) bulk_wait_group0();  // all stores complete before the CTA (and its shared memory) goes away
-    if (MODE != EPI_DGRAD && MODE != EPI_EVAL && MODE != EPI_HEAD && p.stats != nullptr) {
+    if ((MODE & 7) != EPI_DGRAD && (MODE & 7) != EPI_EVAL && (MODE & 7) != EPI_HEAD && p.stats != nullptr) {
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       float* dst = p.stats + (size_t)blockIdx.x * 2 * p.Cout;
       for (int i = threadIdx.x - 128; i < 2 * p.Cout; i += kEpiThreads) {
@@ -589,6 +589,10 @@ int conv_run(const ConvPlan& pl, cudaStream_t st) {
     YB_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<EPI_DGRAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     YB_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<EPI_EVAL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     YB_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<EPI_EVAL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<EPI_DGRAD | EPI_NOADD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<EPI_DGRAD | EPI_NOADD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<EPI_EVAL | EPI_NOADD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<EPI_EVAL | EPI_NOADD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     YB_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<EPI_HEAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     attr_set = true;
   }
@@ -607,10 +611,17 @@ int conv_run(const ConvPlan& pl, cudaStream_t st) {
     mode = EPI_HEAD;
 #define YB_LAUNCH_ROLE(M, X) YB_CHECK_CUDA(launch_pdl(conv_igemm_kernel<M, X>, dim3(pl.grid), dim3(kThreads), pl.smem, st, pl.kp))
   const bool x32 = kq.epi_x32 != 0;
+  if ((mode == EPI_DGRAD || mode == EPI_EVAL) && kq.addend == nullptr) mode |= EPI_NOADD;
   switch (mode) {
     case EPI_TRAIN: if (x32) YB_LAUNCH_ROLE(EPI_TRAIN, true); else YB_LAUNCH_ROLE(EPI_TRAIN, false); break;
     case EPI_DGRAD: if (x32) YB_LAUNCH_ROLE(EPI_DGRAD, true); else YB_LAUNCH_ROLE(EPI_DGRAD, false); break;
     case EPI_EVAL: if (x32) YB_LAUNCH_ROLE(EPI_EVAL, true); else YB_LAUNCH_ROLE(EPI_EVAL, false); break;
+    case EPI_DGRAD | EPI_NOADD:
+      if (x32) YB_LAUNCH_ROLE(EPI_DGRAD | EPI_NOADD, true); else YB_LAUNCH_ROLE(EPI_DGRAD | EPI_NOADD, false);
+      break;
+    case EPI_EVAL | EPI_NOADD:
+      if (x32) YB_LAUNCH_ROLE(EPI_EVAL | EPI_NOADD, true); else YB_LAUNCH_ROLE(EPI_EVAL | EPI_NOADD, false);
+      break;
     case EPI_HEAD: YB_LAUNCH_ROLE(EPI_HEAD, true); break;
     default: YB_LAUNCH_ROLE(EPI_FULL, false); break;
   }

@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
       for (int i = 0; i < p.ngroups; ++i) tma_prefetch_desc(&p.tmO[i]);
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
-  if (MODE != EPI_DGRAD && MODE != EPI_EVAL && p.stats != nullptr && warp >= 4) {
+  if ((MODE & 7) != EPI_DGRAD && (MODE & 7) != EPI_EVAL && p.stats != nullptr && warp >= 4) {
     for (int i = threadIdx.x - 128; i < 4 * 2 * p.Cout; i += kEpiThreads) s_stats[i] = 0.f;
   }
   tc_fence_before();
@@ -272,9 +272,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
     keep_in_reg(BN); keep_in_reg(TWl); keep_in_reg(THl);
     keep_in_reg(os_n); keep_in_reg(os_h); keep_in_reg(os_w); keep_in_reg(as_n); keep_in_reg(as_h); keep_in_reg(as_w);
     const int nchunks = BN / 16;
-    int tma_store = MODE != EPI_FULL ? 0 : p.tma_store, x32 = MODE == EPI_FULL ? p.epi_x32 : (X32 ? 1 : 0);  // compile-time in the role instantiations
-    if (MODE == EPI_FULL) keep_in_reg(tma_store);
-    if (MODE == EPI_FULL) keep_in_reg(x32);
+    int tma_store = (MODE & 7) != EPI_FULL ? 0 : p.tma_store, x32 = (MODE & 7) == EPI_FULL ? p.epi_x32 : (X32 ? 1 : 0);  // compile-time in the role instantiations
+    if ((MODE & 7) == EPI_FULL) keep_in_reg(tma_store);
+    if ((MODE & 7) == EPI_FULL) keep_in_reg(x32);
     const int units = x32 ? nchunks / 2 : nchunks;
     uint8_t* stage_row = o_stage + (size_t)r * 128;
     const bool issuer = threadIdx.x == 128;
@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
       if (lane == 0) mbar_arrive(&tempty_bar[ab]);
     }
     if (tma_store && issuer) bulk_wait_group0();  // all stores complete before the CTA (and its shared memory) goes away
-    if (MODE != EPI_DGRAD && MODE != EPI_EVAL && p.stats != nullptr) {
+    if ((MODE & 7) != EPI_DGRAD && (MODE & 7) != EPI_EVAL && p.stats != nullptr) {
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       float* dst = p.stats + (size_t)blockIdx.x * 2 * p.Cout;
       for (int i = threadIdx.x - 128; i < 2 * p.Cout; i += kEpiThreads) {
@@ -713,6 +713,10 @@ int conv_patch_run(const ConvPlan& pl, cudaStream_t st) {
     YB_CHECK_CUDA(cudaFuncSetAttribute(conv_patch_kernel<EPI_DGRAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     YB_CHECK_CUDA(cudaFuncSetAttribute(conv_patch_kernel<EPI_EVAL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     YB_CHECK_CUDA(cudaFuncSetAttribute(conv_patch_kernel<EPI_EVAL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_patch_kernel<EPI_DGRAD | EPI_NOADD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_patch_kernel<EPI_DGRAD | EPI_NOADD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_patch_kernel<EPI_EVAL | EPI_NOADD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_patch_kernel<EPI_EVAL | EPI_NOADD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     attr_set = true;
   }
   const auto& kq = pl.pp;
@@ -727,10 +731,17 @@ int conv_patch_run(const ConvPlan& pl, cudaStream_t st) {
   }
 #define YB_LAUNCH_ROLE(M, X) YB_CHECK_CUDA(launch_pdl(conv_patch_kernel<M, X>, dim3(pl.grid), dim3(kThreads), pl.smem, st, pl.pp))
   const bool x32 = kq.epi_x32 != 0;
+  if ((mode == EPI_DGRAD || mode == EPI_EVAL) && kq.addend == nullptr) mode |= EPI_NOADD;
   switch (mode) {
     case EPI_TRAIN: if (x32) YB_LAUNCH_ROLE(EPI_TRAIN, true); else YB_LAUNCH_ROLE(EPI_TRAIN, false); break;
     case EPI_DGRAD: if (x32) YB_LAUNCH_ROLE(EPI_DGRAD, true); else YB_LAUNCH_ROLE(EPI_DGRAD, false); break;
     case EPI_EVAL: if (x32) YB_LAUNCH_ROLE(EPI_EVAL, true); else YB_LAUNCH_ROLE(EPI_EVAL, false); break;
+    case EPI_DGRAD | EPI_NOADD:
+      if (x32) YB_LAUNCH_ROLE(EPI_DGRAD | EPI_NOADD, true); else YB_LAUNCH_ROLE(EPI_DGRAD | EPI_NOADD, false);
+      break;
+    case EPI_EVAL | EPI_NOADD:
+      if (x32) YB_LAUNCH_ROLE(EPI_EVAL | EPI_NOADD, true); else YB_LAUNCH_ROLE(EPI_EVAL | EPI_NOADD, false);
+      break;
     default: YB_LAUNCH_ROLE(EPI_FULL, false); break;
   }
 #undef YB_LAUNCH_ROLE
