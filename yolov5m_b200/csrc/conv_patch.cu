@@ -66,6 +66,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
   PTap* s_taps = reinterpret_cast<PTap*>(smem + 512);          // [16] shared copies: indexed constant-bank loads are slow
   PPatch* s_patches = reinterpret_cast<PPatch*>(smem + 640);   // [4] x 28 B
   ConvGroup* s_groups = reinterpret_cast<ConvGroup*>(smem + 768);  // [4] x 24 B
+  STileDec* s_td = reinterpret_cast<STileDec*>(smem + 896);        // tile-decode divisors: 32 B (constant-bank loads of these
+                                                                   // were 12 % of the dgrad epilogue's stall samples)
   uint8_t* o_stage = smem + kBarRegion;  // TMA-store staging: ceil(BLOCK_N / 64) slabs of [128 px][128 B] (conv_igemm.cu)
   uint8_t* a_smem = o_stage + p.stage_bytes;
   uint8_t* b_smem = a_smem + (size_t)p.sa * p.a_stage_bytes;
@@ -79,6 +81,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
   if (threadIdx.x < 16) s_taps[threadIdx.x] = p.taps[threadIdx.x];
   if (threadIdx.x >= 32 && threadIdx.x < 36) s_patches[threadIdx.x - 32] = p.patches[threadIdx.x - 32];
   if (threadIdx.x >= 64 && threadIdx.x < 68) s_groups[threadIdx.x - 64] = p.groups[threadIdx.x - 64];
+  if (threadIdx.x == 96) *s_td = STileDec{p.fd_c, p.fd_w, p.fd_h, p.fd_n};
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.sa; ++i) {
       mbar_init(&afull[i], 1);
@@ -266,7 +269,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
     float* my_stats = s_stats + (size_t)q * 2 * p.Cout;
     // register copies of everything the per-tile loop reads (see keep_in_reg in conv_epilogue.cuh)
     const EpiArgs ea = load_epi_args<MODE>(p);
-    const STileDec td = load_stile_dec(p);
+    const STileDec td = *s_td;
     int BN = p.BLOCK_N, TWl = p.TW, THl = p.TH;
     int64_t os_n = p.os_n, os_h = p.os_h, os_w = p.os_w, as_n = p.as_n, as_h = p.as_h, as_w = p.as_w;
     keep_in_reg(BN); keep_in_reg(TWl); keep_in_reg(THl);
