@@ -231,7 +231,7 @@ static constexpr int kEwThreads = 192;
 static constexpr int kEwUnroll = 4;
 
 template <bool FIXED>
-__global__ void __launch_bounds__(kEwThreads) bn_act_fwd_kernel(const bf16* __restrict__ y, long y_pitch, int H, int W, int C, long npix,
+__global__ void __launch_bounds__(kEwThreads, 4) bn_act_fwd_kernel(const bf16* __restrict__ y, long y_pitch, int H, int W, int C, long npix,
                                   const float* __restrict__ scale, const float* __restrict__ shift,
                                   const bf16* __restrict__ res, long res_pitch, bf16* __restrict__ out, long out_pitch,
                                   bf16* __restrict__ out_up, long up_pitch) {
